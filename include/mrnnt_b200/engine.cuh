@@ -1,0 +1,321 @@
+// Host-side orchestration of the loss-and-gradient hot path: validation, workspace sizing, lazy
+// device set-up, kernel selection and the K1 -> K2 -> K3 launch sequence.
+//
+// This is what GpuRNNTWorkspaceManager / GpuRNNTComputer (include/gpu_workspace_manager.h,
+// include/gpu_rnnt.h) and the flat C ABI (include/mrnnt_c_api.h) are thin shells around.  Compared
+// with the reference's GpuRNNTComputer::cost_and_grad (include/gpu_rnnt.h:27-234, ~21 blocking D2H
+// copies, 8 H2D copies and 2 stream syncs per call) a call here is: 3 kernel launches,
+// one async D2H of B floats and ONE stream synchronisation.  T[] and S[] are fetched to the host
+// once per manager (they are needed for the workspace size, which the API returns on the host).
+//
+// There is no CPU path in this file or anywhere else in the product.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <vector>
+
+#include "../status.h"
+#include "k1_lse.cuh"
+#include "k2_lattice.cuh"
+#include "k3_grad.cuh"
+#include "plan.cuh"
+
+namespace mrnnt {
+
+constexpr int kStreamConsumerWarps = 8;
+
+struct DeviceInfo {
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    bool ok = false;
+};
+
+inline const DeviceInfo &device_info() {
+    // queried once per process per device is not needed: the hot path runs on one device per process
+    static thread_local int cached_dev = -1;
+    static thread_local DeviceInfo info;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        info.ok = false;
+        return info;
+    }
+    if (dev != cached_dev) {
+        info.ok = cudaDeviceGetAttribute(&info.sm_count, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+                  cudaDeviceGetAttribute(&info.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) ==
+                      cudaSuccess;
+        cached_dev = dev;
+    }
+    return info;
+}
+
+// Validation rules of the reference (gpu_workspace_manager.h:232-239, cpu twin :99-107).
+inline RNNTStatus validate_lengths(const int *T_host, const int *S_host, int B, int V, Shape *shape) {
+    if (B <= 0 || V <= 0 || T_host == nullptr || S_host == nullptr) return RNNT_STATUS_INVALID_VALUE;
+    Shape sh;
+    sh.B = B;
+    sh.V = V;
+    for (int b = 0; b < B; ++b) {
+        const int t = T_host[b], s = S_host[b];
+        if (t <= 0 || s < 0 || t < s) return RNNT_STATUS_INVALID_VALUE;
+        sh.T_max = t > sh.T_max ? t : sh.T_max;
+        sh.S_max = s > sh.S_max ? s : sh.S_max;
+        sh.rows += static_cast<int64_t>(t) * (s + 1);
+    }
+    *shape = sh;
+    return RNNT_STATUS_SUCCESS;
+}
+
+class Engine {
+   public:
+    Engine(const float *acts, const int *labels, int B, const int *T_dev, const int *S_dev, int V)
+        : acts_(acts), labels_(labels), T_dev_(T_dev), S_dev_(S_dev), B_(B), V_(V) {}
+
+    Engine(const Engine &) = delete;
+    Engine &operator=(const Engine &) = delete;
+
+    // Supply host copies of the length arrays (skips the one D2H fetch).
+    RNNTStatus set_host_lengths(const int *T_host, const int *S_host) {
+        if (B_ <= 0) return RNNT_STATUS_INVALID_VALUE;
+        T_h_.assign(T_host, T_host + B_);
+        S_h_.assign(S_host, S_host + B_);
+        shape_status_ = validate_lengths(T_h_.data(), S_h_.data(), B_, V_, &shape_);
+        have_shape_ = true;
+        return shape_status_;
+    }
+
+    // One blocking D2H of 2*B ints, the first time the shape is needed.
+    RNNTStatus ensure_shape() {
+        if (have_shape_) return shape_status_;
+        if (B_ <= 0 || V_ <= 0) {
+            have_shape_ = true;
+            return shape_status_ = RNNT_STATUS_INVALID_VALUE;
+        }
+        T_h_.resize(B_);
+        S_h_.resize(B_);
+        if (cudaMemcpy(T_h_.data(), T_dev_, sizeof(int) * B_, cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(S_h_.data(), S_dev_, sizeof(int) * B_, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            have_shape_ = true;
+            return shape_status_ = RNNT_STATUS_MEMOPS_FAILED;
+        }
+        shape_status_ = validate_lengths(T_h_.data(), S_h_.data(), B_, V_, &shape_);
+        have_shape_ = true;
+        return shape_status_;
+    }
+
+    RNNTStatus workspace_size(size_t *bytes) {
+        const RNNTStatus st = ensure_shape();
+        if (st != RNNT_STATUS_SUCCESS) return st;
+        *bytes = workspace_bytes(shape_);
+        return RNNT_STATUS_SUCCESS;
+    }
+
+    // Hand over a caller-owned device buffer of at least workspace_size() bytes.
+    RNNTStatus set_workspace(void *workspace) {
+        const RNNTStatus st = ensure_shape();
+        if (st != RNNT_STATUS_SUCCESS) return st;
+        if (workspace == nullptr) return RNNT_STATUS_INVALID_VALUE;
+        base_ = workspace;
+        ws_ = carve_workspace(workspace, shape_);
+        plan_dirty_ = true;
+        band_dirty_ = true;
+        alignment_ = nullptr;
+        return RNNT_STATUS_SUCCESS;
+    }
+
+    RNNTStatus create_workspace() {
+        size_t bytes = 0;
+        const RNNTStatus st = workspace_size(&bytes);
+        if (st != RNNT_STATUS_SUCCESS) return st;
+        void *p = nullptr;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) return RNNT_STATUS_MEMOPS_FAILED;
+        owned_ = p;
+        return set_workspace(p);
+    }
+
+    void free_workspace() {
+        if (owned_ != nullptr) cudaFree(owned_);
+        owned_ = nullptr;
+        base_ = nullptr;
+    }
+
+    // Restrict the lattice to a band around `alignments` ([B, T_max] device ints).  Takes effect at the
+    // next compute() on that call's stream; `alignments` must stay valid until then.
+    void restrict_to_alignment(const int *alignments, int max_shift, int blank_idx) {
+        alignment_ = alignments;
+        max_shift_ = max_shift;
+        align_blank_ = blank_idx;
+        band_dirty_ = true;
+    }
+
+    const Shape &shape() const { return shape_; }
+    const Workspace &workspace() const { return ws_; }
+    bool has_workspace() const { return base_ != nullptr; }
+    int B() const { return B_; }
+
+    // costs_host: B floats on the host (valid on return).  grads_dev: packed like acts, or nullptr.
+    RNNTStatus compute(int blank, cudaStream_t stream, float *costs_host, float *grads_dev) {
+        if (costs_host == nullptr) return RNNT_STATUS_INVALID_VALUE;
+        RNNTStatus st = ensure_shape();
+        if (st != RNNT_STATUS_SUCCESS) return st;
+        if (base_ == nullptr || blank < 0 || blank >= V_) return RNNT_STATUS_INVALID_VALUE;
+        st = enqueue(blank, stream, grads_dev);
+        if (st != RNNT_STATUS_SUCCESS) return st;
+        if (cudaMemcpyAsync(costs_host, ws_.costs, sizeof(float) * B_, cudaMemcpyDeviceToHost, stream) != cudaSuccess)
+            return RNNT_STATUS_MEMOPS_FAILED;
+        if (cudaStreamSynchronize(stream) != cudaSuccess) return RNNT_STATUS_EXECUTION_FAILED;
+        return RNNT_STATUS_SUCCESS;
+    }
+
+    // Launch everything on `stream` without synchronising; costs stay in workspace().costs.
+    RNNTStatus enqueue(int blank, cudaStream_t stream, float *grads_dev) {
+        const DeviceInfo &dev = device_info();
+        if (!dev.ok) return RNNT_STATUS_EXECUTION_FAILED;
+        RNNTStatus st = setup(stream);
+        if (st != RNNT_STATUS_SUCCESS) return st;
+        st = launch_k1(blank, stream, dev);
+        if (st != RNNT_STATUS_SUCCESS) return st;
+        st = launch_k2(blank, stream, dev, grads_dev != nullptr);
+        if (st != RNNT_STATUS_SUCCESS) return st;
+        if (grads_dev != nullptr) {
+            st = launch_k3(blank, stream, dev, grads_dev);
+            if (st != RNNT_STATUS_SUCCESS) return st;
+        }
+        return RNNT_STATUS_SUCCESS;
+    }
+
+    // Force the generic (non-TMA) streaming kernels; used by the tests to cross-check both variants.
+    void set_force_generic(bool v) { force_generic_ = v; }
+
+   private:
+    static RNNTStatus launched() { return cudaGetLastError() == cudaSuccess ? RNNT_STATUS_SUCCESS : RNNT_STATUS_EXECUTION_FAILED; }
+
+    RNNTStatus setup(cudaStream_t stream) {
+        if (plan_dirty_) {
+            plan_row_start_kernel<<<1, kPlanThreads, 0, stream>>>(T_dev_, S_dev_, B_, ws_.row_start);
+            if (launched() != RNNT_STATUS_SUCCESS) return RNNT_STATUS_EXECUTION_FAILED;
+            plan_dirty_ = false;
+        }
+        if (band_dirty_) {
+            size_t smem = alignment_ != nullptr ? (static_cast<size_t>(shape_.T_max) + 1) * sizeof(int) : 0;
+            if (smem > 48 * 1024) {
+                if (smem > static_cast<size_t>(device_info().max_smem_optin) - 1024) return RNNT_STATUS_INVALID_VALUE;
+                if (cudaFuncSetAttribute(band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)) != cudaSuccess)
+                    return RNNT_STATUS_EXECUTION_FAILED;
+            }
+            band_kernel<<<B_, kBandThreads, smem, stream>>>(T_dev_, S_dev_, shape_.T_max, alignment_, max_shift_,
+                                                            align_blank_, ws_.band);
+            if (launched() != RNNT_STATUS_SUCCESS) return RNNT_STATUS_EXECUTION_FAILED;
+            const int64_t blocks64 = (shape_.rows + 255) / 256;
+            const int blocks = static_cast<int>(blocks64 > 65535 * 8 ? 65535 * 8 : blocks64);
+            rowmeta_kernel<<<blocks, 256, 0, stream>>>(T_dev_, S_dev_, B_, shape_.T_max, shape_.S_max, ws_.row_start,
+                                                       ws_.band, ws_.rowmeta);
+            if (launched() != RNNT_STATUS_SUCCESS) return RNNT_STATUS_EXECUTION_FAILED;
+            band_dirty_ = false;
+        }
+        return RNNT_STATUS_SUCCESS;
+    }
+
+    bool can_stream(const void *p0, const void *p1, size_t extra_per_row, const DeviceInfo &dev, StreamTiling *tl) const {
+        if (force_generic_) return false;
+        if ((reinterpret_cast<uintptr_t>(p0) & 15) || (reinterpret_cast<uintptr_t>(p1) & 15)) return false;
+        if (!stream_tiling(V_, extra_per_row, tl)) return false;
+        return tl->smem_bytes <= static_cast<size_t>(dev.max_smem_optin);
+    }
+
+    int generic_grid(const DeviceInfo &dev) const {
+        const int64_t want = (shape_.rows + kGenericWarps - 1) / kGenericWarps;
+        const int64_t cap = static_cast<int64_t>(dev.sm_count) * 8;
+        return static_cast<int>(want < cap ? (want < 1 ? 1 : want) : cap);
+    }
+
+    RNNTStatus launch_k1(int blank, cudaStream_t stream, const DeviceInfo &dev) {
+        StreamTiling tl;
+        if (can_stream(acts_, acts_, 0, dev, &tl)) {
+            auto kern = k1_lse_tma_kernel<kStreamConsumerWarps>;
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(tl.smem_bytes)) != cudaSuccess)
+                return RNNT_STATUS_EXECUTION_FAILED;
+            kern<<<dev.sm_count, (kStreamConsumerWarps + 1) * kWarp, tl.smem_bytes, stream>>>(
+                acts_, labels_, ws_.rowmeta, ws_.lp, ws_.denom, shape_.rows, V_, blank, tl.G, tl.stages);
+        } else {
+            k1_lse_generic_kernel<<<generic_grid(dev), kGenericWarps * kWarp, 0, stream>>>(
+                acts_, labels_, ws_.rowmeta, ws_.lp, ws_.denom, shape_.rows, V_, blank);
+        }
+        return launched();
+    }
+
+    template <int K>
+    RNNTStatus launch_k2_warp(const K2Args &args, cudaStream_t stream) {
+        auto kern = k2_lattice_kernel<K>;
+        const size_t smem = K2Fifo<K>::kSmemBytes;
+        if (smem > 48 * 1024 &&
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+            return RNNT_STATUS_EXECUTION_FAILED;
+        kern<<<B_, kK2Threads, smem, stream>>>(args, 0);
+        return launched();
+    }
+
+    RNNTStatus launch_k2(int blank, cudaStream_t stream, const DeviceInfo &dev, bool need_beta) {
+        K2Args a;
+        a.T = T_dev_; a.S = S_dev_; a.labels = labels_; a.row_start = ws_.row_start; a.band = ws_.band;
+        a.lp = ws_.lp; a.denom = ws_.denom; a.alpha = ws_.alpha; a.beta = ws_.beta; a.coef = ws_.coef;
+        a.ll_fwd = ws_.ll_fwd; a.ll_bwd = ws_.ll_bwd; a.costs = ws_.costs;
+        a.T_max = shape_.T_max; a.S_max = shape_.S_max; a.V = V_; a.blank = blank;
+        a.need_beta = need_beta ? 1 : 0;
+        const int states = shape_.S_max + 1;
+        if (states <= 32) return launch_k2_warp<1>(a, stream);
+        if (states <= 64) return launch_k2_warp<2>(a, stream);
+        if (states <= 128) return launch_k2_warp<4>(a, stream);
+        if (states <= 256) return launch_k2_warp<8>(a, stream);
+        if (states <= 512) return launch_k2_warp<16>(a, stream);
+        const size_t smem = (static_cast<size_t>(shape_.S_max) + 2) * sizeof(double);
+        if (smem > static_cast<size_t>(dev.max_smem_optin)) return RNNT_STATUS_INVALID_VALUE;
+        if (smem > 48 * 1024 && cudaFuncSetAttribute(k2_lattice_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     static_cast<int>(smem)) != cudaSuccess)
+            return RNNT_STATUS_EXECUTION_FAILED;
+        k2_lattice_wide_kernel<<<B_, kK2Threads, smem, stream>>>(a, 0);
+        return launched();
+    }
+
+    RNNTStatus launch_k3(int blank, cudaStream_t stream, const DeviceInfo &dev, float *grads) {
+        StreamTiling tl;
+        if (can_stream(acts_, grads, sizeof(float4), dev, &tl)) {
+            auto kern = k3_grad_tma_kernel<kStreamConsumerWarps>;
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(tl.smem_bytes)) != cudaSuccess)
+                return RNNT_STATUS_EXECUTION_FAILED;
+            kern<<<dev.sm_count, (kStreamConsumerWarps + 1) * kWarp, tl.smem_bytes, stream>>>(
+                acts_, ws_.coef, grads, shape_.rows, V_, blank, tl.G, tl.stages);
+        } else {
+            k3_grad_generic_kernel<<<generic_grid(dev), kGenericWarps * kWarp, 0, stream>>>(acts_, ws_.coef, grads,
+                                                                                             shape_.rows, V_, blank);
+        }
+        return launched();
+    }
+
+    const float *acts_;
+    const int *labels_;
+    const int *T_dev_;
+    const int *S_dev_;
+    int B_, V_;
+
+    std::vector<int> T_h_, S_h_;
+    Shape shape_;
+    bool have_shape_ = false;
+    RNNTStatus shape_status_ = RNNT_STATUS_UNKNOWN_ERROR;
+
+    void *base_ = nullptr;
+    void *owned_ = nullptr;
+    Workspace ws_;
+    bool plan_dirty_ = true;
+    bool band_dirty_ = true;
+    const int *alignment_ = nullptr;
+    int max_shift_ = 0;
+    int align_blank_ = 0;
+    bool force_generic_ = false;
+};
+
+}  // namespace mrnnt

@@ -1,0 +1,236 @@
+// Workspace layout and the small set-up kernels (row offsets, alignment band, per-row liveness).
+//
+// Replaces the host-side carve-up and the ~20 blocking cudaMemcpy calls of the reference's
+// GpuRNNTWorkspaceManager (include/gpu_workspace_manager.h:228-329, :191-219).  Differences that
+// matter: offsets are 64-bit (the reference's int offsets overflow above 2^31-1 logits),
+// nothing here synchronises the host, and the alignment band is built on the device.
+//
+// Layout of the packed inputs (unchanged from the reference, cpu_workspace_manager.h:46-49,117-135):
+//   acts   [rows, V]   rows = sum_b T_b*(S_b+1); row of (b,t,s) = row_start[b] + t*(S_b+1) + s
+//   labels [B, S_max]  S_max = max_b S_b
+//   alignment [B, T_max], T_max = max_b T_b
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+
+#include "common.cuh"
+
+namespace mrnnt {
+
+// Host-side facts about one batch, derived once from the host copies of T[] and S[].
+struct Shape {
+    int B = 0;
+    int V = 0;
+    int T_max = 0;
+    int S_max = 0;
+    int64_t rows = 0;  // sum_b T_b * (S_b + 1)
+};
+
+// Device arrays carved out of the caller's workspace buffer (all 256-byte aligned).
+struct Workspace {
+    int64_t *row_start = nullptr;  // [B+1]   first row of each utterance
+    int2 *band = nullptr;          // [B*T_max] (min_allowed_s, max_allowed_s) per frame
+    int *rowmeta = nullptr;        // [rows]  >=0: index into labels[], kRowNoLabel, kRowDead
+    double2 *lp = nullptr;         // [rows]  (log p(blank | t,s), log p(label_s | t,s))
+    double *denom = nullptr;       // [rows]  -logsumexp_v acts[row, v]   (reference sign convention)
+    double *alpha = nullptr;       // [rows]  full T x (S+1) grid per utterance, -inf outside the band
+    double *beta = nullptr;        // [rows]
+    float4 *coef = nullptr;        // [rows]  per-row gradient coefficients, see k2_lattice.cuh
+    double *ll_fwd = nullptr;      // [B]     alpha(T-1, S)
+    double *ll_bwd = nullptr;      // [B]     beta(0, 0)  (diagnostic, as in the reference)
+    float *costs = nullptr;        // [B]     -ll_fwd
+};
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Bytes needed for `shape`.  A function of (B, T[], S[]) only, like the reference
+// (gpu_workspace_manager.h:242-247); the value differs (56 B/row + O(B*T_max) instead of 12 B/row).
+inline size_t workspace_bytes(const Shape &sh) {
+    const size_t rows = static_cast<size_t>(sh.rows);
+    const size_t B = static_cast<size_t>(sh.B);
+    size_t n = 256;  // slack to align an arbitrarily aligned base pointer
+    n += align_up((B + 1) * sizeof(int64_t), 256);
+    n += align_up(B * static_cast<size_t>(sh.T_max) * sizeof(int2), 256);
+    n += align_up(rows * sizeof(int), 256);
+    n += align_up(rows * sizeof(double2), 256);
+    n += 3 * align_up(rows * sizeof(double), 256);
+    n += align_up(rows * sizeof(float4), 256);
+    n += 2 * align_up(B * sizeof(double), 256);
+    n += align_up(B * sizeof(float), 256);
+    return n;
+}
+
+inline Workspace carve_workspace(void *base, const Shape &sh) {
+    const size_t rows = static_cast<size_t>(sh.rows);
+    const size_t B = static_cast<size_t>(sh.B);
+    char *p = reinterpret_cast<char *>(align_up(reinterpret_cast<size_t>(base), 256));
+    auto take = [&p](size_t bytes) {
+        char *r = p;
+        p += align_up(bytes, 256);
+        return r;
+    };
+    Workspace w;
+    w.row_start = reinterpret_cast<int64_t *>(take((B + 1) * sizeof(int64_t)));
+    w.band = reinterpret_cast<int2 *>(take(B * static_cast<size_t>(sh.T_max) * sizeof(int2)));
+    w.rowmeta = reinterpret_cast<int *>(take(rows * sizeof(int)));
+    w.lp = reinterpret_cast<double2 *>(take(rows * sizeof(double2)));
+    w.denom = reinterpret_cast<double *>(take(rows * sizeof(double)));
+    w.alpha = reinterpret_cast<double *>(take(rows * sizeof(double)));
+    w.beta = reinterpret_cast<double *>(take(rows * sizeof(double)));
+    w.coef = reinterpret_cast<float4 *>(take(rows * sizeof(float4)));
+    w.ll_fwd = reinterpret_cast<double *>(take(B * sizeof(double)));
+    w.ll_bwd = reinterpret_cast<double *>(take(B * sizeof(double)));
+    w.costs = reinterpret_cast<float *>(take(B * sizeof(float)));
+    return w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// row_start[b] = sum_{b' < b} T_b' * (S_b' + 1)      (one CTA; block-wide exclusive scan, 64-bit)
+// Replaces the host loops + H2D copies at gpu_workspace_manager.h:262-289.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPlanThreads = 1024;
+
+static __global__ void __launch_bounds__(kPlanThreads) plan_row_start_kernel(const int *__restrict__ T,
+                                                                       const int *__restrict__ S, int B,
+                                                                       int64_t *__restrict__ row_start) {
+    __shared__ int64_t warp_tot[kPlanThreads / kWarp];
+    const int tid = threadIdx.x;
+    const int per = (B + kPlanThreads - 1) / kPlanThreads;
+    const int b0 = tid * per;
+    int64_t local = 0;
+    for (int i = 0; i < per; ++i) {
+        const int b = b0 + i;
+        if (b < B) local += static_cast<int64_t>(T[b]) * (S[b] + 1);
+    }
+    // inclusive scan of `local` across the block
+    int64_t incl = local;
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int64_t up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int64_t w = warp_tot[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int64_t up = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += up;
+        }
+        warp_tot[lane] = w;  // inclusive totals of warps 0..lane
+    }
+    __syncthreads();
+    int64_t run = incl - local + (warp > 0 ? warp_tot[warp - 1] : 0);  // exclusive prefix of this thread
+    for (int i = 0; i < per; ++i) {
+        const int b = b0 + i;
+        if (b < B) {
+            row_start[b] = run;
+            run += static_cast<int64_t>(T[b]) * (S[b] + 1);
+            if (b == B - 1) row_start[B] = run;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Alignment band.  Unrestricted: (0, S_b) for every frame (gpu_workspace_manager.h:315-328).
+// Restricted (restrict_to_alignment, gpu_workspace_manager.h:191-219 / cpu twin :207-224):
+//   m[0] = 0, m[t+1] = m[t] + (alignment[b*T_max + t] != blank_idx)
+//   lo[t] = m[max(0, t+1-shift)],  hi[t] = m[min(T_b, t+1+shift)]
+// One CTA per utterance; m[] lives in shared memory ((T_max+1) ints).
+// ---------------------------------------------------------------------------------------------
+constexpr int kBandThreads = 256;
+
+static __global__ void __launch_bounds__(kBandThreads) band_kernel(const int *__restrict__ T, const int *__restrict__ S,
+                                                             int T_max, const int *__restrict__ alignment,
+                                                             int max_shift, int blank_idx, int2 *__restrict__ band) {
+    extern __shared__ int m_sh[];  // [T_b + 1] when alignment != nullptr
+    __shared__ int warp_tot[kBandThreads / kWarp];
+    __shared__ int carry_sh;
+    const int b = blockIdx.x;
+    const int Tb = T[b], Sb = S[b];
+    int2 *band_b = band + static_cast<size_t>(b) * T_max;
+    if (alignment == nullptr) {
+        for (int t = threadIdx.x; t < T_max; t += kBandThreads) band_b[t] = make_int2(0, Sb);
+        return;
+    }
+    const int *al = alignment + static_cast<size_t>(b) * T_max;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        carry_sh = 0;
+        m_sh[0] = 0;
+    }
+    __syncthreads();
+    for (int base = 0; base < Tb; base += kBandThreads) {
+        const int t = base + tid;
+        const int flag = (t < Tb && al[t] != blank_idx) ? 1 : 0;
+        int incl = flag;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        int before = carry_sh;
+        for (int w = 0; w < warp; ++w) before += warp_tot[w];
+        if (t < Tb) m_sh[t + 1] = before + incl;
+        __syncthreads();
+        if (tid == kBandThreads - 1) carry_sh = before + incl;
+        __syncthreads();
+    }
+    const int shift = max_shift < 0 ? 0 : (max_shift > T_max ? T_max : max_shift);
+    for (int t = tid; t < T_max; t += kBandThreads) {
+        if (t < Tb) {
+            const int a = t + 1 - shift;
+            const int c = t + 1 + shift;
+            band_b[t] = make_int2(m_sh[a > 0 ? a : 0], m_sh[c < Tb ? c : Tb]);
+        } else {
+            band_b[t] = make_int2(0, Sb);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// rowmeta[row]: which packed rows can carry probability mass at all.
+// Row (b,t,s) multiplies alpha(t-1, s) everywhere it is used (alpha/beta recursions and the
+// gradient, cpu_rnnt.h:158-166,188-196,220-231), so it is "live" iff alpha(t-1, s) lies inside the
+// lattice:  t == 0: s == 0;  t >= 1: lo[t-1] <= s <= hi[t-1], s <= t, S-s <= T-t
+// (gpu_rnnt_kernel.h:10-32).  Dead rows are never read by the streaming kernels: their gradient
+// is written as zeros (the reference does the same for the geometric part, gpu_rnnt_kernel.h:266-271).
+// Live rows carry the index of their label in labels[] (labels are read at compute time).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int find_utterance(const int64_t *__restrict__ row_start, int B, int64_t row) {
+    int lo = 0, hi = B;  // invariant: row_start[lo] <= row < row_start[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (row_start[mid] <= row) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+static __global__ void __launch_bounds__(256) rowmeta_kernel(const int *__restrict__ T, const int *__restrict__ S, int B,
+                                                       int T_max, int S_max,
+                                                       const int64_t *__restrict__ row_start,
+                                                       const int2 *__restrict__ band, int *__restrict__ rowmeta) {
+    const int64_t rows = row_start[B];
+    for (int64_t row = blockIdx.x * 256ll + threadIdx.x; row < rows; row += 256ll * gridDim.x) {
+        const int b = find_utterance(row_start, B, row);
+        const int Tb = T[b], Sb = S[b];
+        const int local = static_cast<int>(row - row_start[b]);
+        const int t = local / (Sb + 1);
+        const int s = local - t * (Sb + 1);
+        bool live;
+        if (t == 0) {
+            live = (s == 0);
+        } else {
+            const int2 lh = band[static_cast<size_t>(b) * T_max + (t - 1)];
+            live = s >= lh.x && s <= lh.y && s <= t && (Sb - s) <= (Tb - t);
+        }
+        rowmeta[row] = live ? (s < Sb ? b * S_max + s : kRowNoLabel) : kRowDead;
+    }
+}
+
+}  // namespace mrnnt

@@ -1,0 +1,96 @@
+/* Flat C ABI of libmonotonic_rnnt.so (sm_100a).  Plain pointers, ints and sizes only -- this is the
+ * boundary a foreign-function binding (ctypes, cgo, JNI, a C program) links against.  The C++
+ * surface the reference's own bindings compile against (GpuRNNTWorkspaceManager / GpuRNNTComputer /
+ * compute_rnnt_loss) sits on the same engine; see INTEGRATION.md.
+ *
+ * Pointer residency everywhere (reference include/gpu_workspace_manager.h:63-69, gpu_rnnt.h:229):
+ *   DEVICE: acts, labels, T_dev, S_dev, alignments, gradients, workspace        HOST: costs, *_host
+ * Layouts (reference include/cpu_workspace_manager.h:46-49,117-135, pytorch_binding/monotonic_rnnt_op.py:133-140):
+ *   acts       float32 [sum_b T_b*(S_b+1), V], utterances concatenated without padding,
+ *              row of (b,t,s) = row_start(b) + t*(S_b+1) + s
+ *   labels     int32 [B, max_b S_b]          alignments int32 [B, max_b T_b]
+ *   T, S       int32 [B]                     costs float32 [B]      gradients: same shape as acts
+ * All functions return an RNNTStatus (include/status.h).  None of them falls back to the CPU.
+ */
+#ifndef MONOTONIC_RNNT_B200_C_API_H
+#define MONOTONIC_RNNT_B200_C_API_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "status.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mrnnt_handle_st *mrnnt_handle_t;
+
+/* Host-only size query.  Replaces GpuRNNTWorkspaceManager<float>::get_workspace_size
+ * (reference include/gpu_workspace_manager.h:228-254) for callers that hold the lengths on the host.
+ * Same validation: B <= 0, T_b <= 0, S_b < 0 or T_b < S_b -> RNNT_STATUS_INVALID_VALUE. */
+RNNTStatus mrnnt_get_workspace_size(const int *T_host, const int *S_host, int B, int V, size_t *size_bytes);
+
+/* Handle = one GpuRNNTWorkspaceManager<float> (reference include/gpu_workspace_manager.h:33-52).
+ * T_host / S_host may be NULL; the lengths are then fetched from the device once (blocking). */
+RNNTStatus mrnnt_create(mrnnt_handle_t *out, const float *acts, const int *labels, int B, const int *T_dev,
+                        const int *S_dev, int V, const int *T_host, const int *S_host);
+void mrnnt_destroy(mrnnt_handle_t h);
+
+/* gpu_workspace_manager.h:228 (get_workspace_size), :256 (set_workspace), :331-342 (create/free). */
+RNNTStatus mrnnt_workspace_size(mrnnt_handle_t h, size_t *size_bytes);
+RNNTStatus mrnnt_set_workspace(mrnnt_handle_t h, void *workspace);
+RNNTStatus mrnnt_create_workspace(mrnnt_handle_t h);
+void mrnnt_free_workspace(mrnnt_handle_t h);
+
+/* gpu_workspace_manager.h:191-219.  Recorded here, applied on the device by the next compute call on
+ * that call's stream; `alignments` must stay valid until then.  May be called repeatedly. */
+RNNTStatus mrnnt_restrict_to_alignment(mrnnt_handle_t h, const int *alignments, int max_shift, int blank_idx);
+
+/* GpuRNNTComputer<float>::cost_and_grad / cost (reference include/gpu_rnnt.h:27-235) and therefore
+ * compute_rnnt_loss (include/rnnt_entrypoint.h:24-25).  `stream` is a cudaStream_t / CUstream.
+ * gradients == NULL selects cost only.  costs are valid on return (one stream synchronisation). */
+RNNTStatus mrnnt_cost_and_grad(mrnnt_handle_t h, int blank_label, void *stream, float *costs_host, float *gradients);
+
+/* Same work, no host synchronisation: costs stay on the device (mrnnt_device_costs) for callers that
+ * consume them there (e.g. an NCCL all-reduce of the summed cost on the same stream). */
+RNNTStatus mrnnt_enqueue(mrnnt_handle_t h, int blank_label, void *stream, float *gradients);
+const float *mrnnt_device_costs(mrnnt_handle_t h);
+
+/* One-shot convenience: size check + set_workspace + optional restrict_to_alignment + cost_and_grad. */
+RNNTStatus rnnt_loss_grad_gpu(const float *acts, const int *labels, const int *T_dev, const int *S_dev,
+                              const int *T_host, const int *S_host, int B, int V, int blank_label,
+                              const int *alignments_or_null, int max_shift, void *workspace, size_t workspace_bytes,
+                              void *stream, float *costs_host, float *gradients_or_null);
+
+/* ---- test / bench support (not part of the reference's surface) ---------------------------------*/
+enum {
+    MRNNT_OPT_FORCE_GENERIC = 1 /* value != 0: use the generic (non-TMA) streaming kernels */
+};
+RNNTStatus mrnnt_set_option(mrnnt_handle_t h, int option, int value);
+
+enum {
+    MRNNT_DBG_DENOM = 1,    /* double [rows]                                 */
+    MRNNT_DBG_ALPHA = 2,    /* double [rows], -inf outside the band          */
+    MRNNT_DBG_BETA = 3,     /* double [rows]                                 */
+    MRNNT_DBG_LP = 4,       /* double [rows][2] (blank, label)               */
+    MRNNT_DBG_BAND = 5,     /* int32  [B][T_max][2] (min, max allowed s)     */
+    MRNNT_DBG_ROWMETA = 6,  /* int32  [rows]                                 */
+    MRNNT_DBG_LL = 7,       /* double [2][B] (ll_forward, ll_backward)       */
+    MRNNT_DBG_ROWSTART = 8  /* int64  [B+1]                                  */
+};
+/* Blocking copy of an intermediate array to the host (device-synchronises first). */
+RNNTStatus mrnnt_debug_copy(mrnnt_handle_t h, int what, void *dst_host, size_t dst_bytes);
+
+/* Counter-based synthetic logits: x[i] = (splitmix64(seed ^ (index_offset + i)) >> 40) * 2^-24 in [0,1),
+ * the distribution of the reference's genActs (tests/random.cpp:4-20).  Device-side fill. */
+RNNTStatus mrnnt_synth_uniform(float *dst_dev, int64_t n, uint64_t seed, int64_t index_offset, void *stream);
+
+/* Version / build information string (static storage). */
+const char *mrnnt_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* MONOTONIC_RNNT_B200_C_API_H */

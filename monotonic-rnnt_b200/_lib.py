@@ -1,0 +1,92 @@
+"""ctypes binding of libmonotonic_rnnt.so -- the flat C ABI of include/mrnnt_c_api.h.
+
+This is the ONLY way the Python host code reaches the kernels.  There is no Python / CPU fallback:
+if the library is missing, cannot be built or cannot be loaded, importing callers get a loud error.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+from . import build as _build
+
+STATUS_TEXT = {0: "no error", 1: "cuda memcpy or memset failed", 2: "invalid value", 3: "execution failed",
+               4: "unknown error"}
+
+OPT_FORCE_GENERIC = 1
+DBG_DENOM, DBG_ALPHA, DBG_BETA, DBG_LP, DBG_BAND, DBG_ROWMETA, DBG_LL, DBG_ROWSTART = range(1, 9)
+
+# every symbol include/mrnnt_c_api.h and include/rnnt_entrypoint.h declare
+EXPORTED_SYMBOLS = (
+    "compute_rnnt_loss", "mrnnt_get_workspace_size", "mrnnt_create", "mrnnt_destroy", "mrnnt_workspace_size",
+    "mrnnt_set_workspace", "mrnnt_create_workspace", "mrnnt_free_workspace", "mrnnt_restrict_to_alignment",
+    "mrnnt_cost_and_grad", "mrnnt_enqueue", "mrnnt_device_costs", "rnnt_loss_grad_gpu", "mrnnt_set_option",
+    "mrnnt_debug_copy", "mrnnt_synth_uniform", "mrnnt_build_info",
+)
+
+
+class RNNTError(RuntimeError):
+    def __init__(self, status: int, where: str):
+        self.status = int(status)
+        super().__init__(f"{where}: status {status} ({STATUS_TEXT.get(int(status), '?')})")
+
+
+_lib = None
+
+
+def _declare(lib: ctypes.CDLL) -> None:
+    vp, ci, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+    szp = ctypes.POINTER(ctypes.c_size_t)
+    lib.mrnnt_get_workspace_size.argtypes = [vp, vp, ci, ci, szp]
+    lib.mrnnt_create.argtypes = [ctypes.POINTER(vp), vp, vp, ci, vp, vp, ci, vp, vp]
+    lib.mrnnt_destroy.argtypes = [vp]
+    lib.mrnnt_destroy.restype = None
+    lib.mrnnt_workspace_size.argtypes = [vp, szp]
+    lib.mrnnt_set_workspace.argtypes = [vp, vp]
+    lib.mrnnt_create_workspace.argtypes = [vp]
+    lib.mrnnt_free_workspace.argtypes = [vp]
+    lib.mrnnt_free_workspace.restype = None
+    lib.mrnnt_restrict_to_alignment.argtypes = [vp, vp, ci, ci]
+    lib.mrnnt_cost_and_grad.argtypes = [vp, ci, vp, vp, vp]
+    lib.mrnnt_enqueue.argtypes = [vp, ci, vp, vp]
+    lib.mrnnt_device_costs.argtypes = [vp]
+    lib.mrnnt_device_costs.restype = vp
+    lib.rnnt_loss_grad_gpu.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, vp, ci, vp, sz, vp, vp, vp]
+    lib.mrnnt_set_option.argtypes = [vp, ci, ci]
+    lib.mrnnt_debug_copy.argtypes = [vp, ci, vp, sz]
+    lib.mrnnt_synth_uniform.argtypes = [vp, ctypes.c_int64, ctypes.c_uint64, ctypes.c_int64, vp]
+    lib.mrnnt_build_info.argtypes = []
+    lib.mrnnt_build_info.restype = ctypes.c_char_p
+    for name in ("mrnnt_get_workspace_size", "mrnnt_create", "mrnnt_workspace_size", "mrnnt_set_workspace",
+                 "mrnnt_create_workspace", "mrnnt_restrict_to_alignment", "mrnnt_cost_and_grad", "mrnnt_enqueue",
+                 "rnnt_loss_grad_gpu", "mrnnt_set_option", "mrnnt_debug_copy", "mrnnt_synth_uniform"):
+        getattr(lib, name).restype = ci
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    """Load (building first if the sources are newer and nvcc is available) the CUDA library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not _build.up_to_date():
+        try:
+            _build.build()
+        except Exception as exc:  # no nvcc on this machine: a prebuilt library is acceptable, nothing else is
+            if not os.path.exists(path):
+                raise RuntimeError(
+                    f"monotonic-rnnt_b200: {path} is missing and could not be built ({exc}); "
+                    "there is no CPU fallback") from exc
+    lib = ctypes.CDLL(path)
+    _declare(lib)
+    _lib = lib
+    return lib
+
+
+def check(status: int, where: str) -> None:
+    if status != 0:
+        raise RNNTError(status, where)

@@ -1,0 +1,209 @@
+// libmonotonic_rnnt.so -- the one translation unit of the library.
+//
+// Exports (extern "C"):
+//   compute_rnnt_loss           the reference's C entry point (include/rnnt_entrypoint.h:24-25,
+//                               src/rnnt_entrypoint.cpp:16-48), GPU only
+//   mrnnt_* / rnnt_loss_grad_gpu  the flat C ABI declared in include/mrnnt_c_api.h
+// All of them are thin shells over mrnnt::Engine (include/mrnnt_b200/engine.cuh), which is header-only
+// so that the reference's framework bindings can compile the same kernels from `-I include` alone.
+#include <cstdio>
+#include <new>
+
+#include "gpu_rnnt.h"
+#include "gpu_workspace_manager.h"
+#include "mrnnt_c_api.h"
+#include "rnnt_entrypoint.h"
+
+struct mrnnt_handle_st {
+    GpuRNNTWorkspaceManager<float> manager;
+    mrnnt_handle_st(const float *acts, const int *labels, int B, const int *T, const int *S, int V)
+        : manager(acts, labels, B, T, S, V) {}
+};
+
+namespace {
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    uint64_t z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(256) synth_uniform_kernel(float *__restrict__ dst, int64_t n, uint64_t seed,
+                                                             int64_t offset) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t u = splitmix64(seed ^ static_cast<uint64_t>(offset + i));
+        dst[i] = static_cast<float>(u >> 40) * (1.0f / 16777216.0f);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+RNNTStatus compute_rnnt_loss(RNNTWorkspaceManager &workspace_manager, RNNTOptions options, float *costs,
+                             float *gradients) {
+    if (costs == nullptr) return RNNT_STATUS_INVALID_VALUE;
+    if (options.loc == RNNT_CPU) {
+        std::fprintf(stderr, "monotonic-rnnt_b200: CPU execution requested, but this library is GPU-only\n");
+        return RNNT_STATUS_EXECUTION_FAILED;
+    }
+    if (options.loc != RNNT_GPU) return RNNT_STATUS_INVALID_VALUE;
+    auto *manager = dynamic_cast<GpuRNNTWorkspaceManager<float> *>(&workspace_manager);
+    if (manager == nullptr) return RNNT_STATUS_INVALID_VALUE;  // the reference would throw std::bad_cast here
+    GpuRNNTComputer<float> computer(*manager, options.blank_label, options.stream);
+    return gradients != nullptr ? computer.cost_and_grad(costs, gradients) : computer.cost(costs);
+}
+
+RNNTStatus mrnnt_get_workspace_size(const int *T_host, const int *S_host, int B, int V, size_t *size_bytes) {
+    if (size_bytes == nullptr) return RNNT_STATUS_INVALID_VALUE;
+    mrnnt::Shape sh;
+    const RNNTStatus st = mrnnt::validate_lengths(T_host, S_host, B, V, &sh);
+    if (st != RNNT_STATUS_SUCCESS) return st;
+    *size_bytes = mrnnt::workspace_bytes(sh);
+    return RNNT_STATUS_SUCCESS;
+}
+
+RNNTStatus mrnnt_create(mrnnt_handle_t *out, const float *acts, const int *labels, int B, const int *T_dev,
+                        const int *S_dev, int V, const int *T_host, const int *S_host) {
+    if (out == nullptr) return RNNT_STATUS_INVALID_VALUE;
+    *out = nullptr;
+    if (B <= 0 || V <= 0) return RNNT_STATUS_INVALID_VALUE;
+    auto *h = new (std::nothrow) mrnnt_handle_st(acts, labels, B, T_dev, S_dev, V);
+    if (h == nullptr) return RNNT_STATUS_UNKNOWN_ERROR;
+    if (T_host != nullptr && S_host != nullptr) {
+        const RNNTStatus st = h->manager.set_host_lengths(T_host, S_host);
+        if (st != RNNT_STATUS_SUCCESS) {
+            delete h;
+            return st;
+        }
+    }
+    *out = h;
+    return RNNT_STATUS_SUCCESS;
+}
+
+void mrnnt_destroy(mrnnt_handle_t h) { delete h; }
+
+RNNTStatus mrnnt_workspace_size(mrnnt_handle_t h, size_t *size_bytes) {
+    if (h == nullptr || size_bytes == nullptr) return RNNT_STATUS_INVALID_VALUE;
+    return h->manager.get_workspace_size(size_bytes);
+}
+
+RNNTStatus mrnnt_set_workspace(mrnnt_handle_t h, void *workspace) {
+    if (h == nullptr) return RNNT_STATUS_INVALID_VALUE;
+    return h->manager.engine().set_workspace(workspace);
+}
+
+RNNTStatus mrnnt_create_workspace(mrnnt_handle_t h) {
+    if (h == nullptr) return RNNT_STATUS_INVALID_VALUE;
+    return h->manager.create_workspace();
+}
+
+void mrnnt_free_workspace(mrnnt_handle_t h) {
+    if (h != nullptr) h->manager.free_workspace();
+}
+
+RNNTStatus mrnnt_restrict_to_alignment(mrnnt_handle_t h, const int *alignments, int max_shift, int blank_idx) {
+    if (h == nullptr || alignments == nullptr) return RNNT_STATUS_INVALID_VALUE;
+    h->manager.restrict_to_alignment(alignments, max_shift, blank_idx);
+    return RNNT_STATUS_SUCCESS;
+}
+
+RNNTStatus mrnnt_cost_and_grad(mrnnt_handle_t h, int blank_label, void *stream, float *costs_host, float *gradients) {
+    if (h == nullptr) return RNNT_STATUS_INVALID_VALUE;
+    return h->manager.engine().compute(blank_label, static_cast<cudaStream_t>(stream), costs_host, gradients);
+}
+
+RNNTStatus mrnnt_enqueue(mrnnt_handle_t h, int blank_label, void *stream, float *gradients) {
+    if (h == nullptr) return RNNT_STATUS_INVALID_VALUE;
+    mrnnt::Engine &e = h->manager.engine();
+    const RNNTStatus st = e.ensure_shape();
+    if (st != RNNT_STATUS_SUCCESS) return st;
+    if (!e.has_workspace() || blank_label < 0 || blank_label >= e.shape().V) return RNNT_STATUS_INVALID_VALUE;
+    return e.enqueue(blank_label, static_cast<cudaStream_t>(stream), gradients);
+}
+
+const float *mrnnt_device_costs(mrnnt_handle_t h) {
+    return (h != nullptr && h->manager.engine().has_workspace()) ? h->manager.engine().workspace().costs : nullptr;
+}
+
+RNNTStatus rnnt_loss_grad_gpu(const float *acts, const int *labels, const int *T_dev, const int *S_dev,
+                              const int *T_host, const int *S_host, int B, int V, int blank_label,
+                              const int *alignments_or_null, int max_shift, void *workspace, size_t workspace_bytes,
+                              void *stream, float *costs_host, float *gradients_or_null) {
+    if (costs_host == nullptr || workspace == nullptr || B <= 0 || V <= 0) return RNNT_STATUS_INVALID_VALUE;
+    GpuRNNTWorkspaceManager<float> manager(acts, labels, B, T_dev, S_dev, V);
+    if (T_host != nullptr && S_host != nullptr) {
+        const RNNTStatus st = manager.set_host_lengths(T_host, S_host);
+        if (st != RNNT_STATUS_SUCCESS) return st;
+    }
+    size_t need = 0;
+    RNNTStatus st = manager.get_workspace_size(&need);
+    if (st != RNNT_STATUS_SUCCESS) return st;
+    if (workspace_bytes < need) return RNNT_STATUS_INVALID_VALUE;
+    st = manager.engine().set_workspace(workspace);
+    if (st != RNNT_STATUS_SUCCESS) return st;
+    if (alignments_or_null != nullptr) manager.restrict_to_alignment(alignments_or_null, max_shift, blank_label);
+    return manager.engine().compute(blank_label, static_cast<cudaStream_t>(stream), costs_host, gradients_or_null);
+}
+
+RNNTStatus mrnnt_set_option(mrnnt_handle_t h, int option, int value) {
+    if (h == nullptr) return RNNT_STATUS_INVALID_VALUE;
+    switch (option) {
+        case MRNNT_OPT_FORCE_GENERIC:
+            h->manager.engine().set_force_generic(value != 0);
+            return RNNT_STATUS_SUCCESS;
+        default:
+            return RNNT_STATUS_INVALID_VALUE;
+    }
+}
+
+RNNTStatus mrnnt_debug_copy(mrnnt_handle_t h, int what, void *dst_host, size_t dst_bytes) {
+    if (h == nullptr || dst_host == nullptr) return RNNT_STATUS_INVALID_VALUE;
+    mrnnt::Engine &e = h->manager.engine();
+    if (!e.has_workspace()) return RNNT_STATUS_INVALID_VALUE;
+    const mrnnt::Shape &sh = e.shape();
+    const mrnnt::Workspace &w = e.workspace();
+    const size_t rows = static_cast<size_t>(sh.rows), B = static_cast<size_t>(sh.B);
+    const void *src = nullptr;
+    size_t bytes = 0;
+    switch (what) {
+        case MRNNT_DBG_DENOM: src = w.denom; bytes = rows * sizeof(double); break;
+        case MRNNT_DBG_ALPHA: src = w.alpha; bytes = rows * sizeof(double); break;
+        case MRNNT_DBG_BETA: src = w.beta; bytes = rows * sizeof(double); break;
+        case MRNNT_DBG_LP: src = w.lp; bytes = rows * sizeof(double2); break;
+        case MRNNT_DBG_BAND: src = w.band; bytes = B * static_cast<size_t>(sh.T_max) * sizeof(int2); break;
+        case MRNNT_DBG_ROWMETA: src = w.rowmeta; bytes = rows * sizeof(int); break;
+        case MRNNT_DBG_ROWSTART: src = w.row_start; bytes = (B + 1) * sizeof(int64_t); break;
+        case MRNNT_DBG_LL: {
+            if (dst_bytes < 2 * B * sizeof(double)) return RNNT_STATUS_INVALID_VALUE;
+            if (cudaDeviceSynchronize() != cudaSuccess) return RNNT_STATUS_EXECUTION_FAILED;
+            char *d = static_cast<char *>(dst_host);
+            if (cudaMemcpy(d, w.ll_fwd, B * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess ||
+                cudaMemcpy(d + B * sizeof(double), w.ll_bwd, B * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess)
+                return RNNT_STATUS_MEMOPS_FAILED;
+            return RNNT_STATUS_SUCCESS;
+        }
+        default: return RNNT_STATUS_INVALID_VALUE;
+    }
+    if (dst_bytes < bytes) return RNNT_STATUS_INVALID_VALUE;
+    if (cudaDeviceSynchronize() != cudaSuccess) return RNNT_STATUS_EXECUTION_FAILED;
+    if (cudaMemcpy(dst_host, src, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return RNNT_STATUS_MEMOPS_FAILED;
+    return RNNT_STATUS_SUCCESS;
+}
+
+RNNTStatus mrnnt_synth_uniform(float *dst_dev, int64_t n, uint64_t seed, int64_t index_offset, void *stream) {
+    if (dst_dev == nullptr || n < 0) return RNNT_STATUS_INVALID_VALUE;
+    if (n == 0) return RNNT_STATUS_SUCCESS;
+    const int64_t want = (n + 255) / 256;
+    const int blocks = static_cast<int>(want < 148 * 16 ? want : 148 * 16);
+    synth_uniform_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(dst_dev, n, seed, index_offset);
+    return cudaGetLastError() == cudaSuccess ? RNNT_STATUS_SUCCESS : RNNT_STATUS_EXECUTION_FAILED;
+}
+
+const char *mrnnt_build_info(void) {
+    return "monotonic-rnnt_b200 (sm_100a; K1 lse+gather / K2 lattice / K3 grad; no CPU fallback) built " __DATE__;
+}
+
+}  // extern "C"

@@ -1,0 +1,220 @@
+"""Host-side mirror of the reference's PyTorch operator interface for the loss-and-gradient path.
+
+Same names, argument meaning and error behaviour as pytorch_binding/monotonic_rnnt_op.py
+(MonotonicRNNTFunction :19-118, monotonic_rnnt_loss :121-163, MonotonicRNNTLoss :166-217), but the
+work goes through the flat C ABI of libmonotonic_rnnt.so (ctypes) instead of a JIT-built pybind11
+module.  PyTorch is used for device memory, streams and autograd plumbing only.
+
+Differences, all on the host side of the boundary:
+  * CUDA tensors only.  CPU tensors raise: this product has no CPU path.
+  * gradients are allocated with ``empty_like`` -- the kernels write every element exactly once
+    (the reference allocates ``zeros_like``, monotonic_rnnt_op.py:32-36: one extra pass over N floats).
+  * costs never visit the host in the autograd path (the reference copies them D2H and back,
+    monotonic_rnnt_op.py:37,90).
+  * ``MonotonicRNNTLoss`` works (the reference module passes kwargs to ``Function.apply`` and reads an
+    undefined ``self.blank``, monotonic_rnnt_op.py:207-215).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _check_inputs(acts, labels, input_lengths, label_lengths) -> None:
+    if not acts.is_cuda:
+        raise RuntimeError("monotonic-rnnt_b200 is GPU-only: acts must be a CUDA tensor (no CPU fallback)")
+    for name, t in (("labels", labels), ("input_lengths", input_lengths), ("label_lengths", label_lengths)):
+        if not t.is_cuda:
+            raise RuntimeError(f"{name} must be a CUDA tensor")  # monotonic_rnnt.cu:85-88
+        if t.dtype != torch.int32:
+            raise TypeError(f"{name} must be int32")             # data_ptr<int>() in monotonic_rnnt.cu:99-101
+    if acts.dtype != torch.float32:
+        raise TypeError("acts must be float32")                  # monotonic_rnnt.cu:84
+    if acts.dim() != 2:
+        raise ValueError("acts must be the packed 2-D tensor [sum_b T_b*(S_b+1), V]")
+    if not (acts.is_contiguous() and labels.is_contiguous() and input_lengths.is_contiguous()
+            and label_lengths.is_contiguous()):
+        raise ValueError("inputs must be contiguous")
+
+
+def workspace_size(input_lengths_host, label_lengths_host, V: int) -> int:
+    """Bytes of device workspace for a batch (host-only query; validates the lengths)."""
+    T = np.ascontiguousarray(np.asarray(input_lengths_host, dtype=np.int32))
+    S = np.ascontiguousarray(np.asarray(label_lengths_host, dtype=np.int32))
+    out = ctypes.c_size_t(0)
+    st = _lib.load().mrnnt_get_workspace_size(T.ctypes.data, S.ctypes.data, int(T.shape[0]), int(V), ctypes.byref(out))
+    _lib.check(st, "mrnnt_get_workspace_size")
+    return int(out.value)
+
+
+class LossHandle:
+    """One bound batch = one ``GpuRNNTWorkspaceManager<float>`` plus its workspace.
+
+    Mirrors how the reference bindings drive the C++ classes (pytorch_binding/monotonic_rnnt.cu:99-111):
+    construct on (acts, labels, B, T, S, V), size and attach the workspace, optionally
+    ``restrict_to_alignment``, then ``cost_and_grad``.  Reusable across calls on the same tensors.
+    """
+
+    def __init__(self, acts: torch.Tensor, labels: torch.Tensor, input_lengths: torch.Tensor,
+                 label_lengths: torch.Tensor, lengths_host: Optional[Tuple] = None):
+        _check_inputs(acts, labels, input_lengths, label_lengths)
+        self._lib = _lib.load()
+        self.acts, self.labels = acts, labels
+        self.input_lengths, self.label_lengths = input_lengths, label_lengths
+        self.B = int(input_lengths.shape[0])
+        self.V = int(acts.shape[1])
+        self._alignment = None
+        if label_lengths.shape[0] != self.B or labels.shape[0] != self.B:
+            raise ValueError("labels / input_lengths / label_lengths disagree on the batch size")
+        th = sh = None
+        if lengths_host is not None:
+            self._T_h = np.ascontiguousarray(np.asarray(lengths_host[0], dtype=np.int32))
+            self._S_h = np.ascontiguousarray(np.asarray(lengths_host[1], dtype=np.int32))
+            th, sh = self._T_h.ctypes.data, self._S_h.ctypes.data
+        h = ctypes.c_void_p()
+        with torch.cuda.device(acts.device):
+            st = self._lib.mrnnt_create(ctypes.byref(h), acts.data_ptr(), labels.data_ptr(), self.B,
+                                        input_lengths.data_ptr(), label_lengths.data_ptr(), self.V, th, sh)
+            _lib.check(st, "mrnnt_create")
+            self._h = h
+            size = ctypes.c_size_t(0)
+            _lib.check(self._lib.mrnnt_workspace_size(self._h, ctypes.byref(size)), "mrnnt_workspace_size")
+            self.workspace_bytes = int(size.value)
+            # caller-owned workspace, as the TensorFlow op does with allocate_temp (monotonic_rnnt_op.cu:117-123)
+            self.workspace = torch.empty(self.workspace_bytes, dtype=torch.uint8, device=acts.device)
+            _lib.check(self._lib.mrnnt_set_workspace(self._h, self.workspace.data_ptr()), "mrnnt_set_workspace")
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.mrnnt_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, option: int, value: int) -> None:
+        _lib.check(self._lib.mrnnt_set_option(self._h, option, value), "mrnnt_set_option")
+
+    def restrict_to_alignment(self, alignment: torch.Tensor, max_shift: int, blank_idx: int) -> None:
+        if not alignment.is_cuda or alignment.dtype != torch.int32 or not alignment.is_contiguous():
+            raise TypeError("alignment must be a contiguous CUDA int32 tensor [B, T_max]")
+        self._alignment = alignment  # keep alive until the next compute call consumes it
+        _lib.check(self._lib.mrnnt_restrict_to_alignment(self._h, alignment.data_ptr(), int(max_shift), int(blank_idx)),
+                   "mrnnt_restrict_to_alignment")
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.acts.device).cuda_stream
+
+    def cost_and_grad(self, blank_label: int = 0, grads: Optional[torch.Tensor] = None,
+                      costs_host: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """GpuRNNTComputer::cost_and_grad: costs land on the HOST, valid on return (one stream sync)."""
+        if costs_host is None:
+            costs_host = torch.empty(self.B, dtype=torch.float32, device="cpu")
+        assert costs_host.device.type == "cpu" and costs_host.dtype == torch.float32 and costs_host.numel() == self.B
+        gptr = None
+        if grads is not None:
+            assert grads.is_cuda and grads.dtype == torch.float32 and grads.is_contiguous()
+            assert grads.numel() == self.acts.numel()
+            gptr = grads.data_ptr()
+        with torch.cuda.device(self.acts.device):
+            st = self._lib.mrnnt_cost_and_grad(self._h, int(blank_label), self._stream(), costs_host.data_ptr(), gptr)
+        _lib.check(st, "mrnnt_cost_and_grad")
+        return costs_host
+
+    def cost(self, blank_label: int = 0, costs_host: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return self.cost_and_grad(blank_label, None, costs_host)
+
+    def enqueue(self, blank_label: int = 0, grads: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Launch without synchronising the host; returns a device VIEW of the costs (valid in stream order)."""
+        gptr = grads.data_ptr() if grads is not None else None
+        with torch.cuda.device(self.acts.device):
+            st = self._lib.mrnnt_enqueue(self._h, int(blank_label), self._stream(), gptr)
+        _lib.check(st, "mrnnt_enqueue")
+        return self.device_costs()
+
+    def device_costs(self) -> torch.Tensor:
+        ptr = self._lib.mrnnt_device_costs(self._h)
+        off = int(ptr) - self.workspace.data_ptr()
+        assert 0 <= off <= self.workspace_bytes - 4 * self.B
+        return self.workspace[off:off + 4 * self.B].view(torch.float32)
+
+    def debug(self, what: int) -> np.ndarray:
+        """Intermediate arrays for kernel-level parity tests (blocking)."""
+        T = self.input_lengths.cpu().numpy().astype(np.int64)
+        S = self.label_lengths.cpu().numpy().astype(np.int64)
+        rows = int((T * (S + 1)).sum())
+        shapes = {
+            _lib.DBG_DENOM: (np.float64, (rows,)), _lib.DBG_ALPHA: (np.float64, (rows,)),
+            _lib.DBG_BETA: (np.float64, (rows,)), _lib.DBG_LP: (np.float64, (rows, 2)),
+            _lib.DBG_BAND: (np.int32, (self.B, int(T.max()), 2)), _lib.DBG_ROWMETA: (np.int32, (rows,)),
+            _lib.DBG_LL: (np.float64, (2, self.B)), _lib.DBG_ROWSTART: (np.int64, (self.B + 1,)),
+        }
+        dt, shape = shapes[what]
+        out = np.empty(shape, dtype=dt)
+        with torch.cuda.device(self.acts.device):
+            _lib.check(self._lib.mrnnt_debug_copy(self._h, what, out.ctypes.data, out.nbytes), "mrnnt_debug_copy")
+        return out
+
+
+class MonotonicRNNTFunction(torch.autograd.Function):
+    """Same call signature as the reference's autograd function (monotonic_rnnt_op.py:19-118)."""
+
+    @staticmethod
+    def forward(ctx, acts, labels, input_lengths, label_lengths, alignment=None, max_distance_from_alignment=0,
+                blank_label=0):
+        handle = LossHandle(acts, labels, input_lengths, label_lengths)
+        if alignment is not None:
+            handle.restrict_to_alignment(alignment, max_distance_from_alignment, blank_label)
+        grads = torch.empty_like(acts) if acts.requires_grad else None
+        costs = handle.enqueue(blank_label, grads).clone()
+        # the workspace and alignment must outlive the kernels that are still in flight on this stream
+        handle.workspace.record_stream(torch.cuda.current_stream(acts.device))
+        handle.close()
+        if grads is None:
+            grads = torch.zeros(0, dtype=acts.dtype, device=acts.device)
+        ctx.save_for_backward(grads, input_lengths, label_lengths)
+        return costs
+
+    @staticmethod
+    def backward(ctx, grad_outputs):
+        # every logit of utterance b receives grads[i] * grad_outputs[b] (monotonic_rnnt_op.py:97-118)
+        grads, input_lengths, label_lengths = ctx.saved_tensors
+        repeats = (input_lengths * (label_lengths + 1)).to(torch.int64)
+        scale = grad_outputs.to(grads.dtype).repeat_interleave(repeats, output_size=grads.shape[0]).unsqueeze(1)
+        return grads * scale, None, None, None, None, None, None
+
+
+def monotonic_rnnt_loss(acts, labels, input_lengths, label_lengths, alignment: Optional[torch.Tensor] = None,
+                        max_distance_from_alignment: int = 0, blank_label: int = 0) -> torch.Tensor:
+    """Monotonic RNN-T loss per utterance (negative log-likelihood), softmax applied internally.
+
+    Arguments as in the reference (monotonic_rnnt_op.py:121-152): ``acts`` packed
+    [sum_b T_b*(S_b+1), V] float32, ``labels`` [B, max_b S_b] int32, ``input_lengths`` / ``label_lengths``
+    [B] int32, optional ``alignment`` [B, max_b T_b] int32 with ``max_distance_from_alignment``.
+    Returns a float32 tensor [B] on ``acts.device``.
+    """
+    result = MonotonicRNNTFunction.apply(acts, labels, input_lengths, label_lengths, alignment,
+                                         max_distance_from_alignment, blank_label)
+    assert result is not None
+    return result
+
+
+class MonotonicRNNTLoss(torch.nn.Module):
+    """Module form (reference monotonic_rnnt_op.py:166-217)."""
+
+    def __init__(self, blank_label: int = 0) -> None:
+        super().__init__()
+        self.blank_label = blank_label
+
+    def forward(self, acts, labels, input_lengths, label_lengths, alignment: Optional[torch.Tensor] = None,
+                max_distance_from_alignment: int = 0) -> torch.Tensor:
+        return monotonic_rnnt_loss(acts, labels, input_lengths, label_lengths, alignment,
+                                   max_distance_from_alignment, self.blank_label)

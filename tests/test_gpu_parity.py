@@ -1,0 +1,223 @@
+"""-m gpu: the CUDA path (through the flat C ABI) against the oracle and the reference's golden outputs.
+
+Tolerances (BASELINE.json north_star): per-utterance costs within 1e-5 relative, gradients within 1e-5
+absolute, lengths / bands / label indexing bit-exact.  The gradient tolerance is applied against the
+double-precision reference (`grads_f64`, CpuRNNTComputer<double>); against the float reference it holds on
+the small fixtures and is bounded by that reference's own rounding floor on the large shapes.
+"""
+import numpy as np
+import pytest
+import torch
+
+import fixtures
+import golden_io
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+COST_RTOL = 1e-5
+GRAD_ATOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def gu():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import gpu_util
+    return gpu_util
+
+
+def _oracle(case, precision):
+    return oracle.run(case.acts, case.labels, case.T, case.S, case.V, blank=case.blank, alignment=case.alignment,
+                      max_shift=case.max_shift, precision=precision, want_lattice=True)
+
+
+def _check_costs(got, ref):
+    ref = np.asarray(ref, dtype=np.float64)
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(got), fin)
+    np.testing.assert_allclose(got[fin], ref[fin], rtol=COST_RTOL, atol=0)
+    assert np.all(got[~fin] == ref[~fin])
+
+
+@pytest.mark.parametrize("generic", [False, True], ids=["stream", "generic"])
+@pytest.mark.parametrize("name", golden_io.names())
+def test_golden(gu, name, generic):
+    case, ref = golden_io.load(name)
+    r = gu.run_case(case, force_generic=generic)
+    _check_costs(r.costs, ref["costs_f32"])
+    _check_costs(r.costs, ref["costs_f64"])
+    assert not np.isnan(r.grads).any(), "an element of grads was not written"
+    assert np.abs(r.grads - ref["grads_f64"]).max() <= GRAD_ATOL
+    assert np.abs(r.grads - ref["grads_f32"]).max() <= GRAD_ATOL + np.abs(ref["grads_f32"] - ref["grads_f64"]).max()
+    if case.expect_costs is not None:
+        assert np.all(np.abs(r.costs - case.expect_costs) < 1e-4)      # the reference tests' own tolerance
+    # cost() (gradients == NULL) gives the same costs (bwd_test, tests/test_gpu.cu)
+    c = gu.run_case(case, want_grads=False, force_generic=generic)
+    assert np.array_equal(c.costs, r.costs)
+
+
+def test_readme_grads_two_decimals(gu):
+    r = gu.run_case(fixtures.readme_case())
+    assert np.all(np.abs(r.grads.ravel() - fixtures.README_GRADS_2DP) < 1e-2)      # tests/test_gpu.cu:247
+
+
+@pytest.mark.parametrize("name", ["rand_v17_shift1", "rand_v32", "rand_edges", "rand_wide_shift3", "infnan"])
+def test_intermediates(gu, name):
+    """K1 (denominators, gathered log-probs), the band, row liveness and K2 (alpha, beta) one by one."""
+    from monotonic_rnnt_b200 import _lib
+    case, _ = golden_io.load(name)
+    o = _oracle(case, "f64_from_f32")
+    r = gu.run_case(case, keep_handle=True)
+    h = r.handle
+    T, S = case.T.astype(np.int64), case.S.astype(np.int64)
+    row_start = np.concatenate([[0], np.cumsum(T * (S + 1))])
+    assert np.array_equal(h.debug(_lib.DBG_ROWSTART), row_start)                       # bit-exact offsets
+    # band: restatement of cpu_workspace_manager.h:207-224
+    band = h.debug(_lib.DBG_BAND)
+    for b in range(case.B):
+        lo = np.zeros(T[b], np.int32); hi = np.full(T[b], S[b], np.int32)
+        if case.alignment is not None:
+            m = np.concatenate([[0], np.cumsum(case.alignment[b, :T[b]] != case.blank)])
+            for t in range(T[b]):
+                lo[t] = m[max(0, t + 1 - case.max_shift)]
+                hi[t] = m[min(T[b], t + 1 + case.max_shift)]
+        assert np.array_equal(band[b, :T[b], 0], lo) and np.array_equal(band[b, :T[b], 1], hi)
+    meta = h.debug(_lib.DBG_ROWMETA)
+    live = meta != -2
+    denom, alpha, beta, lp = (h.debug(w) for w in (_lib.DBG_DENOM, _lib.DBG_ALPHA, _lib.DBG_BETA, _lib.DBG_LP))
+    np.testing.assert_allclose(denom[live], o.denom[live], rtol=0, atol=5e-7)
+    # a row is dead exactly when alpha(t-1, s) lies outside the lattice -> its gradient row is zero
+    assert np.all(o.grads[~live] == 0.0)
+    S_max = max(int(S.max()), 1)
+    acts = case.acts.reshape(case.rows, case.V).astype(np.float64)
+    for b in range(case.B):
+        for i in range(int(row_start[b]), int(row_start[b + 1])):
+            if not live[i]:
+                continue
+            assert abs(lp[i, 0] - (acts[i, case.blank] + o.denom[i])) < 5e-7
+            s = (i - row_start[b]) % (S[b] + 1)
+            if s < S[b]:
+                assert meta[i] == b * S_max + s                                           # label indexing bit-exact
+                assert abs(lp[i, 1] - (acts[i, case.labels[b, s]] + o.denom[i])) < 5e-7
+            else:
+                assert meta[i] == -1
+    for got, ref in ((alpha, o.alphas), (beta, o.betas)):
+        assert np.array_equal(np.isneginf(got), np.isneginf(ref))                        # same band, cell for cell
+        fin = np.isfinite(ref)
+        np.testing.assert_allclose(got[fin], ref[fin], rtol=0, atol=2e-5)
+    ll = h.debug(_lib.DBG_LL)
+    np.testing.assert_allclose(ll[0], -o.costs, rtol=1e-7)
+    np.testing.assert_allclose(ll[1], o.ll_backward, rtol=1e-7)
+    h.close()
+
+
+SHAPES = [
+    # name, B, V, T_range, S_range, dist
+    ("v4_tiny_rows", 6, 4, (2, 30), (0, 10), "normal3"),
+    ("v8", 5, 8, (5, 40), (1, 20), "uniform"),
+    ("v64_g32", 7, 64, (10, 60), (3, 30), "normal3"),
+    ("v1000", 4, 1000, (30, 60), (5, 20), "uniform"),
+    ("v1000_peaky", 3, 1000, (30, 60), (5, 20), "normal3"),
+    ("v1022_unaligned", 3, 1022, (20, 30), (4, 9), "uniform"),
+    ("v5000_g1", 2, 5000, (20, 30), (4, 9), "uniform"),
+    ("v16384_3stage", 1, 16384, (12, 16), (3, 5), "uniform"),
+    ("v20000_too_big_for_ring", 1, 20000, (10, 12), (3, 4), "uniform"),
+    ("s_gt_32", 3, 16, (70, 90), (33, 60), "normal3"),
+    ("s_gt_64", 2, 12, (150, 170), (70, 120), "uniform"),
+    ("s_gt_128", 2, 8, (300, 310), (130, 250), "uniform"),
+    ("s_gt_256", 1, 8, (530, 540), (260, 500), "uniform"),
+    ("s_gt_512_wide_kernel", 1, 8, (620, 640), (520, 600), "uniform"),
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: s[0])
+@pytest.mark.parametrize("restricted", [False, True], ids=["free", "aligned"])
+def test_random_shapes(gu, shape, restricted):
+    name, B, V, tr, sr, dist = shape
+    case = fixtures.random_case(name, 1000 + len(name), B=B, V=V, T_range=tr, S_range=sr, dist=dist)
+    if restricted:
+        al = fixtures.random_alignment(np.random.default_rng(7), case.T, case.S, case.labels)
+        case = case.with_alignment(al, 2)
+    o64 = _oracle(case, "f64_from_f32")
+    r = gu.run_case(case)
+    _check_costs(r.costs, o64.costs)
+    assert not np.isnan(r.grads).any()
+    assert np.abs(r.grads - o64.grads).max() <= GRAD_ATOL
+    # the generic kernels agree with the streaming ones to rounding
+    g = gu.run_case(case, force_generic=True)
+    _check_costs(g.costs, o64.costs)
+    assert np.abs(g.grads - o64.grads).max() <= GRAD_ATOL
+
+
+def test_device_lengths_fetch_and_repeated_restrict(gu):
+    """One manager reused across restrict_to_alignment + cost calls (tests/test_cpu.cpp:412-430), lengths
+    fetched from the device (no host copies given)."""
+    base = fixtures.readme_case()
+    import gpu_util
+    acts = gpu_util.to_dev(base.acts, torch.float32); labels = gpu_util.to_dev(base.labels, torch.int32)
+    T = gpu_util.to_dev(base.T, torch.int32); S = gpu_util.to_dev(base.S, torch.int32)
+    import monotonic_rnnt_b200 as mr
+    h = mr.LossHandle(acts, labels, T, S)
+    al = gpu_util.to_dev(np.array([[0, 1, 0, 2]], np.int32), torch.int32)
+    assert abs(h.cost(0).item() + np.log(0.363)) < 1e-4
+    for shift, p in ((2, 0.363), (0, 0.072), (1, 0.2958)):
+        h.restrict_to_alignment(al, shift, 0)
+        assert abs(h.cost(0).item() + np.log(p)) < 1e-4
+    h.close()
+
+
+def test_infeasible_alignment_gives_inf_cost(gu):
+    """Alignment with the wrong number of labels: terminal state outside the band -> cost = +inf
+    (SURVEY A.4).  Other utterances of the batch are unaffected."""
+    base = golden_io.load("align_mb_shift0")[0]
+    al = base.alignment.copy()
+    al[0] = [0, 1, 0, 0]          # only one label emitted for S=2
+    case = base.with_alignment(al, 0)
+    o = _oracle(case, "f64_from_f32")
+    r = gu.run_case(case)
+    assert np.isposinf(o.costs[0]) and np.isposinf(r.costs[0])
+    assert abs(r.costs[1] - o.costs[1]) < 1e-5
+    rows0 = int(case.T[0] * (case.S[0] + 1))
+    assert np.abs(r.grads[rows0:] - o.grads[rows0:]).max() <= GRAD_ATOL
+    assert not np.isfinite(r.grads[:rows0]).all()     # as in the reference: no finite gradient exists
+
+
+def test_validation_and_errors(gu):
+    import monotonic_rnnt_b200 as mr
+    c = fixtures.readme_case()
+    import gpu_util
+    acts = gpu_util.to_dev(c.acts, torch.float32); labels = gpu_util.to_dev(c.labels, torch.int32)
+    for T, S in (([0], [0]), ([2], [3]), ([4], [-1])):
+        with pytest.raises(mr.RNNTError) as e:
+            mr.LossHandle(acts, labels, gpu_util.to_dev(np.array(T, np.int32), torch.int32),
+                          gpu_util.to_dev(np.array(S, np.int32), torch.int32))
+        assert e.value.status == 2
+    with pytest.raises(RuntimeError):
+        mr.LossHandle(acts.cpu(), labels, gpu_util.to_dev(c.T, torch.int32), gpu_util.to_dev(c.S, torch.int32))
+    h = mr.LossHandle(acts, labels, gpu_util.to_dev(c.T, torch.int32), gpu_util.to_dev(c.S, torch.int32))
+    with pytest.raises(mr.RNNTError) as e:
+        h.cost(blank_label=3)                      # blank outside [0, V)
+    assert e.value.status == 2
+    h.close()
+
+
+def test_autograd_op_matches_reference_semantics(gu):
+    """monotonic_rnnt_loss: costs on the device, backward scales the saved gradients per utterance."""
+    import monotonic_rnnt_b200 as mr
+    import gpu_util
+    case, ref = golden_io.load("rand_v32")
+    acts = gpu_util.to_dev(case.acts, torch.float32).requires_grad_(True)
+    labels = gpu_util.to_dev(case.labels, torch.int32)
+    T = gpu_util.to_dev(case.T, torch.int32); S = gpu_util.to_dev(case.S, torch.int32)
+    costs = mr.monotonic_rnnt_loss(acts, labels, T, S, blank_label=case.blank)
+    assert costs.is_cuda and costs.shape == (case.B,)
+    w = torch.arange(1, case.B + 1, device="cuda", dtype=torch.float32)
+    (costs * w).sum().backward()
+    np.testing.assert_allclose(costs.detach().cpu().numpy(), ref["costs_f64"], rtol=COST_RTOL)
+    rows = case.T.astype(np.int64) * (case.S + 1)
+    scale = np.repeat(np.arange(1, case.B + 1, dtype=np.float64), rows)[:, None]
+    assert np.abs(acts.grad.cpu().numpy() - ref["grads_f64"] * scale).max() <= GRAD_ATOL * case.B
+    loss_mod = mr.MonotonicRNNTLoss(blank_label=case.blank)
+    c2 = loss_mod(acts.detach(), labels, T, S)
+    assert torch.equal(c2, costs.detach())
