@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- loss+grad throughput of the monotonic RNN-T hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU implementation, host cores
+
+One "step" = one pass of the hot path over one batch of synthetic input: the configuration BASELINE.json
+quotes the metric on (configs[1]: B=32 T=150 S=40 V=1000 fp32 logits, fixed lengths) per GPU.  Weak
+scaling: every rank runs that batch on its own logits; the only collective is one all-reduce of the summed
+cost per step.  Rank 0 prints ONE JSON line.
+
+  value     whole-job utterances/s with inputs resident in HBM; the timed region is K calls of the C-ABI
+            entry (mrnnt_cost_and_grad: K1 -> K2 -> K3, async D2H of the B costs, one stream sync)
+            bracketed by barrier + synchronize, CUDA events on the launch stream, max over ranks.
+  e2e       same metric through the public host API with HOST buffers: every step copies the step's
+            logits/labels/lengths from pinned host memory, builds the handle, runs, reads costs back.
+  roofline  dominant kernel (K3, gradient: reads the live logits, writes every gradient) timed per launch
+            with CUDA events recorded around it on the same stream in a second, instrumented pass of K steps.
+  cpu_baseline  the reference's own CPU implementation (oracle/_ref, compiled from the unmodified
+            reference sources) on the box's host cores, same inputs, bounded sample; also used here as the
+            checker of the GPU result (costs / gradients), which is the only reason bench.py touches oracle/.
+Inputs (0.79 GB logits + 0.79 GB gradients per step) exceed the 126 MB L2, so no L2 flush is needed
+between iterations (config.l2: "inputs>L2").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "loss_grad_utterances_per_sec"
+UNIT = "utt/s"
+WORKLOAD = "c2"  # BASELINE.json configs[1]
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def _traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture, if any."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get(WORKLOAD, {}).get(kernel)
+    return None
+
+
+def _config(wl, extra=None):
+    cfg = {"workload": f"{wl.name}: synthetic B={wl.B} T={int(wl.T.max())} S={int(wl.S.max())} V={wl.V} fp32 logits, "
+                       f"fixed lengths (BASELINE.json configs[1]) per GPU",
+           "batch_per_gpu": wl.B, "rows_per_gpu": wl.rows, "logit_bytes_per_gpu": wl.elements * 4,
+           "algorithmic_bytes_per_step_per_gpu": wl.algorithmic_bytes, "l2": "inputs>L2 (no flush needed)",
+           "parallelism": "utterance-sharded, one all-reduce of the summed cost"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks: NVML sampled from a thread while the timed regions run
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.power = [], set(), []
+        self.sm_max = None
+        self._stop = threading.Event()
+        self._active = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        except Exception as exc:  # NVML missing: report that, never fake numbers
+            self._nv = None
+            self.error = repr(exc)
+
+    def _run(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            if self._active.is_set():
+                try:
+                    self.samples.append(int(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self._h) / 1000.0)
+                    get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                        nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                    mask = int(get(self._h))
+                    for bit, name in self.REASONS.items():
+                        if mask & bit and name != "gpu_idle":
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            time.sleep(0.002)
+
+    def start(self):
+        self._active.set()
+
+    def pause(self):
+        self._active.clear()
+
+    def result(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=1.0)
+        if self._nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "error": getattr(self, "error", "nvml")}
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "power_w_max": max(self.power) if self.power else None}
+
+
+# ----------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU implementation on the host cores
+# ----------------------------------------------------------------------------------------------------
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # under torchrun only rank 0 measures the host baseline
+    import monotonic_rnnt_b200 as mr
+    from oracle import oracle
+
+    oracle.build()
+    wl = mr.synth.workload(WORKLOAD)
+    kind = "reference" if oracle.have_ref() else "port"
+    runner = oracle.run_ref if kind == "reference" else oracle.run
+    cores = oracle.num_threads(reference=(kind == "reference"))
+    per_utt = int(wl.T[0]) * (int(wl.S[0]) + 1) * wl.V
+
+    all_acts = mr.synth.uniform_logits(wl.B * per_utt, wl.logits_seed, 0)  # generated once, outside the timing
+
+    def step(B):
+        acts = all_acts[: B * per_utt]
+        t0 = time.perf_counter()
+        res = runner(acts, wl.labels[:B], wl.T[:B], wl.S[:B], wl.V, blank=wl.blank, precision="f32",
+                     want_grads=True, num_threads=0)
+        dt = time.perf_counter() - t0
+        assert np.isfinite(res.costs).all()
+        return dt
+
+    # bounded sample: as many utterances of the workload as keep the whole run within ~2 minutes
+    probe_B = min(wl.B, max(1, cores))
+    t_probe = step(probe_B)
+    per_utt_s = t_probe / probe_B
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    B = int(max(1, min(wl.B, budget / per_utt_s)))
+    if B >= cores:
+        B = B // cores * cores
+    for _ in range(args.warmup):
+        step(B)
+    t = [step(B) for _ in range(args.steps)]
+    ms = 1000.0 * sum(t) / len(t)
+    value = B / (ms / 1000.0)
+    sample = (f"{B} of the {wl.B} utterances of {wl.name} per step (full T={int(wl.T[0])} S={int(wl.S[0])} V={wl.V}), "
+              f"CpuRNNTComputer<float>::cost_and_grad, -O2 -fopenmp, {cores} threads")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": _config(wl, {"sample_batch": B}),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------
+def run_b200(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    import monotonic_rnnt_b200 as mr
+    from monotonic_rnnt_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path "
+                         "(use --impl reference for the host baseline)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    lib = _lib.load()
+    wl = mr.synth.workload(WORKLOAD)
+    n = wl.elements
+    stream = torch.cuda.current_stream()
+
+    # ---- inputs resident in HBM ------------------------------------------------------------------
+    acts = torch.empty((wl.rows, wl.V), dtype=torch.float32, device=dev)
+    _lib.check(lib.mrnnt_synth_uniform(acts.data_ptr(), n, wl.logits_seed, rank * n, stream.cuda_stream), "synth")
+    labels = torch.from_numpy(wl.labels).to(dev)
+    T = torch.from_numpy(wl.T).to(dev)
+    S = torch.from_numpy(wl.S).to(dev)
+    grads = torch.empty_like(acts)
+    costs_host = torch.empty(wl.B, dtype=torch.float32).pin_memory()
+    handle = mr.LossHandle(acts, labels, T, S, lengths_host=(wl.T, wl.S))
+    if wl.alignment is not None:
+        handle.restrict_to_alignment(torch.from_numpy(wl.alignment).to(dev), wl.max_shift, wl.blank)
+    cost_sum = torch.zeros((), dtype=torch.float32, device=dev)
+
+    def one_step():
+        handle.cost_and_grad(wl.blank, grads, costs_host)
+        if world > 1:
+            total = handle.device_costs().sum()
+            dist.all_reduce(total)
+            cost_sum.copy_(total)
+
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+
+    # ---- timed region: value ---------------------------------------------------------------------
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    if clocks:
+        clocks.start()
+    t0 = time.perf_counter()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        one_step()
+    ev1.record(stream)
+    barrier()
+    wall_ms = 1000.0 * (time.perf_counter() - t0)
+    if clocks:
+        clocks.pause()
+    ms_total = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms_total.item()) / args.steps
+    value = world * wl.B / (ms_per_step / 1000.0)
+
+    # ---- instrumented pass: per-kernel durations (CUDA events around K1, K2, K3 on the launch stream) -
+    handle.set_option(_lib.OPT_TIMING, 1)
+    handle.cost_and_grad(wl.blank, grads, costs_host)
+    acc = np.zeros(3)
+    if clocks:
+        clocks.start()
+    for _ in range(args.steps):
+        handle.cost_and_grad(wl.blank, grads, costs_host)
+        acc += np.array(handle.last_timings())
+    if clocks:
+        clocks.pause()
+    handle.set_option(_lib.OPT_TIMING, 0)
+    k_ms = acc / args.steps
+    costs_gpu = costs_host.clone().numpy()
+
+    # ---- e2e: host buffers, copies inside the timed region --------------------------------------------
+    acts_h = torch.empty((wl.rows, wl.V), dtype=torch.float32).pin_memory()
+    acts_h.copy_(acts)
+    labels_h = torch.from_numpy(wl.labels).pin_memory()
+    T_h = torch.from_numpy(wl.T).pin_memory()
+    S_h = torch.from_numpy(wl.S).pin_memory()
+    h2d = acts_h.numel() * 4 + labels_h.numel() * 4 + T_h.numel() * 4 + S_h.numel() * 4
+    d2h = wl.B * 4
+
+    def e2e_step():
+        acts.copy_(acts_h, non_blocking=True)
+        labels.copy_(labels_h, non_blocking=True)
+        T.copy_(T_h, non_blocking=True)
+        S.copy_(S_h, non_blocking=True)
+        h = mr.LossHandle(acts, labels, T, S, lengths_host=(wl.T, wl.S))
+        h.cost_and_grad(wl.blank, grads, costs_host)     # returns with the costs on the host
+        h.close()
+
+    e2e_steps = max(3, min(args.steps, 20))
+    e2e_step()
+    barrier()
+    if clocks:
+        clocks.start()
+    ev0.record(stream)
+    for _ in range(e2e_steps):
+        e2e_step()
+    ev1.record(stream)
+    barrier()
+    if clocks:
+        clocks.pause()
+    e2e_ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_ms_per_step = float(e2e_ms.item()) / e2e_steps
+    e2e_value = world * wl.B / (e2e_ms_per_step / 1000.0)
+    assert np.allclose(costs_host.numpy(), costs_gpu, rtol=1e-6)
+
+    # ---- CPU baseline beside it (rank 0, N == 1 only), doubling as the checker ---------------------------
+    cpu_baseline, parity = None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle
+        oracle.build()
+        kind = "reference" if oracle.have_ref() else "port"
+        runner = oracle.run_ref if kind == "reference" else oracle.run
+        cores = oracle.num_threads(reference=(kind == "reference"))
+        acts_np = acts_h.numpy()
+        times, res = [], None
+        t_budget = time.perf_counter()
+        for i in range(3):
+            t1 = time.perf_counter()
+            res = runner(acts_np, wl.labels, wl.T, wl.S, wl.V, blank=wl.blank, precision="f32", want_grads=True,
+                         num_threads=0)
+            times.append(time.perf_counter() - t1)
+            if time.perf_counter() - t_budget > 20.0:
+                break
+        best = min(times)
+        cpu_baseline = {"value": wl.B / best, "unit": UNIT, "cores": cores, "kind": kind,
+                        "sample": f"the full {wl.name} batch ({wl.B} utterances), best of {len(times)} runs of "
+                                  f"CpuRNNTComputer<float>::cost_and_grad (-O2 -fopenmp), {best * 1000:.0f} ms"}
+        g = grads.cpu().numpy()
+        parity = {"checker": f"oracle/{'_ref' if kind == 'reference' else 'liboracle'} f32 on the same inputs",
+                  "cost_max_rel": float(np.max(np.abs(costs_gpu - res.costs) / np.abs(res.costs))),
+                  "grad_max_abs_vs_f32_cpu": float(np.abs(g - res.grads).max()),
+                  "note": "the float CPU reference itself is only ~4e-4 from exact arithmetic on this shape "
+                          "(SURVEY D6); tests/test_gpu_fullsize.py checks against the double-precision oracle"}
+
+    clock_info = clocks.result() if clocks else None
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+
+    peak, peak_src = _peaks()
+    k3_bytes = 2 * 4 * n  # K3 algorithmic bytes per launch: read logits once + write gradients once
+    k3_gbs = k3_bytes / (k_ms[2] * 1e-3) / 1e9
+    call_gbs = wl.algorithmic_bytes / (ms_per_step * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": _config(wl),
+        "roofline": {"kernel": "k3_grad_tma_kernel", "bound": "hbm", "achieved": k3_gbs, "peak": peak, "unit": "GB/s",
+                     "frac": k3_gbs / peak, "traffic": _traffic("k3_grad_tma_kernel"), "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": k3_bytes, "ms_per_launch": float(k_ms[2])},
+        "kernels_ms": {"k1_lse_gather": float(k_ms[0]), "k2_lattice": float(k_ms[1]), "k3_grad": float(k_ms[2]),
+                       "sum": float(k_ms.sum()), "k1_GBps_of_4N": 4 * n / (k_ms[0] * 1e-3) / 1e9},
+        "call_roofline": {"algorithmic_bytes": wl.algorithmic_bytes, "achieved_GBps": call_gbs,
+                          "frac_of_measured_peak": call_gbs / peak, "frac_of_8TBps_nominal": call_gbs / 8000.0,
+                          "per_gpu": True},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms_per_step, "steps": e2e_steps,
+                "path": "pinned host -> H2D -> LossHandle(...) -> mrnnt_cost_and_grad -> costs on host"},
+        "gpu_launches": 3 * args.steps,
+        "clocks": clock_info, "wall_ms_timed_region": wall_ms,
+        "cpu_baseline": cpu_baseline, "parity": parity,
+        "build": lib.mrnnt_build_info().decode(),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-CPU baseline/checker leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -24,7 +24,6 @@
 
 namespace mrnnt {
 
-constexpr int kStreamConsumerWarps = 8;
 
 struct DeviceInfo {
     int sm_count = 0;
@@ -48,6 +47,20 @@ inline const DeviceInfo &device_info() {
         cached_dev = dev;
     }
     return info;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) costs host microseconds; do it once per (kernel, device).
+// `cache` is a per-kernel-instantiation static table.  A benign race only repeats the call.
+constexpr int kMaxDevices = 32;
+template <typename Kern>
+inline bool ensure_dynamic_smem(Kern kern, size_t bytes, size_t (&cache)[kMaxDevices]) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return false;
+    if (bytes <= 48 * 1024 || bytes <= cache[dev]) return true;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)) != cudaSuccess)
+        return false;
+    cache[dev] = bytes;
+    return true;
 }
 
 // Validation rules of the reference (gpu_workspace_manager.h:232-239, cpu twin :99-107).
@@ -174,21 +187,59 @@ class Engine {
         if (!dev.ok) return RNNT_STATUS_EXECUTION_FAILED;
         RNNTStatus st = setup(stream);
         if (st != RNNT_STATUS_SUCCESS) return st;
+        mark(0, stream);
         st = launch_k1(blank, stream, dev);
         if (st != RNNT_STATUS_SUCCESS) return st;
+        mark(1, stream);
         st = launch_k2(blank, stream, dev, grads_dev != nullptr);
         if (st != RNNT_STATUS_SUCCESS) return st;
+        mark(2, stream);
         if (grads_dev != nullptr) {
             st = launch_k3(blank, stream, dev, grads_dev);
             if (st != RNNT_STATUS_SUCCESS) return st;
         }
+        mark(3, stream);
         return RNNT_STATUS_SUCCESS;
+    }
+
+    // Per-kernel device timing for the bench (CUDA events on the launch stream).  Off by default.
+    RNNTStatus set_timing(bool on) {
+        if (on && !timing_) {
+            for (auto &e : ev_)
+                if (cudaEventCreate(&e) != cudaSuccess) return RNNT_STATUS_EXECUTION_FAILED;
+        } else if (!on && timing_) {
+            for (auto &e : ev_) cudaEventDestroy(e);
+        }
+        timing_ = on;
+        return RNNT_STATUS_SUCCESS;
+    }
+
+    // Durations (ms) of K1, K2, K3 of the last enqueue(); the stream must have been synchronised.
+    RNNTStatus last_timings(float ms[3]) const {
+        if (!timing_) return RNNT_STATUS_INVALID_VALUE;
+        for (int i = 0; i < 3; ++i)
+            if (cudaEventElapsedTime(&ms[i], ev_[i], ev_[i + 1]) != cudaSuccess) return RNNT_STATUS_EXECUTION_FAILED;
+        return RNNT_STATUS_SUCCESS;
+    }
+
+    ~Engine() {
+        if (timing_)
+            for (auto &e : ev_) cudaEventDestroy(e);
     }
 
     // Force the generic (non-TMA) streaming kernels; used by the tests to cross-check both variants.
     void set_force_generic(bool v) { force_generic_ = v; }
+    // Consumer warps per CTA of the streaming kernels (8 or 16); tuning knob for the bench.
+    void set_stream_warps(int k1, int k3) {
+        if (k1 == 8 || k1 == 16) k1_warps_ = k1;
+        if (k3 == 8 || k3 == 16) k3_warps_ = k3;
+    }
 
    private:
+    void mark(int i, cudaStream_t stream) {
+        if (timing_) cudaEventRecord(ev_[i], stream);
+    }
+
     static RNNTStatus launched() { return cudaGetLastError() == cudaSuccess ? RNNT_STATUS_SUCCESS : RNNT_STATUS_EXECUTION_FAILED; }
 
     RNNTStatus setup(cudaStream_t stream) {
@@ -201,9 +252,8 @@ class Engine {
             size_t smem = alignment_ != nullptr ? (static_cast<size_t>(shape_.T_max) + 1) * sizeof(int) : 0;
             if (smem > 48 * 1024) {
                 if (smem > static_cast<size_t>(device_info().max_smem_optin) - 1024) return RNNT_STATUS_INVALID_VALUE;
-                if (cudaFuncSetAttribute(band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem)) != cudaSuccess)
-                    return RNNT_STATUS_EXECUTION_FAILED;
+                static size_t configured[kMaxDevices] = {};
+                if (!ensure_dynamic_smem(band_kernel, smem, configured)) return RNNT_STATUS_EXECUTION_FAILED;
             }
             band_kernel<<<B_, kBandThreads, smem, stream>>>(T_dev_, S_dev_, shape_.T_max, alignment_, max_shift_,
                                                             align_blank_, ws_.band);
@@ -218,11 +268,18 @@ class Engine {
         return RNNT_STATUS_SUCCESS;
     }
 
-    bool can_stream(const void *p0, const void *p1, size_t extra_per_row, const DeviceInfo &dev, StreamTiling *tl) const {
+    // Pick the streaming (TMA-staged) configuration: the preferred consumer-warp count if a safe ring exists
+    // for it, else 8 warps, else none (generic kernels).
+    bool can_stream(const void *p0, const void *p1, size_t extra_per_row, int preferred_warps, const DeviceInfo &dev,
+                    StreamTiling *tl) const {
         if (force_generic_) return false;
         if ((reinterpret_cast<uintptr_t>(p0) & 15) || (reinterpret_cast<uintptr_t>(p1) & 15)) return false;
-        if (!stream_tiling(V_, extra_per_row, tl)) return false;
-        return tl->smem_bytes <= static_cast<size_t>(dev.max_smem_optin);
+        const int order[2] = {preferred_warps, 8};
+        for (int w : order) {
+            if (stream_tiling(V_, extra_per_row, w, tl) && tl->smem_bytes <= static_cast<size_t>(dev.max_smem_optin))
+                return true;
+        }
+        return false;
     }
 
     int generic_grid(const DeviceInfo &dev) const {
@@ -231,29 +288,40 @@ class Engine {
         return static_cast<int>(want < cap ? (want < 1 ? 1 : want) : cap);
     }
 
+    template <int NW, int C>
+    RNNTStatus launch_k1_tma(int blank, cudaStream_t stream, const DeviceInfo &dev, const StreamTiling &tl) {
+        auto kern = k1_lse_tma_kernel<NW, C>;
+        static size_t configured[kMaxDevices] = {};
+        if (!ensure_dynamic_smem(kern, tl.smem_bytes, configured)) return RNNT_STATUS_EXECUTION_FAILED;
+        kern<<<dev.sm_count, (NW + 1) * kWarp, tl.smem_bytes, stream>>>(acts_, labels_, ws_.rowmeta, ws_.lp, ws_.denom,
+                                                                         shape_.rows, V_, blank, tl.G, tl.stages);
+        return launched();
+    }
+
+    template <int NW>
+    RNNTStatus launch_k1_nw(int blank, cudaStream_t stream, const DeviceInfo &dev, const StreamTiling &tl) {
+        const int V4 = V_ / 4;
+        if (V4 <= 8 * kWarp) return launch_k1_tma<NW, 8>(blank, stream, dev, tl);    // row in 32 registers / lane
+        if (V4 <= 16 * kWarp) return launch_k1_tma<NW, 16>(blank, stream, dev, tl);  // 64 registers / lane
+        return launch_k1_tma<NW, 0>(blank, stream, dev, tl);                         // two passes over smem
+    }
+
     RNNTStatus launch_k1(int blank, cudaStream_t stream, const DeviceInfo &dev) {
         StreamTiling tl;
-        if (can_stream(acts_, acts_, 0, dev, &tl)) {
-            auto kern = k1_lse_tma_kernel<kStreamConsumerWarps>;
-            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(tl.smem_bytes)) != cudaSuccess)
-                return RNNT_STATUS_EXECUTION_FAILED;
-            kern<<<dev.sm_count, (kStreamConsumerWarps + 1) * kWarp, tl.smem_bytes, stream>>>(
-                acts_, labels_, ws_.rowmeta, ws_.lp, ws_.denom, shape_.rows, V_, blank, tl.G, tl.stages);
-        } else {
-            k1_lse_generic_kernel<<<generic_grid(dev), kGenericWarps * kWarp, 0, stream>>>(
-                acts_, labels_, ws_.rowmeta, ws_.lp, ws_.denom, shape_.rows, V_, blank);
+        if (can_stream(acts_, acts_, 0, k1_warps_, dev, &tl)) {
+            return tl.warps == 8 ? launch_k1_nw<8>(blank, stream, dev, tl) : launch_k1_nw<16>(blank, stream, dev, tl);
         }
+        k1_lse_generic_kernel<<<generic_grid(dev), kGenericWarps * kWarp, 0, stream>>>(
+            acts_, labels_, ws_.rowmeta, ws_.lp, ws_.denom, shape_.rows, V_, blank);
         return launched();
     }
 
     template <int K>
     RNNTStatus launch_k2_warp(const K2Args &args, cudaStream_t stream) {
         auto kern = k2_lattice_kernel<K>;
-        const size_t smem = K2Fifo<K>::kSmemBytes;
-        if (smem > 48 * 1024 &&
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
-            return RNNT_STATUS_EXECUTION_FAILED;
+        const size_t smem = k2_smem_bytes(shape_.S_max);
+        static size_t configured[kMaxDevices] = {};
+        if (!ensure_dynamic_smem(kern, smem, configured)) return RNNT_STATUS_EXECUTION_FAILED;
         kern<<<B_, kK2Threads, smem, stream>>>(args, 0);
         return launched();
     }
@@ -265,6 +333,7 @@ class Engine {
         a.ll_fwd = ws_.ll_fwd; a.ll_bwd = ws_.ll_bwd; a.costs = ws_.costs;
         a.T_max = shape_.T_max; a.S_max = shape_.S_max; a.V = V_; a.blank = blank;
         a.need_beta = need_beta ? 1 : 0;
+        a.chunk_frames = k2_chunk_frames(shape_.S_max);
         const int states = shape_.S_max + 1;
         if (states <= 32) return launch_k2_warp<1>(a, stream);
         if (states <= 64) return launch_k2_warp<2>(a, stream);
@@ -273,26 +342,31 @@ class Engine {
         if (states <= 512) return launch_k2_warp<16>(a, stream);
         const size_t smem = (static_cast<size_t>(shape_.S_max) + 2) * sizeof(double);
         if (smem > static_cast<size_t>(dev.max_smem_optin)) return RNNT_STATUS_INVALID_VALUE;
-        if (smem > 48 * 1024 && cudaFuncSetAttribute(k2_lattice_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                     static_cast<int>(smem)) != cudaSuccess)
-            return RNNT_STATUS_EXECUTION_FAILED;
+        static size_t configured[kMaxDevices] = {};
+        if (!ensure_dynamic_smem(k2_lattice_wide_kernel, smem, configured)) return RNNT_STATUS_EXECUTION_FAILED;
         k2_lattice_wide_kernel<<<B_, kK2Threads, smem, stream>>>(a, 0);
+        return launched();
+    }
+
+    template <int NW>
+    RNNTStatus launch_k3_tma(int blank, cudaStream_t stream, const DeviceInfo &dev, const StreamTiling &tl,
+                             float *grads) {
+        auto kern = k3_grad_tma_kernel<NW>;
+        static size_t configured[kMaxDevices] = {};
+        if (!ensure_dynamic_smem(kern, tl.smem_bytes, configured)) return RNNT_STATUS_EXECUTION_FAILED;
+        kern<<<dev.sm_count, (NW + 1) * kWarp, tl.smem_bytes, stream>>>(acts_, ws_.coef, grads, shape_.rows, V_, blank,
+                                                                         tl.G, tl.stages);
         return launched();
     }
 
     RNNTStatus launch_k3(int blank, cudaStream_t stream, const DeviceInfo &dev, float *grads) {
         StreamTiling tl;
-        if (can_stream(acts_, grads, sizeof(float4), dev, &tl)) {
-            auto kern = k3_grad_tma_kernel<kStreamConsumerWarps>;
-            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(tl.smem_bytes)) != cudaSuccess)
-                return RNNT_STATUS_EXECUTION_FAILED;
-            kern<<<dev.sm_count, (kStreamConsumerWarps + 1) * kWarp, tl.smem_bytes, stream>>>(
-                acts_, ws_.coef, grads, shape_.rows, V_, blank, tl.G, tl.stages);
-        } else {
-            k3_grad_generic_kernel<<<generic_grid(dev), kGenericWarps * kWarp, 0, stream>>>(acts_, ws_.coef, grads,
-                                                                                             shape_.rows, V_, blank);
+        if (can_stream(acts_, grads, sizeof(float4), k3_warps_, dev, &tl)) {
+            return tl.warps == 8 ? launch_k3_tma<8>(blank, stream, dev, tl, grads)
+                                 : launch_k3_tma<16>(blank, stream, dev, tl, grads);
         }
+        k3_grad_generic_kernel<<<generic_grid(dev), kGenericWarps * kWarp, 0, stream>>>(acts_, ws_.coef, grads,
+                                                                                         shape_.rows, V_, blank);
         return launched();
     }
 
@@ -316,6 +390,10 @@ class Engine {
     int max_shift_ = 0;
     int align_blank_ = 0;
     bool force_generic_ = false;
+    int k1_warps_ = 16;
+    int k3_warps_ = 16;
+    bool timing_ = false;
+    cudaEvent_t ev_[4] = {};
 };
 
 }  // namespace mrnnt

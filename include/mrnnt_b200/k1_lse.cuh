@@ -12,8 +12,10 @@
 //   * persistent CTAs, one per SM; the flat row space is cut into tiles of G consecutive rows;
 //   * a producer warp stages each tile's LIVE rows into a shared-memory ring with 1-D bulk async
 //     copies (TMA engine, cp.async.bulk / SASS UBLKCP) that complete on an mbarrier;
-//   * NW consumer warps take one row each: 128-bit shared loads, online max / sum-of-2^x in
-//     registers (one MUFU.EX2 per element), a 10-shuffle warp combine, and one 24-byte result.
+//   * NW consumer warps take one row each.  For V <= 2048 the row is pulled into registers with
+//     128-bit shared loads once; the exact row max comes from one redux.sync on order-preserving
+//     integer keys, the sum of 2^((x - max) log2 e) costs one FFMA + one MUFU.EX2 per element with no
+//     branches, and five shuffles finish the sum.  Larger rows make two passes over shared memory.
 // A generic variant (direct global loads, any V / alignment) covers V % 4 != 0, unaligned bases and
 // rows too large for the ring.
 #pragma once
@@ -22,45 +24,69 @@
 
 namespace mrnnt {
 
-// Running log2-sum-exp2 of the values one lane has seen: sum_i 2^(x_i*log2e - mL), mL = max*log2e.
-struct LaneLse {
-    float m = kNegInfF;   // running max of x
-    float mL = kNegInfF;  // m * log2e, rounded once; every term and the final result use this value
-    float neg = 0.0f;          // -mL once a finite max has been seen, 0 before (keeps -inf inputs NaN-free)
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-
-    __device__ __forceinline__ void raise(float cm) {
-        if (cm > m) {
-            const float nmL = cm * kLog2e;
-            const float f = (m == kNegInfF) ? 0.0f : ex2_approx(mL - nmL);
-            s0 *= f; s1 *= f; s2 *= f; s3 *= f;
-            m = cm; mL = nmL; neg = -nmL;
-        }
-    }
-    __device__ __forceinline__ void add(const float4 &a) {
-        s0 += ex2_approx(fmaf(a.x, kLog2e, neg));
-        s1 += ex2_approx(fmaf(a.y, kLog2e, neg));
-        s2 += ex2_approx(fmaf(a.z, kLog2e, neg));
-        s3 += ex2_approx(fmaf(a.w, kLog2e, neg));
-    }
-    __device__ __forceinline__ void add1(float x) { s0 += ex2_approx(fmaf(x, kLog2e, neg)); }
-
-    // Warp-wide result: natural-log denominator  -(max + log sum exp(x - max)), in double.
-    __device__ __forceinline__ double finish() const {
-        const float ML = warp_max(mL);
-        const float scale = (mL == kNegInfF) ? 0.0f : ex2_approx(mL - ML);
-        const double mine = (static_cast<double>(s0) + static_cast<double>(s1) +
-                             static_cast<double>(s2) + static_cast<double>(s3)) * static_cast<double>(scale);
-        const double tot = warp_sum(mine);
-        int e;
-        const double f = frexp(tot, &e);  // tot = f * 2^e, f in [0.5, 1)
-        const double lse2 = static_cast<double>(ML) + static_cast<double>(e - 1) +
-                            static_cast<double>(log2f(static_cast<float>(f + f)));
-        return -lse2 * kLn2D;
-    }
-};
-
 __device__ __forceinline__ float max4(const float4 &a) { return fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)); }
+
+// Warp-wide float max with ONE redux.sync: floats are mapped to signed ints that sort the same way.
+__device__ __forceinline__ float warp_max_redux(float v) {
+    int k = __float_as_int(v);
+    k ^= (k >> 31) & 0x7fffffff;
+    k = __reduce_max_sync(0xffffffffu, k);
+    k ^= (k >> 31) & 0x7fffffff;
+    return __int_as_float(k);
+}
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// sum over the lane's 4 components of 2^(x*log2e + neg)
+__device__ __forceinline__ void exp_acc(const float4 &a, float neg, float &s0, float &s1, float &s2, float &s3) {
+    s0 += ex2_approx(fmaf(a.x, kLog2e, neg));
+    s1 += ex2_approx(fmaf(a.y, kLog2e, neg));
+    s2 += ex2_approx(fmaf(a.z, kLog2e, neg));
+    s3 += ex2_approx(fmaf(a.w, kLog2e, neg));
+}
+
+// From the warp-wide max (times log2 e, rounded once and used for every term) and the warp-wide sum of
+// 2^(x log2e - ML): the natural-log denominator -(max + log sum exp(x - max)), in double.
+__device__ __forceinline__ double lse_finish(float ML, float sum) {
+    return -(static_cast<double>(ML) + log2_split(sum)) * kLn2D;
+}
+
+// One row resident in shared memory (16-byte aligned, V4 float4).  C > 0: the lane's <= C float4 live
+// in registers (V4 <= 32*C); C == 0: two passes over shared memory, any V4.
+template <int C>
+__device__ __forceinline__ double row_denominator(const float4 *__restrict__ x4, int V4, int lane) {
+    const float4 ninf = make_float4(kNegInfF, kNegInfF, kNegInfF, kNegInfF);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    float ML;
+    if constexpr (C > 0) {
+        float4 v[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int j = lane + c * kWarp;
+            v[c] = (j < V4) ? x4[j] : ninf;
+        }
+        float m = max4(v[0]);
+#pragma unroll
+        for (int c = 1; c < C; ++c) m = fmaxf(m, max4(v[c]));
+        ML = warp_max_redux(m) * kLog2e;
+        const float neg = -ML;
+#pragma unroll
+        for (int c = 0; c < C; ++c) exp_acc(v[c], neg, s0, s1, s2, s3);
+    } else {
+        float m = kNegInfF;
+#pragma unroll 4
+        for (int j = lane; j < V4; j += kWarp) m = fmaxf(m, max4(x4[j]));
+        ML = warp_max_redux(m) * kLog2e;
+        const float neg = -ML;
+#pragma unroll 4
+        for (int j = lane; j < V4; j += kWarp) exp_acc(x4[j], neg, s0, s1, s2, s3);
+    }
+    return lse_finish(ML, warp_sum_f((s0 + s1) + (s2 + s3)));
+}
 
 // What lane 0 writes for one row.
 __device__ __forceinline__ void k1_store_row(double2 *__restrict__ lp, double *__restrict__ denom, int64_t row,
@@ -71,7 +97,7 @@ __device__ __forceinline__ void k1_store_row(double2 *__restrict__ lp, double *_
 }
 
 // ---------------------------------------------------------------------------------------------
-// Generic variant: one warp per row, scalar global loads.  Any V, any alignment.
+// Generic variant: one warp per row, scalar global loads (second pass hits L1).  Any V, any alignment.
 // ---------------------------------------------------------------------------------------------
 constexpr int kGenericWarps = 8;
 
@@ -92,13 +118,12 @@ static __global__ void __launch_bounds__(kGenericWarps * kWarp)
             continue;
         }
         const float *x = acts + row * V;
-        LaneLse acc;
-        for (int v = lane; v < V; v += kWarp) {
-            const float xv = __ldg(x + v);
-            acc.raise(xv);
-            acc.add1(xv);
-        }
-        const double den = acc.finish();
+        float m = kNegInfF;
+        for (int v = lane; v < V; v += kWarp) m = fmaxf(m, __ldg(x + v));
+        const float ML = warp_max_redux(m) * kLog2e;
+        float s = 0.f;
+        for (int v = lane; v < V; v += kWarp) s += ex2_approx(fmaf(__ldg(x + v), kLog2e, -ML));
+        const double den = lse_finish(ML, warp_sum_f(s));
         if (lane == 0) {
             const int lab = meta >= 0 ? __ldg(labels + meta) : -1;
             const bool has = lab >= 0 && lab < V;
@@ -113,8 +138,9 @@ static __global__ void __launch_bounds__(kGenericWarps * kWarp)
 // Shared memory: [stages][G*V] floats | full[stages] | empty[stages] | meta[stages][32]
 // ---------------------------------------------------------------------------------------------
 struct StreamTiling {
-    int G = 0;       // rows per tile (1..32)
+    int G = 0;       // rows per tile: a power of two in 1..32
     int stages = 0;  // ring depth
+    int warps = 0;   // consumer warps (8 or 16)
     size_t smem_bytes = 0;
 };
 
@@ -122,19 +148,28 @@ constexpr int kStreamMaxStages = 12;
 constexpr size_t kStreamSmemBudget = 200 * 1024;  // of the 227 KB a CTA may use
 constexpr int kStreamTileTarget = 32 * 1024;      // bytes per ring slot we aim for
 
-// extra_per_row: additional per-row shared bytes a kernel keeps next to the tile (K3: its coefficients)
-inline bool stream_tiling(int V, size_t extra_per_row, StreamTiling *out) {
-    if (V <= 0 || (V % 4) != 0) return false;
+// Tiling of the streaming kernels for vocabulary size V with `warps` consumer warps.
+// extra_per_row: additional per-row shared bytes a kernel keeps next to the tile (K3: its coefficients).
+//
+// Ring-safety rule: consumer warp w handles the rows q = w, w+NW, ... of the CTA's row sequence.  When
+// NW > G a warp only touches every (NW/G)-th tile; a parity wait on an mbarrier is only meaningful if the
+// waiting warp also consumed the PREVIOUS use of that ring stage (bulk copies complete out of order, so
+// "an earlier tile was issued first" proves nothing).  Hence G is a power of two and the ring depth is a
+// multiple of the stride NW/G: every warp then cycles through a fixed subset of the stages.
+inline bool stream_tiling(int V, size_t extra_per_row, int warps, StreamTiling *out) {
+    if (V <= 0 || (V % 4) != 0 || (warps != 8 && warps != 16)) return false;
     const size_t row_bytes = static_cast<size_t>(V) * 4;
-    int G = static_cast<int>(kStreamTileTarget / row_bytes);
-    if (G < 1) G = 1;
-    if (G > 32) G = 32;
+    int G = 1;
+    while (G < 32 && static_cast<size_t>(2 * G) * row_bytes <= static_cast<size_t>(kStreamTileTarget)) G *= 2;
     const size_t slot = static_cast<size_t>(G) * row_bytes + 32 * (sizeof(int) + extra_per_row) + 16;
     int stages = static_cast<int>(kStreamSmemBudget / slot);
-    if (stages < 3) return false;  // rows this large go through the generic kernels
     if (stages > kStreamMaxStages) stages = kStreamMaxStages;
+    const int stride = warps > G ? warps / G : 1;
+    stages = stages / stride * stride;
+    if (stages < 3) return false;
     out->G = G;
     out->stages = stages;
+    out->warps = warps;
     out->smem_bytes = static_cast<size_t>(stages) * slot + 128;
     return true;
 }
@@ -153,7 +188,7 @@ __device__ __forceinline__ void issue_live_runs(uint32_t mask, float *tile, cons
     }
 }
 
-template <int NW>
+template <int NW, int C>
 __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
     k1_lse_tma_kernel(const float *__restrict__ acts, const int *__restrict__ labels,
                       const int *__restrict__ rowmeta, double2 *__restrict__ lp, double *__restrict__ denom,
@@ -181,12 +216,17 @@ __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
     if (warp == NW) {
         // ---------------- producer warp ----------------
         const uint64_t policy = l2_policy_evict_first();
+        auto load_meta = [&](int64_t k) {
+            const int64_t row = (blockIdx.x + k * gridDim.x) * G + lane;
+            return (k < nloc && lane < G && row < rows) ? __ldg(rowmeta + row) : kRowDead;
+        };
+        int m_next = load_meta(0);
+        int stage = 0;
+        uint32_t phase = 0;
         for (int64_t k = 0; k < nloc; ++k) {
-            const int stage = static_cast<int>(k % stages);
-            const uint32_t phase = static_cast<uint32_t>((k / stages) & 1);
+            const int m = m_next;
+            m_next = load_meta(k + 1);  // one tile ahead: its latency hides behind this tile's wait
             const int64_t row0 = (blockIdx.x + k * gridDim.x) * G;
-            int m = kRowDead;
-            if (lane < G && row0 + lane < rows) m = __ldg(rowmeta + row0 + lane);
             const uint32_t mask = __ballot_sync(0xffffffffu, m != kRowDead);
             mbar_wait(empty + stage, phase ^ 1u);
             meta_sh[stage * 32 + lane] = m;
@@ -194,6 +234,10 @@ __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
             if (lane == 0) {
                 mbar_arrive_expect_tx(full + stage, static_cast<uint32_t>(__popc(mask)) * static_cast<uint32_t>(V) * 4u);
                 issue_live_runs(mask, tiles + stage * tile_floats, acts + row0 * V, V, full + stage, policy);
+            }
+            if (++stage == stages) {
+                stage = 0;
+                phase ^= 1u;
             }
         }
     } else {
@@ -216,19 +260,9 @@ __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
                     }
                 } else {
                     const float *xrow = tiles + stage * tile_floats + static_cast<size_t>(r) * V;
-                    const float4 *x4 = reinterpret_cast<const float4 *>(xrow);
                     int lab = -1;
-                    if (lane == 0 && meta >= 0) lab = __ldg(labels + meta);  // latency hides under the row loop
-                    LaneLse acc;
-                    const float4 ninf = make_float4(kNegInfF, kNegInfF, kNegInfF, kNegInfF);
-                    for (int j = lane; j < V4; j += 2 * kWarp) {
-                        const float4 a = x4[j];
-                        const float4 b = (j + kWarp < V4) ? x4[j + kWarp] : ninf;
-                        acc.raise(fmaxf(max4(a), max4(b)));
-                        acc.add(a);
-                        acc.add(b);
-                    }
-                    const double den = acc.finish();
+                    if (lane == 0 && meta >= 0) lab = __ldg(labels + meta);  // latency hides under the row math
+                    const double den = row_denominator<C>(reinterpret_cast<const float4 *>(xrow), V4, lane);
                     if (lane == 0) {
                         const bool has = lab >= 0 && lab < V;
                         k1_store_row(lp, denom, row, den, xrow[blank], has ? xrow[lab] : 0.0f, has);

@@ -93,20 +93,28 @@ __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
     if (warp == NW) {
         // ---------------- producer warp ----------------
         const uint64_t policy = l2_policy_evict_first();
+        auto load_coef = [&](int64_t k) {
+            const int64_t row = (blockIdx.x + k * gridDim.x) * G + lane;
+            return (k < nloc && lane < G && row < rows) ? __ldg(coef + row) : make_float4(kNegInfF, 0.f, 0.f, 0.f);
+        };
+        float4 c_next = load_coef(0);
+        int stage = 0;
+        uint32_t phase = 0;
         for (int64_t k = 0; k < nloc; ++k) {
-            const int stage = static_cast<int>(k % stages);
-            const uint32_t phase = static_cast<uint32_t>((k / stages) & 1);
+            const float4 c = c_next;
+            c_next = load_coef(k + 1);  // one tile ahead: its latency hides behind this tile's wait
             const int64_t row0 = (blockIdx.x + k * gridDim.x) * G;
-            float4 c = make_float4(kNegInfF, 0.f, 0.f, 0.f);
-            if (lane < G && row0 + lane < rows) c = __ldg(coef + row0 + lane);
-            const bool live = (lane < G) && (row0 + lane < rows) && !(c.x == kNegInfF);
-            const uint32_t mask = __ballot_sync(0xffffffffu, live);
+            const uint32_t mask = __ballot_sync(0xffffffffu, !(c.x == kNegInfF));
             mbar_wait(empty + stage, phase ^ 1u);
             coef_sh[stage * 32 + lane] = c;
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive_expect_tx(full + stage, static_cast<uint32_t>(__popc(mask)) * static_cast<uint32_t>(V) * 4u);
                 issue_live_runs(mask, tiles + stage * tile_floats, acts + row0 * V, V, full + stage, policy);
+            }
+            if (++stage == stages) {
+                stage = 0;
+                phase ^= 1u;
             }
         }
     } else {

@@ -44,16 +44,24 @@ struct Workspace {
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// K2 prefetches lp[] and band[] up to 8 frames beyond either end of an utterance without bounds checks
+// (k2_lattice.cuh); the two arrays therefore carry this much never-consumed slack on both sides.
+constexpr int kPrefetchFrames = 8;
+inline size_t lp_slack_bytes(const Shape &sh) {
+    return align_up(static_cast<size_t>(kPrefetchFrames) * (static_cast<size_t>(sh.S_max) + 1) * sizeof(double2), 256);
+}
+constexpr size_t kBandSlackBytes = 256;  // >= kPrefetchFrames * sizeof(int2)
+
 // Bytes needed for `shape`.  A function of (B, T[], S[]) only, like the reference
-// (gpu_workspace_manager.h:242-247); the value differs (56 B/row + O(B*T_max) instead of 12 B/row).
+// (gpu_workspace_manager.h:242-247); the value differs (60 B/row + O(B*T_max) instead of 12 B/row).
 inline size_t workspace_bytes(const Shape &sh) {
     const size_t rows = static_cast<size_t>(sh.rows);
     const size_t B = static_cast<size_t>(sh.B);
     size_t n = 256;  // slack to align an arbitrarily aligned base pointer
     n += align_up((B + 1) * sizeof(int64_t), 256);
-    n += align_up(B * static_cast<size_t>(sh.T_max) * sizeof(int2), 256);
+    n += align_up(B * static_cast<size_t>(sh.T_max) * sizeof(int2), 256) + 2 * kBandSlackBytes;
     n += align_up(rows * sizeof(int), 256);
-    n += align_up(rows * sizeof(double2), 256);
+    n += align_up(rows * sizeof(double2), 256) + 2 * lp_slack_bytes(sh);
     n += 3 * align_up(rows * sizeof(double), 256);
     n += align_up(rows * sizeof(float4), 256);
     n += 2 * align_up(B * sizeof(double), 256);
@@ -72,9 +80,13 @@ inline Workspace carve_workspace(void *base, const Shape &sh) {
     };
     Workspace w;
     w.row_start = reinterpret_cast<int64_t *>(take((B + 1) * sizeof(int64_t)));
+    take(kBandSlackBytes);
     w.band = reinterpret_cast<int2 *>(take(B * static_cast<size_t>(sh.T_max) * sizeof(int2)));
+    take(kBandSlackBytes);
     w.rowmeta = reinterpret_cast<int *>(take(rows * sizeof(int)));
+    take(lp_slack_bytes(sh));
     w.lp = reinterpret_cast<double2 *>(take(rows * sizeof(double2)));
+    take(lp_slack_bytes(sh));
     w.denom = reinterpret_cast<double *>(take(rows * sizeof(double)));
     w.alpha = reinterpret_cast<double *>(take(rows * sizeof(double)));
     w.beta = reinterpret_cast<double *>(take(rows * sizeof(double)));

@@ -65,9 +65,14 @@ RNNTStatus rnnt_loss_grad_gpu(const float *acts, const int *labels, const int *T
 
 /* ---- test / bench support (not part of the reference's surface) ---------------------------------*/
 enum {
-    MRNNT_OPT_FORCE_GENERIC = 1 /* value != 0: use the generic (non-TMA) streaming kernels */
+    MRNNT_OPT_FORCE_GENERIC = 1, /* value != 0: use the generic (non-TMA) streaming kernels */
+    MRNNT_OPT_TIMING = 2,        /* value != 0: record CUDA events around K1 / K2 / K3 of every call */
+    MRNNT_OPT_K1_WARPS = 3,      /* consumer warps per CTA of K1 (8 or 16)                              */
+    MRNNT_OPT_K3_WARPS = 4       /* consumer warps per CTA of K3 (8 or 16)                              */
 };
 RNNTStatus mrnnt_set_option(mrnnt_handle_t h, int option, int value);
+/* Durations in ms of K1, K2, K3 of the last call (MRNNT_OPT_TIMING on, stream synchronised). */
+RNNTStatus mrnnt_last_timings(mrnnt_handle_t h, float ms_k1_k2_k3[3]);
 
 enum {
     MRNNT_DBG_DENOM = 1,    /* double [rows]                                 */

@@ -14,6 +14,9 @@ STATUS_TEXT = {0: "no error", 1: "cuda memcpy or memset failed", 2: "invalid val
                4: "unknown error"}
 
 OPT_FORCE_GENERIC = 1
+OPT_TIMING = 2
+OPT_K1_WARPS = 3
+OPT_K3_WARPS = 4
 DBG_DENOM, DBG_ALPHA, DBG_BETA, DBG_LP, DBG_BAND, DBG_ROWMETA, DBG_LL, DBG_ROWSTART = range(1, 9)
 
 # every symbol include/mrnnt_c_api.h and include/rnnt_entrypoint.h declare
@@ -21,7 +24,7 @@ EXPORTED_SYMBOLS = (
     "compute_rnnt_loss", "mrnnt_get_workspace_size", "mrnnt_create", "mrnnt_destroy", "mrnnt_workspace_size",
     "mrnnt_set_workspace", "mrnnt_create_workspace", "mrnnt_free_workspace", "mrnnt_restrict_to_alignment",
     "mrnnt_cost_and_grad", "mrnnt_enqueue", "mrnnt_device_costs", "rnnt_loss_grad_gpu", "mrnnt_set_option",
-    "mrnnt_debug_copy", "mrnnt_synth_uniform", "mrnnt_build_info",
+    "mrnnt_debug_copy", "mrnnt_synth_uniform", "mrnnt_build_info", "mrnnt_last_timings",
 )
 
 
@@ -54,12 +57,14 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.rnnt_loss_grad_gpu.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, vp, ci, vp, sz, vp, vp, vp]
     lib.mrnnt_set_option.argtypes = [vp, ci, ci]
     lib.mrnnt_debug_copy.argtypes = [vp, ci, vp, sz]
+    lib.mrnnt_last_timings.argtypes = [vp, vp]
     lib.mrnnt_synth_uniform.argtypes = [vp, ctypes.c_int64, ctypes.c_uint64, ctypes.c_int64, vp]
     lib.mrnnt_build_info.argtypes = []
     lib.mrnnt_build_info.restype = ctypes.c_char_p
     for name in ("mrnnt_get_workspace_size", "mrnnt_create", "mrnnt_workspace_size", "mrnnt_set_workspace",
                  "mrnnt_create_workspace", "mrnnt_restrict_to_alignment", "mrnnt_cost_and_grad", "mrnnt_enqueue",
-                 "rnnt_loss_grad_gpu", "mrnnt_set_option", "mrnnt_debug_copy", "mrnnt_synth_uniform"):
+                 "rnnt_loss_grad_gpu", "mrnnt_set_option", "mrnnt_debug_copy", "mrnnt_synth_uniform",
+                 "mrnnt_last_timings"):
         getattr(lib, name).restype = ci
 
 

@@ -154,9 +154,22 @@ RNNTStatus mrnnt_set_option(mrnnt_handle_t h, int option, int value) {
         case MRNNT_OPT_FORCE_GENERIC:
             h->manager.engine().set_force_generic(value != 0);
             return RNNT_STATUS_SUCCESS;
+        case MRNNT_OPT_TIMING:
+            return h->manager.engine().set_timing(value != 0);
+        case MRNNT_OPT_K1_WARPS:
+            h->manager.engine().set_stream_warps(value, 0);
+            return RNNT_STATUS_SUCCESS;
+        case MRNNT_OPT_K3_WARPS:
+            h->manager.engine().set_stream_warps(0, value);
+            return RNNT_STATUS_SUCCESS;
         default:
             return RNNT_STATUS_INVALID_VALUE;
     }
+}
+
+RNNTStatus mrnnt_last_timings(mrnnt_handle_t h, float ms_k1_k2_k3[3]) {
+    if (h == nullptr || ms_k1_k2_k3 == nullptr) return RNNT_STATUS_INVALID_VALUE;
+    return h->manager.engine().last_timings(ms_k1_k2_k3);
 }
 
 RNNTStatus mrnnt_debug_copy(mrnnt_handle_t h, int what, void *dst_host, size_t dst_bytes) {

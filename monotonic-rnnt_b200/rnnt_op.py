@@ -103,6 +103,12 @@ class LossHandle:
     def set_option(self, option: int, value: int) -> None:
         _lib.check(self._lib.mrnnt_set_option(self._h, option, value), "mrnnt_set_option")
 
+    def last_timings(self):
+        """(ms_K1, ms_K2, ms_K3) of the last call; needs set_option(OPT_TIMING, 1) and a synchronised stream."""
+        out = (ctypes.c_float * 3)()
+        _lib.check(self._lib.mrnnt_last_timings(self._h, out), "mrnnt_last_timings")
+        return float(out[0]), float(out[1]), float(out[2])
+
     def restrict_to_alignment(self, alignment: torch.Tensor, max_shift: int, blank_idx: int) -> None:
         if not alignment.is_cuda or alignment.dtype != torch.int32 or not alignment.is_contiguous():
             raise TypeError("alignment must be a contiguous CUDA int32 tensor [B, T_max]")

@@ -1,0 +1,74 @@
+"""Per-kernel device times (CUDA events inside the engine) for the named workloads and tuning knobs.
+
+    python tools/kernel_times.py [c2 c3 c5 ...] [--iters 20]
+
+Prints one line per (workload, K1 warps, K3 warps).  Development aid; bench.py is the contract.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import monotonic_rnnt_b200 as mr  # noqa: E402
+from monotonic_rnnt_b200 import _lib  # noqa: E402
+
+
+def run(name: str, iters: int, combos) -> None:
+    wl = mr.synth.workload(name)
+    dev = torch.device("cuda", 0)
+    lib = _lib.load()
+    acts = torch.empty((wl.rows, wl.V), dtype=torch.float32, device=dev)
+    _lib.check(lib.mrnnt_synth_uniform(acts.data_ptr(), wl.elements, 0, 0, torch.cuda.current_stream().cuda_stream), "s")
+    labels = torch.from_numpy(wl.labels).to(dev)
+    T = torch.from_numpy(wl.T).to(dev)
+    S = torch.from_numpy(wl.S).to(dev)
+    grads = torch.empty_like(acts)
+    h = mr.LossHandle(acts, labels, T, S, lengths_host=(wl.T, wl.S))
+    if wl.alignment is not None:
+        h.restrict_to_alignment(torch.from_numpy(wl.alignment).to(dev), wl.max_shift, wl.blank)
+    h.set_option(_lib.OPT_TIMING, 1)
+    costs = torch.empty(wl.B, dtype=torch.float32).pin_memory()
+    n4 = wl.elements * 4
+    for k1w, k3w in combos:
+        h.set_option(_lib.OPT_K1_WARPS, k1w)
+        h.set_option(_lib.OPT_K3_WARPS, k3w)
+        ts, wall = [], []
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(iters + 3):
+            ev0.record()
+            h.cost_and_grad(wl.blank, grads, costs)
+            ev1.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                ts.append(h.last_timings())
+                wall.append(ev0.elapsed_time(ev1))
+        k = np.median(np.array(ts), axis=0)
+        w = float(np.median(wall))
+        print(f"{wl.name} B={wl.B} V={wl.V} rows={wl.rows} k1w={k1w} k3w={k3w}: "
+              f"K1 {k[0]*1e3:7.1f} us ({n4/k[0]/1e6:6.0f} GB/s of 4N)  K2 {k[1]*1e3:7.1f} us  "
+              f"K3 {k[2]*1e3:7.1f} us ({2*n4/k[2]/1e6:6.0f} GB/s of 8N)  call {w*1e3:7.1f} us "
+              f"({3*n4/w/1e6:6.0f} GB/s of 12N, {wl.B/w*1e3:8.0f} utt/s)", flush=True)
+    # cost-only call (K1 + alpha pass, no beta / coefficients / K3)
+    ts = []
+    for i in range(8):
+        h.cost(wl.blank, costs)
+        ts.append(h.last_timings())
+    k = np.median(np.array(ts[3:]), axis=0)
+    print(f"{wl.name} cost-only: K1 {k[0]*1e3:7.1f} us  K2(alpha only) {k[1]*1e3:7.1f} us", flush=True)
+    h.close()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("workloads", nargs="*", default=["c2"])
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--combos", default="8:8,16:8,8:16,16:16")
+    a = ap.parse_args()
+    combos = [tuple(int(x) for x in c.split(":")) for c in a.combos.split(",")]
+    for name in a.workloads:
+        run(name, a.iters, combos)
