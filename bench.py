@@ -141,7 +141,8 @@ def run_reference(args) -> None:
     from oracle import oracle
 
     oracle.build()
-    wl = mr.synth.workload(WORKLOAD)
+    wl = mr.synth.workload(WORKLOAD, B=int(os.environ["MRNNT_BENCH_TEST_B"]) if "MRNNT_BENCH_TEST_B" in os.environ
+                           else None)  # the override exists for tests/test_host_cpu.py only
     kind = "reference" if oracle.have_ref() else "port"
     runner = oracle.run_ref if kind == "reference" else oracle.run
     cores = oracle.num_threads(reference=(kind == "reference"))

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <mutex>
 #include <vector>
 
 #include "../status.h"
@@ -50,16 +51,39 @@ inline const DeviceInfo &device_info() {
 }
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) costs host microseconds; do it once per (kernel, device).
-// `cache` is a per-kernel-instantiation static table.  A benign race only repeats the call.
+// The table has INTERNAL linkage on purpose: every module that carries these headers (libmonotonic_rnnt.so, a
+// framework extension compiled from the same headers) owns its own copies of the kernels, so the "already
+// configured" state must not be shared between modules (a function-local static in a template would be: it
+// is emitted as a process-wide unique symbol).
 constexpr int kMaxDevices = 32;
+struct SmemAttrEntry {
+    const void *kernel = nullptr;
+    size_t bytes[kMaxDevices] = {};
+};
+static SmemAttrEntry g_smem_attr[48];
+static std::mutex g_smem_attr_mutex;
+
 template <typename Kern>
-inline bool ensure_dynamic_smem(Kern kern, size_t bytes, size_t (&cache)[kMaxDevices]) {
+inline bool ensure_dynamic_smem(Kern kern, size_t bytes) {
+    if (bytes <= 48 * 1024) return true;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return false;
-    if (bytes <= 48 * 1024 || bytes <= cache[dev]) return true;
+    const void *key = reinterpret_cast<const void *>(kern);
+    std::lock_guard<std::mutex> lock(g_smem_attr_mutex);
+    SmemAttrEntry *slot = nullptr;
+    for (auto &e : g_smem_attr) {
+        if (e.kernel == key || e.kernel == nullptr) {
+            slot = &e;
+            break;
+        }
+    }
+    if (slot != nullptr && slot->kernel == key && bytes <= slot->bytes[dev]) return true;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)) != cudaSuccess)
         return false;
-    cache[dev] = bytes;
+    if (slot != nullptr) {
+        slot->kernel = key;
+        slot->bytes[dev] = bytes;
+    }
     return true;
 }
 
@@ -252,8 +276,7 @@ class Engine {
             size_t smem = alignment_ != nullptr ? (static_cast<size_t>(shape_.T_max) + 1) * sizeof(int) : 0;
             if (smem > 48 * 1024) {
                 if (smem > static_cast<size_t>(device_info().max_smem_optin) - 1024) return RNNT_STATUS_INVALID_VALUE;
-                static size_t configured[kMaxDevices] = {};
-                if (!ensure_dynamic_smem(band_kernel, smem, configured)) return RNNT_STATUS_EXECUTION_FAILED;
+                if (!ensure_dynamic_smem(band_kernel, smem)) return RNNT_STATUS_EXECUTION_FAILED;
             }
             band_kernel<<<B_, kBandThreads, smem, stream>>>(T_dev_, S_dev_, shape_.T_max, alignment_, max_shift_,
                                                             align_blank_, ws_.band);
@@ -291,8 +314,7 @@ class Engine {
     template <int NW, int C>
     RNNTStatus launch_k1_tma(int blank, cudaStream_t stream, const DeviceInfo &dev, const StreamTiling &tl) {
         auto kern = k1_lse_tma_kernel<NW, C>;
-        static size_t configured[kMaxDevices] = {};
-        if (!ensure_dynamic_smem(kern, tl.smem_bytes, configured)) return RNNT_STATUS_EXECUTION_FAILED;
+        if (!ensure_dynamic_smem(kern, tl.smem_bytes)) return RNNT_STATUS_EXECUTION_FAILED;
         kern<<<dev.sm_count, (NW + 1) * kWarp, tl.smem_bytes, stream>>>(acts_, labels_, ws_.rowmeta, ws_.lp, ws_.denom,
                                                                          shape_.rows, V_, blank, tl.G, tl.stages);
         return launched();
@@ -320,8 +342,7 @@ class Engine {
     RNNTStatus launch_k2_warp(const K2Args &args, cudaStream_t stream) {
         auto kern = k2_lattice_kernel<K>;
         const size_t smem = k2_smem_bytes(shape_.S_max);
-        static size_t configured[kMaxDevices] = {};
-        if (!ensure_dynamic_smem(kern, smem, configured)) return RNNT_STATUS_EXECUTION_FAILED;
+        if (!ensure_dynamic_smem(kern, smem)) return RNNT_STATUS_EXECUTION_FAILED;
         kern<<<B_, kK2Threads, smem, stream>>>(args, 0);
         return launched();
     }
@@ -342,8 +363,7 @@ class Engine {
         if (states <= 512) return launch_k2_warp<16>(a, stream);
         const size_t smem = (static_cast<size_t>(shape_.S_max) + 2) * sizeof(double);
         if (smem > static_cast<size_t>(dev.max_smem_optin)) return RNNT_STATUS_INVALID_VALUE;
-        static size_t configured[kMaxDevices] = {};
-        if (!ensure_dynamic_smem(k2_lattice_wide_kernel, smem, configured)) return RNNT_STATUS_EXECUTION_FAILED;
+        if (!ensure_dynamic_smem(k2_lattice_wide_kernel, smem)) return RNNT_STATUS_EXECUTION_FAILED;
         k2_lattice_wide_kernel<<<B_, kK2Threads, smem, stream>>>(a, 0);
         return launched();
     }
@@ -352,8 +372,7 @@ class Engine {
     RNNTStatus launch_k3_tma(int blank, cudaStream_t stream, const DeviceInfo &dev, const StreamTiling &tl,
                              float *grads) {
         auto kern = k3_grad_tma_kernel<NW>;
-        static size_t configured[kMaxDevices] = {};
-        if (!ensure_dynamic_smem(kern, tl.smem_bytes, configured)) return RNNT_STATUS_EXECUTION_FAILED;
+        if (!ensure_dynamic_smem(kern, tl.smem_bytes)) return RNNT_STATUS_EXECUTION_FAILED;
         kern<<<dev.sm_count, (NW + 1) * kWarp, tl.smem_bytes, stream>>>(acts_, ws_.coef, grads, shape_.rows, V_, blank,
                                                                          tl.G, tl.stages);
         return launched();

@@ -189,7 +189,7 @@ __device__ __forceinline__ void issue_live_runs(uint32_t mask, float *tile, cons
 }
 
 template <int NW, int C>
-__global__ void __launch_bounds__((NW + 1) * kWarp, 1)
+static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
     k1_lse_tma_kernel(const float *__restrict__ acts, const int *__restrict__ labels,
                       const int *__restrict__ rowmeta, double2 *__restrict__ lp, double *__restrict__ denom,
                       int64_t rows, int V, int blank, int G, int stages) {

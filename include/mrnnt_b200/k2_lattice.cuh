@@ -371,7 +371,7 @@ __device__ __forceinline__ void k2_coef_rows(const K2Args &a, int b) {
 }
 
 template <int K>
-__global__ void __launch_bounds__(kK2Threads) k2_lattice_kernel(K2Args a, int b_begin) {
+static __global__ void __launch_bounds__(kK2Threads) k2_lattice_kernel(K2Args a, int b_begin) {
     extern __shared__ __align__(128) unsigned char k2_smem[];
     const int b = b_begin + blockIdx.x;
     const int warp = threadIdx.x >> 5;

@@ -66,7 +66,7 @@ static __global__ void __launch_bounds__(kGenericWarps * kWarp)
 // Shared memory: [stages][G*V] floats | full[stages] | empty[stages] | pad[stages][32] ints | coef[stages][32] float4
 // ---------------------------------------------------------------------------------------------
 template <int NW>
-__global__ void __launch_bounds__((NW + 1) * kWarp, 1)
+static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
     k3_grad_tma_kernel(const float *__restrict__ acts, const float4 *__restrict__ coef, float *__restrict__ grads,
                        int64_t rows, int V, int blank, int G, int stages) {
     extern __shared__ __align__(128) unsigned char smem_raw[];

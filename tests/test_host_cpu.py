@@ -1,0 +1,201 @@
+"""-m "not gpu": host-side logic -- the C-ABI library loads without a GPU and exports every declared symbol,
+size/validation queries, the no-CPU-fallback behaviour, sharding, synthetic generators, the gloo path."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import fixtures
+import monotonic_rnnt_b200 as mr
+from monotonic_rnnt_b200 import _lib
+from oracle import oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    names = set()
+    for header in ("mrnnt_c_api.h", "rnnt_entrypoint.h"):
+        text = open(os.path.join(ROOT, "include", header)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        text = re.sub(r"//[^\n]*", "", text)
+        names |= set(re.findall(r"\b(mrnnt_\w+|rnnt_loss_grad_gpu|compute_rnnt_loss)\s*\(", text))
+    return names
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    declared = _declared_functions()
+    assert {"compute_rnnt_loss", "mrnnt_cost_and_grad", "rnnt_loss_grad_gpu"} <= declared
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.lib_path()], capture_output=True, text=True).stdout
+    for name in declared:
+        assert re.search(rf"\bT {name}\b", out), name
+    assert b"sm_100a" in lib.mrnnt_build_info()
+
+
+def test_cubin_is_sm100a_with_bulk_copies():
+    """The library carries sm_100a SASS and the streaming kernels really use the TMA engine (UBLKCP)."""
+    res = subprocess.run(["cuobjdump", "-sass", _lib.lib_path()], capture_output=True, text=True)
+    if res.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in res.stdout
+    assert "UBLKCP" in res.stdout and "SYNCS" in res.stdout     # cp.async.bulk + mbarrier
+    assert "REDUX" in res.stdout and "MUFU.EX2" in res.stdout
+
+
+def test_workspace_size_query_and_validation():
+    lib = _lib.load()
+    size = mr.workspace_size([4], [2], 3)
+    assert size > 12 * 56
+    big = mr.workspace_size([150] * 32, [40] * 32, 1000)
+    assert big > 32 * 150 * 41 * 56 and big == mr.workspace_size([150] * 32, [40] * 32, 5000)   # V does not enter
+    for T, S in (([0], [0]), ([2], [3]), ([4], [-1]), ([], [])):
+        with pytest.raises(mr.RNNTError) as e:
+            mr.workspace_size(T, S, 3)
+        assert e.value.status == 2                                      # RNNT_STATUS_INVALID_VALUE
+    assert mr.workspace_size([3], [3], 5) > 0                           # T == S is legal
+    out = ctypes.c_size_t(0)
+    assert lib.mrnnt_get_workspace_size(None, None, 1, 3, ctypes.byref(out)) == 2
+    h = ctypes.c_void_p()
+    assert lib.mrnnt_create(ctypes.byref(h), None, None, 0, None, None, 3, None, None) == 2
+
+
+def test_no_cpu_fallback():
+    c = fixtures.readme_case()
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt)
+    with pytest.raises(RuntimeError, match="GPU-only"):
+        mr.monotonic_rnnt_loss(t(c.acts, torch.float32), t(c.labels, torch.int32), t(c.T, torch.int32),
+                               t(c.S, torch.int32))
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(mr.build, "LIB_PATH", str(tmp_path / "nope.so"))
+    monkeypatch.setattr(mr.build, "up_to_date", lambda: False)
+
+    def boom(*a, **k):
+        raise RuntimeError("nvcc not found")
+    monkeypatch.setattr(mr.build, "build", boom)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under the package or include/ imports, links or dlopens it."""
+    bad = re.compile(r"^\s*(from|import)\s+oracle\b|liboracle|libmrnnt_ref|rnnt_oracle|oracle/_ref", re.M)
+    for top in ("monotonic-rnnt_b200", "include"):
+        for d, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h")):
+                    assert not bad.search(open(os.path.join(d, f)).read()), os.path.join(d, f)
+
+
+# ---- synthetic generators -----------------------------------------------------------------------------
+def test_synth_generator():
+    a = mr.synth.uniform_logits(1000, seed=0)
+    assert a.dtype == np.float32 and a.min() >= 0.0 and a.max() < 1.0
+    assert np.array_equal(mr.synth.uniform_logits(300, 0, 700), a[700:])       # counter based: offsets compose
+    assert not np.array_equal(mr.synth.uniform_logits(1000, seed=1), a)
+    assert abs(float(a.mean()) - 0.5) < 0.05
+    lab = mr.synth.labels_for(8, 40, 1000)
+    assert lab.min() >= 1 and lab.max() <= 999                                  # never blank
+    for name, rows in (("c2", 196800), ("c4", 774400), ("c5", 585600)):
+        wl = mr.synth.workload(name)
+        assert wl.rows == rows and wl.algorithmic_bytes == 12 * rows * wl.V
+    wl = mr.synth.workload("c3")
+    assert wl.T[0] == 400 and wl.S[0] == 80 and (wl.T >= wl.S).all() and wl.T.max() <= 400
+    wl = mr.synth.workload("c5")
+    assert ((wl.alignment != 0).sum(axis=1) == wl.S).all()                      # a valid alignment per utterance
+
+
+# ---- sharding -----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+def test_partition_covers_and_balances(world):
+    wl = mr.synth.workload("c3")
+    parts = mr.shard.partition_contiguous(wl.T, wl.S, world)
+    assert len(parts) == world and parts[0][0] == 0 and parts[-1][1] == wl.B
+    assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+    w = wl.T.astype(np.int64) * (wl.S + 1)
+    loads = [int(w[a:b].sum()) for a, b in parts]
+    assert min(loads) > 0 and max(loads) <= 1.35 * (sum(loads) / world)
+    fixed = mr.shard.partition_contiguous([150] * 32, [40] * 32, world)
+    if 32 % world == 0:
+        assert all(b - a == 32 // world for a, b in fixed)
+    few = mr.shard.partition_contiguous([5, 6], [1, 2], 4)                      # B < world: empty tails
+    assert sum(b - a for a, b in few) == 2
+
+
+def test_sharded_results_equal_whole_batch():
+    """Utterances are independent: running each shard on its own (labels / alignment re-strided to the shard's
+    own maxima, as the ABI requires) reproduces the whole-batch costs and gradients bit for bit."""
+    case = fixtures.random_case("shardme", 77, B=7, V=11, T_range=(4, 25), S_range=(0, 9))
+    al = fixtures.random_alignment(np.random.default_rng(3), case.T, case.S, case.labels)
+    whole = oracle.run(case.acts, case.labels, case.T, case.S, case.V, alignment=al, max_shift=1)
+    for world in (2, 3):
+        costs, grads = [], []
+        for b0, b1 in mr.shard.partition_contiguous(case.T, case.S, world):
+            sh = mr.shard.make_shard(case.T, case.S, case.labels, b0, b1, alignment=al)
+            r = oracle.run(case.acts[sh.row0:sh.row1], sh.labels, sh.T, sh.S, case.V, alignment=sh.alignment,
+                           max_shift=1)
+            costs.append(r.costs)
+            grads.append(r.grads)
+        assert np.array_equal(np.concatenate(costs), whole.costs)
+        assert np.array_equal(np.concatenate(grads), whole.grads)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    case = fixtures.random_case("gloo", 5, B=6, V=9, T_range=(3, 15), S_range=(0, 6))
+    b0, b1 = mr.shard.partition_contiguous(case.T, case.S, world)[rank]
+    sh = mr.shard.make_shard(case.T, case.S, case.labels, b0, b1)
+    r = oracle.run(case.acts[sh.row0:sh.row1], sh.labels, sh.T, sh.S, case.V)
+    total = mr.shard.allreduce_cost_sum(torch.from_numpy(r.costs))        # the path's ONE collective
+    q.put((rank, float(total), b0, b1))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_world_size_2_cost_allreduce():
+    import torch.multiprocessing as tmp
+    ctx = tmp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    case = fixtures.random_case("gloo", 5, B=6, V=9, T_range=(3, 15), S_range=(0, 6))
+    whole = oracle.run(case.acts, case.labels, case.T, case.S, case.V)
+    for rank, total, b0, b1 in got:
+        assert abs(total - float(whole.costs.sum(dtype=np.float64))) < 1e-3
+    assert sorted((b0, b1) for _, _, b0, b1 in got)[0][0] == 0
+
+
+def test_bench_reference_arm_schema():
+    env = dict(os.environ, MRNNT_BENCH_TEST_B="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "utt/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
+    # other ranks of a torchrun launch exit 0 without work
+    env["RANK"] = "1"
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1"],
+                         capture_output=True, text=True, env=env, timeout=60)
+    assert out.returncode == 0 and out.stdout.strip() == ""
