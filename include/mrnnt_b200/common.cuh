@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
+#include <cmath>
 #include <cstdint>
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 900)
@@ -26,6 +27,46 @@ constexpr double kNegInf = -__builtin_huge_val();
 // rowmeta encoding (see plan.cuh)
 constexpr int kRowNoLabel = -1;  // live row with s == S_b (no label transition leaves it)
 constexpr int kRowDead = -2;     // alpha(t-1, s) is outside the lattice: gradient row is exactly zero
+
+// ---------------------------------------------------------------------------------------------
+// Scaled linear-domain numbers used by the lattice (K2): value = m * 2^e with a float mantissa and an int
+// exponent per cell, so the recursion is multiply-add instead of log-sum-exp and still cannot underflow.
+// Non-zero mantissas are >= 1 (weights are normalised to [1,2], the state is brought back to [1,2) once per
+// chunk of frames, see cell_renorm).  Zero (an unreachable cell, a masked transition) is m == 0 with the
+// exponent kZeroExp: far below every exponent a non-zero value can have, so that a zero term always loses
+// the exponent comparison of cell_add without any test of the mantissa; products and sums of zeros drift
+// further down (by at most kZeroExp per frame, 16 frames between renormalisations) and never come back.
+// ---------------------------------------------------------------------------------------------
+struct __align__(8) Cell {  // alpha / beta lattice cell
+    float m;
+    int e;
+};
+struct __align__(16) Weight {  // transition weights of one packed row: p(blank) = mb * 2^eb, p(label) = ml * 2^el
+    float mb;
+    int eb;
+    float ml;
+    int el;
+};
+struct __align__(16) RawRow {  // what K1 leaves per live packed row (dead rows are never read)
+    float xb;  // logit of the blank
+    float xl;  // logit of the row's label (-inf without one)
+    float dh;  // dh + dl = -log2 sum_v exp(x[v]) as an unevaluated sum of two floats (~48 bits), so that
+    float dl;  //           log2 p(v) = x[v] * log2(e) + dh + dl
+};
+constexpr int kZeroExp = -(1 << 24);  // non-zero values reach down to 2^-(2^23); 17 frames of drift stay below 2^29
+
+// error-free sum of two floats: s + err == a + b exactly
+__host__ __device__ inline void two_sum(float a, float b, float &s, float &err) {
+    s = a + b;
+    const float bb = s - a;
+    err = (a - (s - bb)) + (b - bb);
+}
+
+// natural log of m * 2^e in double (-inf for a zero cell)
+__host__ __device__ inline double cell_log(float m, int e) {
+    if (!(m > 0.0f)) return kNegInf;
+    return (static_cast<double>(e) + log2(static_cast<double>(m))) * kLn2D;
+}
 
 // ---------------------------------------------------------------------------------------------
 // shared-memory addresses, mbarrier, bulk async copy
@@ -145,54 +186,70 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// log2 of a positive finite float to ~6e-8 absolute: exponent exactly, mantissa in [1,2) through
-// log2f (whose error is relative to a result below 1).
-__device__ __forceinline__ double log2_split(float s) {
-    int e;
-    const float f = frexpf(s, &e);  // s = f * 2^e, f in [0.5, 1)
-    return static_cast<double>(e - 1) + static_cast<double>(log2f(f + f));
+// 2^-k for 0 <= k < 127; exactly 0 for k >= 127 (the scaled term is then either an exact zero or ~2^-100 below
+// the other operand's resolution)
+__device__ __forceinline__ float pow2_neg(unsigned k) {
+    return __int_as_float(static_cast<int>(min(k, 127u)) * -0x00800000 + 0x3f800000);
 }
 
-// log(exp(x) + exp(y)) for the lattice recursion (reference rnnt_helper.h:21-30).  The large
-// parts are kept in double (|alpha| grows like T*log V, where a float ulp is already ~6e-5),
-// only the bounded correction log1p(exp(-|x-y|)) in (0, ln 2] is evaluated in float.
-__device__ __forceinline__ double lse_pair(double x, double y) {
-    const double mx = fmax(x, y);
-    const double mn = fmin(x, y);
-    const float d = static_cast<float>(mn - mx);  // <= 0; NaN only when both are -inf
-    const float r = log1pf(expf(d));
-    const double out = mx + static_cast<double>(r);
-    return (mn == kNegInf) ? mx : out;
+// (m1,e1) + (m2,e2) in the scaled linear domain.  Inputs are non-negative; zeros carry exponents around
+// kZeroExp (see above), so the larger exponent is always the right common exponent.
+__device__ __forceinline__ Cell cell_add(float m1, int e1, float m2, int e2) {
+    const int d = e1 - e2;
+    const bool first = d >= 0;
+    const float big = first ? m1 : m2;
+    const float small = first ? m2 : m1;
+    Cell r;
+    r.m = fmaf(small, pow2_neg(static_cast<unsigned>(abs(d))), big);
+    r.e = max(e1, e2);
+    return r;
 }
 
-// Same, with the correction term from the MUFU units: 2^(d log2 e) and log2(1 + u) in float
-// (absolute error of the term ~1e-7; it enters a double accumulator, so errors add up like a random
-// walk over the T frames instead of being amplified by |alpha|).  ~70 cycles of dependent latency
-// instead of ~250 for expf + log1pf; the lattice recursion is a pure latency chain, so this is what
-// sets the duration of K2.
-__device__ __forceinline__ double lse_pair_fast(double x, double y) {
-    const bool gt = x > y;
-    const double mx = gt ? x : y;
-    const double mn = gt ? y : x;
-    const float d = __double2float_rn(mn - mx);  // <= 0, -inf when only one side is -inf, NaN when both are
-    const float u = ex2_approx(d * kLog2e);
-    float r;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + u));
-    const double out = mx + static_cast<double>(r * 0.69314718055994531f);
-    return (mx == kNegInf) ? kNegInf : out;
+// bring the mantissa back to [1,2) (exact: only exponent bits move); zeros become the canonical zero
+__device__ __forceinline__ void cell_renorm(float &m, int &e) {
+    const int bits = __float_as_int(m);
+    const bool zero = (m == 0.0f);
+    e = zero ? kZeroExp : e + (bits >> 23) - 127;
+    m = zero ? 0.0f : __int_as_float((bits & 0x007fffff) | 0x3f800000);
 }
 
-// lse_pair_fast with the band mask folded into the same select: -inf when the cell is outside the band.
-__device__ __forceinline__ double lse_pair_masked(double x, double y, bool in_band) {
-    const bool gt = x > y;
-    const double mx = gt ? x : y;
-    const double mn = gt ? y : x;
-    const float d = __double2float_rn(mn - mx);
-    const float u = ex2_approx(d * kLog2e);
-    float r;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + u));
-    const double out = mx + static_cast<double>(r * 0.69314718055994531f);
-    return (in_band && mx != kNegInf) ? out : kNegInf;
+// Transition weight p = 2^(x * log2(e) + dh + dl) as m * 2^e with m in [2^-1/2, 2^1/2], in float arithmetic
+// only (the lattice kernel converts two weights per row on the fly; double-precision instructions are too
+// slow for that).  y = x*log2(e) + dh + dl is formed as an unevaluated float pair (exact product split,
+// error-free sum), its nearest integer becomes the exponent, and 2^(fraction) is a degree-7 Taylor
+// polynomial (truncation 5e-9; the result carries about one float ulp of rounding).  `ok == false`, -inf, NaN
+// and anything below 2^-(2^22) give the zero weight.
+__device__ __forceinline__ void weight_from_logit(float x, float dh, float dl, bool ok, float &m, int &e) {
+    constexpr float kL1 = 1.44269502162933349609375f;  // float(log2 e)
+    constexpr float kL2 = 1.925963033500011e-8f;       // log2 e - kL1
+    constexpr float kMagic = 12582912.0f;              // 1.5 * 2^23: adding it rounds to the nearest integer
+    const float ph = x * kL1;
+    const float pl = fmaf(x, kL2, fmaf(x, kL1, -ph));
+    float s, err;
+    two_sum(ph, dh, s, err);
+    const float lo = (err + pl) + dl;
+    const float r = s + kMagic;
+    const float n = r - kMagic;
+    const float f = (s - n) + lo;  // in [-1/2, 1/2] (+- a few ulp)
+    float p = 1.5252733804059841e-05f;
+    p = fmaf(p, f, 1.5403530393381608e-04f);
+    p = fmaf(p, f, 1.3333558146428443e-03f);
+    p = fmaf(p, f, 9.6181291076284770e-03f);
+    p = fmaf(p, f, 5.5504108664821580e-02f);
+    p = fmaf(p, f, 2.4022650695910072e-01f);
+    p = fmaf(p, f, 6.9314718055994531e-01f);
+    p = fmaf(p, f, 1.0f);
+    ok = ok && (s > -4194304.0f) && (s < 4194304.0f);
+    m = ok ? p : 0.0f;
+    e = ok ? __float_as_int(r) - __float_as_int(kMagic) : kZeroExp;
+}
+
+// log2 of a positive finite float as an integer part and a float in [0,1) (absolute error ~6e-8)
+__device__ __forceinline__ void log2_parts(float v, int &ip, float &fp) {
+    int ex;
+    const float f = frexpf(v, &ex);  // v = f * 2^ex, f in [0.5, 1)
+    ip = ex - 1;
+    fp = log2f(f + f);
 }
 
 }  // namespace mrnnt

@@ -253,6 +253,8 @@ class Engine {
 
     // Force the generic (non-TMA) streaming kernels; used by the tests to cross-check both variants.
     void set_force_generic(bool v) { force_generic_ = v; }
+    // Upper limit for the CTAs per utterance of the lattice kernel's coefficient phase (0: automatic).
+    void set_k2_parts(int parts) { k2_parts_ = parts < 0 ? 0 : parts; }
     // Consumer warps per CTA of the streaming kernels (8 or 16); tuning knob for the bench.
     void set_stream_warps(int k1, int k3) {
         if (k1 == 8 || k1 == 16) k1_warps_ = k1;
@@ -268,7 +270,7 @@ class Engine {
 
     RNNTStatus setup(cudaStream_t stream) {
         if (plan_dirty_) {
-            plan_row_start_kernel<<<1, kPlanThreads, 0, stream>>>(T_dev_, S_dev_, B_, ws_.row_start);
+            plan_row_start_kernel<<<1, kPlanThreads, 0, stream>>>(T_dev_, S_dev_, B_, ws_.row_start, ws_.k2_flags);
             if (launched() != RNNT_STATUS_SUCCESS) return RNNT_STATUS_EXECUTION_FAILED;
             plan_dirty_ = false;
         }
@@ -315,8 +317,8 @@ class Engine {
     RNNTStatus launch_k1_tma(int blank, cudaStream_t stream, const DeviceInfo &dev, const StreamTiling &tl) {
         auto kern = k1_lse_tma_kernel<NW, C>;
         if (!ensure_dynamic_smem(kern, tl.smem_bytes)) return RNNT_STATUS_EXECUTION_FAILED;
-        kern<<<dev.sm_count, (NW + 1) * kWarp, tl.smem_bytes, stream>>>(acts_, labels_, ws_.rowmeta, ws_.lp, ws_.denom,
-                                                                         shape_.rows, V_, blank, tl.G, tl.stages);
+        kern<<<dev.sm_count, (NW + 1) * kWarp, tl.smem_bytes, stream>>>(acts_, labels_, ws_.rowmeta, ws_.lp, shape_.rows,
+                                                                         V_, blank, tl.G, tl.stages);
         return launched();
     }
 
@@ -334,37 +336,50 @@ class Engine {
             return tl.warps == 8 ? launch_k1_nw<8>(blank, stream, dev, tl) : launch_k1_nw<16>(blank, stream, dev, tl);
         }
         k1_lse_generic_kernel<<<generic_grid(dev), kGenericWarps * kWarp, 0, stream>>>(
-            acts_, labels_, ws_.rowmeta, ws_.lp, ws_.denom, shape_.rows, V_, blank);
+            acts_, labels_, ws_.rowmeta, ws_.lp, shape_.rows, V_, blank);
         return launched();
     }
 
     template <int K>
     RNNTStatus launch_k2_warp(const K2Args &args, cudaStream_t stream) {
         auto kern = k2_lattice_kernel<K>;
-        const size_t smem = k2_smem_bytes(shape_.S_max);
+        const size_t smem = k2_smem_bytes(shape_.S_max, args.row_warps);
         if (!ensure_dynamic_smem(kern, smem)) return RNNT_STATUS_EXECUTION_FAILED;
-        kern<<<B_, kK2Threads, smem, stream>>>(args, 0);
+        kern<<<B_ * args.parts, kK2Threads, smem, stream>>>(args);
         return launched();
     }
 
     RNNTStatus launch_k2(int blank, cudaStream_t stream, const DeviceInfo &dev, bool need_beta) {
         K2Args a;
         a.T = T_dev_; a.S = S_dev_; a.labels = labels_; a.row_start = ws_.row_start; a.band = ws_.band;
-        a.lp = ws_.lp; a.denom = ws_.denom; a.alpha = ws_.alpha; a.beta = ws_.beta; a.coef = ws_.coef;
+        a.lp = ws_.lp; a.wts = ws_.wts; a.alpha = ws_.alpha; a.beta = ws_.beta; a.coef = ws_.coef;
         a.ll_fwd = ws_.ll_fwd; a.ll_bwd = ws_.ll_bwd; a.costs = ws_.costs;
         a.T_max = shape_.T_max; a.S_max = shape_.S_max; a.V = V_; a.blank = blank;
         a.need_beta = need_beta ? 1 : 0;
         a.chunk_frames = k2_chunk_frames(shape_.S_max);
+        // Coefficient phase: spread every utterance over `parts` CTAs while the whole grid still fits on the
+        // machine at one CTA per SM (the extra CTAs wait for their utterance's recursion on idle SMs).
+        int parts = need_beta ? dev.sm_count / B_ : 1;
+        parts = parts < 1 ? 1 : (parts > kK2MaxParts ? kK2MaxParts : parts);
+        if (k2_parts_ > 0 && k2_parts_ < parts) parts = k2_parts_;
+        a.parts = parts;
+        a.flags = ws_.k2_flags;
+        if (++epoch_ == 0u) ++epoch_;
+        a.epoch = epoch_;
         const int states = shape_.S_max + 1;
-        if (states <= 32) return launch_k2_warp<1>(a, stream);
-        if (states <= 64) return launch_k2_warp<2>(a, stream);
-        if (states <= 128) return launch_k2_warp<4>(a, stream);
-        if (states <= 256) return launch_k2_warp<8>(a, stream);
-        if (states <= 512) return launch_k2_warp<16>(a, stream);
-        const size_t smem = (static_cast<size_t>(shape_.S_max) + 2) * sizeof(double);
+        const int K = k2_states_per_lane(states);
+        if (K > 0) {
+            a.row_warps = k2_row_warps(states, K);
+            a.chunk_bufs = k2_chunk_bufs(a.row_warps);
+            return K == 1 ? launch_k2_warp<1>(a, stream) : K == 2 ? launch_k2_warp<2>(a, stream) : launch_k2_warp<4>(a, stream);
+        }
+        a.parts = 1;
+        a.row_warps = 0;
+        a.chunk_bufs = 0;
+        const size_t smem = (static_cast<size_t>(shape_.S_max) + 2) * sizeof(Cell);
         if (smem > static_cast<size_t>(dev.max_smem_optin)) return RNNT_STATUS_INVALID_VALUE;
         if (!ensure_dynamic_smem(k2_lattice_wide_kernel, smem)) return RNNT_STATUS_EXECUTION_FAILED;
-        k2_lattice_wide_kernel<<<B_, kK2Threads, smem, stream>>>(a, 0);
+        k2_lattice_wide_kernel<<<B_, kK2Threads, smem, stream>>>(a);
         return launched();
     }
 
@@ -411,6 +426,8 @@ class Engine {
     bool force_generic_ = false;
     int k1_warps_ = 16;
     int k3_warps_ = 16;
+    int k2_parts_ = 0;     // 0: automatic
+    unsigned epoch_ = 0u;  // launch counter published through Workspace::k2_flags
     bool timing_ = false;
     cudaEvent_t ev_[4] = {};
 };

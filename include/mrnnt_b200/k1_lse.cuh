@@ -5,8 +5,9 @@
 // reads of the logits with 4-byte loads and two stream syncs) and the strided `log_p` gathers inside
 // the alpha/beta kernels (gpu_rnnt_kernel.h:80-84,144-149).  CPU twin: cpu_rnnt.h:98-115.
 //
-//   denom[row] = -(max_v x + log sum_v exp(x - max))            (reference sign convention)
-//   lp[row]    = (x[blank] + denom, x[label(b,s)] + denom)
+//   D = -log2 sum_v exp(x[v])  as two floats (dh, dl)           (log2 p(v) = x[v] log2 e + D; the reference's
+//                                                                 denominator is D ln 2, reduce.h:112-139)
+//   lp[row] = (x[blank], x[label(b,s)], dh, dl)                   one 16-byte record per live row
 //
 // Streaming design (HBM-bound; algorithmic bytes = 4*V per live row, nothing for dead rows):
 //   * persistent CTAs, one per SM; the flat row space is cut into tiles of G consecutive rows;
@@ -50,15 +51,27 @@ __device__ __forceinline__ void exp_acc(const float4 &a, float neg, float &s0, f
 }
 
 // From the warp-wide max (times log2 e, rounded once and used for every term) and the warp-wide sum of
-// 2^(x log2e - ML): the natural-log denominator -(max + log sum exp(x - max)), in double.
-__device__ __forceinline__ double lse_finish(float ML, float sum) {
-    return -(static_cast<double>(ML) + log2_split(sum)) * kLn2D;
+// 2^(x log2e - ML): the base-2 denominator -(ML + log2 sum) = -log2 sum_v exp(x[v]) as an unevaluated sum of
+// two floats (error-free additions; the only error is log2f's ~6e-8 on a value in [0,1)).
+struct Denominator {
+    float hi, lo;
+};
+__device__ __forceinline__ Denominator lse_finish(float ML, float sum) {
+    int ip;
+    float fp, h, l1, h2, l2;
+    log2_parts(sum, ip, fp);
+    two_sum(ML, static_cast<float>(ip), h, l1);
+    two_sum(h, fp, h2, l2);
+    Denominator d;
+    d.hi = -h2;
+    d.lo = -(l1 + l2);
+    return d;
 }
 
 // One row resident in shared memory (16-byte aligned, V4 float4).  C > 0: the lane's <= C float4 live
 // in registers (V4 <= 32*C); C == 0: two passes over shared memory, any V4.
 template <int C>
-__device__ __forceinline__ double row_denominator(const float4 *__restrict__ x4, int V4, int lane) {
+__device__ __forceinline__ Denominator row_denominator(const float4 *__restrict__ x4, int V4, int lane) {
     const float4 ninf = make_float4(kNegInfF, kNegInfF, kNegInfF, kNegInfF);
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     float ML;
@@ -88,12 +101,17 @@ __device__ __forceinline__ double row_denominator(const float4 *__restrict__ x4,
     return lse_finish(ML, warp_sum_f((s0 + s1) + (s2 + s3)));
 }
 
-// What lane 0 writes for one row.
-__device__ __forceinline__ void k1_store_row(double2 *__restrict__ lp, double *__restrict__ denom, int64_t row,
-                                             double den, float x_blank, float x_label, bool has_label) {
-    denom[row] = den;
-    lp[row] = make_double2(static_cast<double>(x_blank) + den,
-                           has_label ? static_cast<double>(x_label) + den : kNegInf);
+// What lane 0 writes for one live row: the two gathered logits and the denominator (one 16-byte store).  The
+// lattice kernel turns them into transition weights on its otherwise idle warps (k2_lattice.cuh); dead rows
+// are never read again, so nothing is written for them.
+__device__ __forceinline__ void k1_store_row(RawRow *__restrict__ lp, int64_t row, const Denominator &den,
+                                             float x_blank, float x_label) {
+    RawRow r;
+    r.xb = x_blank;
+    r.xl = x_label;
+    r.dh = den.hi;
+    r.dl = den.lo;
+    lp[row] = r;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -103,31 +121,24 @@ constexpr int kGenericWarps = 8;
 
 static __global__ void __launch_bounds__(kGenericWarps * kWarp)
     k1_lse_generic_kernel(const float *__restrict__ acts, const int *__restrict__ labels,
-                          const int *__restrict__ rowmeta, double2 *__restrict__ lp, double *__restrict__ denom,
-                          int64_t rows, int V, int blank) {
+                          const int *__restrict__ rowmeta, RawRow *__restrict__ lp, int64_t rows, int V, int blank) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * kGenericWarps + (threadIdx.x >> 5);
     const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kGenericWarps;
     for (int64_t row = warp0; row < rows; row += nwarps) {
         const int meta = rowmeta[row];
-        if (meta == kRowDead) {
-            if (lane == 0) {
-                denom[row] = 0.0;
-                lp[row] = make_double2(0.0, 0.0);
-            }
-            continue;
-        }
+        if (meta == kRowDead) continue;
         const float *x = acts + row * V;
         float m = kNegInfF;
         for (int v = lane; v < V; v += kWarp) m = fmaxf(m, __ldg(x + v));
         const float ML = warp_max_redux(m) * kLog2e;
         float s = 0.f;
         for (int v = lane; v < V; v += kWarp) s += ex2_approx(fmaf(__ldg(x + v), kLog2e, -ML));
-        const double den = lse_finish(ML, warp_sum_f(s));
+        const Denominator den = lse_finish(ML, warp_sum_f(s));
         if (lane == 0) {
             const int lab = meta >= 0 ? __ldg(labels + meta) : -1;
             const bool has = lab >= 0 && lab < V;
-            k1_store_row(lp, denom, row, den, __ldg(x + blank), has ? __ldg(x + lab) : 0.0f, has);
+            k1_store_row(lp, row, den, __ldg(x + blank), has ? __ldg(x + lab) : kNegInfF);
         }
     }
 }
@@ -191,8 +202,8 @@ __device__ __forceinline__ void issue_live_runs(uint32_t mask, float *tile, cons
 template <int NW, int C>
 static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
     k1_lse_tma_kernel(const float *__restrict__ acts, const int *__restrict__ labels,
-                      const int *__restrict__ rowmeta, double2 *__restrict__ lp, double *__restrict__ denom,
-                      int64_t rows, int V, int blank, int G, int stages) {
+                      const int *__restrict__ rowmeta, RawRow *__restrict__ lp, int64_t rows, int V, int blank,
+                      int G, int stages) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const size_t tile_floats = static_cast<size_t>(G) * V;
     float *tiles = reinterpret_cast<float *>(smem_raw);
@@ -252,21 +263,14 @@ static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
             const int64_t row = (blockIdx.x + k * gridDim.x) * G + r;
             mbar_wait(full + stage, phase);
             const int meta = meta_sh[stage * 32 + r];
-            if (row < rows) {
-                if (meta == kRowDead) {
-                    if (lane == 0) {
-                        denom[row] = 0.0;
-                        lp[row] = make_double2(0.0, 0.0);
-                    }
-                } else {
-                    const float *xrow = tiles + stage * tile_floats + static_cast<size_t>(r) * V;
-                    int lab = -1;
-                    if (lane == 0 && meta >= 0) lab = __ldg(labels + meta);  // latency hides under the row math
-                    const double den = row_denominator<C>(reinterpret_cast<const float4 *>(xrow), V4, lane);
-                    if (lane == 0) {
-                        const bool has = lab >= 0 && lab < V;
-                        k1_store_row(lp, denom, row, den, xrow[blank], has ? xrow[lab] : 0.0f, has);
-                    }
+            if (row < rows && meta != kRowDead) {
+                const float *xrow = tiles + stage * tile_floats + static_cast<size_t>(r) * V;
+                int lab = -1;
+                if (lane == 0 && meta >= 0) lab = __ldg(labels + meta);  // latency hides under the row math
+                const Denominator den = row_denominator<C>(reinterpret_cast<const float4 *>(xrow), V4, lane);
+                if (lane == 0) {
+                    const bool has = lab >= 0 && lab < V;
+                    k1_store_row(lp, row, den, xrow[blank], has ? xrow[lab] : kNegInfF);
                 }
             }
             __syncwarp();

@@ -32,14 +32,15 @@ struct Workspace {
     int64_t *row_start = nullptr;  // [B+1]   first row of each utterance
     int2 *band = nullptr;          // [B*T_max] (min_allowed_s, max_allowed_s) per frame
     int *rowmeta = nullptr;        // [rows]  >=0: index into labels[], kRowNoLabel, kRowDead
-    double2 *lp = nullptr;         // [rows]  (log p(blank | t,s), log p(label_s | t,s))
-    double *denom = nullptr;       // [rows]  -logsumexp_v acts[row, v]   (reference sign convention)
-    double *alpha = nullptr;       // [rows]  full T x (S+1) grid per utterance, -inf outside the band
-    double *beta = nullptr;        // [rows]
+    RawRow *lp = nullptr;          // [rows]  (x[blank], x[label_s], -log2 sum_v exp x[v]) per live row, from K1
+    Weight *wts = nullptr;         // [rows]  transition weights (m * 2^e pairs, band folded in), K2 phase A
+    Cell *alpha = nullptr;         // [rows]  full T x (S+1) grid per utterance (m * 2^e), zero outside the band
+    Cell *beta = nullptr;          // [rows]
     float4 *coef = nullptr;        // [rows]  per-row gradient coefficients, see k2_lattice.cuh
     double *ll_fwd = nullptr;      // [B]     alpha(T-1, S)
     double *ll_bwd = nullptr;      // [B]     beta(0, 0)  (diagnostic, as in the reference)
     float *costs = nullptr;        // [B]     -ll_fwd
+    unsigned *k2_flags = nullptr;  // [2B]    per utterance: phase-A arrivals, epoch of the last recursion (k2_lattice.cuh)
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -48,7 +49,7 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 // (k2_lattice.cuh); the two arrays therefore carry this much never-consumed slack on both sides.
 constexpr int kPrefetchFrames = 8;
 inline size_t lp_slack_bytes(const Shape &sh) {
-    return align_up(static_cast<size_t>(kPrefetchFrames) * (static_cast<size_t>(sh.S_max) + 1) * sizeof(double2), 256);
+    return align_up(static_cast<size_t>(kPrefetchFrames) * (static_cast<size_t>(sh.S_max) + 1) * sizeof(RawRow), 256);
 }
 constexpr size_t kBandSlackBytes = 256;  // >= kPrefetchFrames * sizeof(int2)
 
@@ -61,11 +62,13 @@ inline size_t workspace_bytes(const Shape &sh) {
     n += align_up((B + 1) * sizeof(int64_t), 256);
     n += align_up(B * static_cast<size_t>(sh.T_max) * sizeof(int2), 256) + 2 * kBandSlackBytes;
     n += align_up(rows * sizeof(int), 256);
-    n += align_up(rows * sizeof(double2), 256) + 2 * lp_slack_bytes(sh);
-    n += 3 * align_up(rows * sizeof(double), 256);
+    n += align_up(rows * sizeof(RawRow), 256) + 2 * lp_slack_bytes(sh);
+    n += align_up(rows * sizeof(Weight), 256);
+    n += 2 * align_up(rows * sizeof(Cell), 256);
     n += align_up(rows * sizeof(float4), 256);
     n += 2 * align_up(B * sizeof(double), 256);
     n += align_up(B * sizeof(float), 256);
+    n += align_up(2 * B * sizeof(unsigned), 256);
     return n;
 }
 
@@ -85,31 +88,35 @@ inline Workspace carve_workspace(void *base, const Shape &sh) {
     take(kBandSlackBytes);
     w.rowmeta = reinterpret_cast<int *>(take(rows * sizeof(int)));
     take(lp_slack_bytes(sh));
-    w.lp = reinterpret_cast<double2 *>(take(rows * sizeof(double2)));
+    w.lp = reinterpret_cast<RawRow *>(take(rows * sizeof(RawRow)));
     take(lp_slack_bytes(sh));
-    w.denom = reinterpret_cast<double *>(take(rows * sizeof(double)));
-    w.alpha = reinterpret_cast<double *>(take(rows * sizeof(double)));
-    w.beta = reinterpret_cast<double *>(take(rows * sizeof(double)));
+    w.wts = reinterpret_cast<Weight *>(take(rows * sizeof(Weight)));
+    w.alpha = reinterpret_cast<Cell *>(take(rows * sizeof(Cell)));
+    w.beta = reinterpret_cast<Cell *>(take(rows * sizeof(Cell)));
     w.coef = reinterpret_cast<float4 *>(take(rows * sizeof(float4)));
     w.ll_fwd = reinterpret_cast<double *>(take(B * sizeof(double)));
     w.ll_bwd = reinterpret_cast<double *>(take(B * sizeof(double)));
     w.costs = reinterpret_cast<float *>(take(B * sizeof(float)));
+    w.k2_flags = reinterpret_cast<unsigned *>(take(2 * B * sizeof(unsigned)));
     return w;
 }
 
 // ---------------------------------------------------------------------------------------------
 // row_start[b] = sum_{b' < b} T_b' * (S_b' + 1)      (one CTA; block-wide exclusive scan, 64-bit)
+// Also clears the per-utterance hand-over flags of the lattice kernel.
 // Replaces the host loops + H2D copies at gpu_workspace_manager.h:262-289.
 // ---------------------------------------------------------------------------------------------
 constexpr int kPlanThreads = 1024;
 
 static __global__ void __launch_bounds__(kPlanThreads) plan_row_start_kernel(const int *__restrict__ T,
                                                                        const int *__restrict__ S, int B,
-                                                                       int64_t *__restrict__ row_start) {
+                                                                       int64_t *__restrict__ row_start,
+                                                                       unsigned *__restrict__ k2_flags) {
     __shared__ int64_t warp_tot[kPlanThreads / kWarp];
     const int tid = threadIdx.x;
     const int per = (B + kPlanThreads - 1) / kPlanThreads;
     const int b0 = tid * per;
+    for (int b = tid; b < 2 * B; b += kPlanThreads) k2_flags[b] = 0u;
     int64_t local = 0;
     for (int i = 0; i < per; ++i) {
         const int b = b0 + i;

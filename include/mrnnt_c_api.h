@@ -68,17 +68,18 @@ enum {
     MRNNT_OPT_FORCE_GENERIC = 1, /* value != 0: use the generic (non-TMA) streaming kernels */
     MRNNT_OPT_TIMING = 2,        /* value != 0: record CUDA events around K1 / K2 / K3 of every call */
     MRNNT_OPT_K1_WARPS = 3,      /* consumer warps per CTA of K1 (8 or 16)                              */
-    MRNNT_OPT_K3_WARPS = 4       /* consumer warps per CTA of K3 (8 or 16)                              */
+    MRNNT_OPT_K3_WARPS = 4,      /* consumer warps per CTA of K3 (8 or 16)                              */
+    MRNNT_OPT_K2_PARTS = 5       /* upper limit of CTAs per utterance in K2's coefficient phase (0: auto) */
 };
 RNNTStatus mrnnt_set_option(mrnnt_handle_t h, int option, int value);
 /* Durations in ms of K1, K2, K3 of the last call (MRNNT_OPT_TIMING on, stream synchronised). */
 RNNTStatus mrnnt_last_timings(mrnnt_handle_t h, float ms_k1_k2_k3[3]);
 
 enum {
-    MRNNT_DBG_DENOM = 1,    /* double [rows]                                 */
-    MRNNT_DBG_ALPHA = 2,    /* double [rows], -inf outside the band          */
-    MRNNT_DBG_BETA = 3,     /* double [rows]                                 */
-    MRNNT_DBG_LP = 4,       /* double [rows][2] (blank, label)               */
+    MRNNT_DBG_DENOM = 1,    /* double [rows] (meaningful for live rows)         */
+    MRNNT_DBG_ALPHA = 2,    /* double [rows] (log alpha), -inf outside the band */
+    MRNNT_DBG_BETA = 3,     /* double [rows] (log beta)                      */
+    MRNNT_DBG_LP = 4,       /* double [rows][2] (log p blank, log p label)   */
     MRNNT_DBG_BAND = 5,     /* int32  [B][T_max][2] (min, max allowed s)     */
     MRNNT_DBG_ROWMETA = 6,  /* int32  [rows]                                 */
     MRNNT_DBG_LL = 7,       /* double [2][B] (ll_forward, ll_backward)       */

@@ -8,6 +8,7 @@
 // so that the reference's framework bindings can compile the same kernels from `-I include` alone.
 #include <cstdio>
 #include <new>
+#include <vector>
 
 #include "gpu_rnnt.h"
 #include "gpu_workspace_manager.h"
@@ -162,6 +163,9 @@ RNNTStatus mrnnt_set_option(mrnnt_handle_t h, int option, int value) {
         case MRNNT_OPT_K3_WARPS:
             h->manager.engine().set_stream_warps(0, value);
             return RNNT_STATUS_SUCCESS;
+        case MRNNT_OPT_K2_PARTS:
+            h->manager.engine().set_k2_parts(value);
+            return RNNT_STATUS_SUCCESS;
         default:
             return RNNT_STATUS_INVALID_VALUE;
     }
@@ -182,10 +186,40 @@ RNNTStatus mrnnt_debug_copy(mrnnt_handle_t h, int what, void *dst_host, size_t d
     const void *src = nullptr;
     size_t bytes = 0;
     switch (what) {
-        case MRNNT_DBG_DENOM: src = w.denom; bytes = rows * sizeof(double); break;
-        case MRNNT_DBG_ALPHA: src = w.alpha; bytes = rows * sizeof(double); break;
-        case MRNNT_DBG_BETA: src = w.beta; bytes = rows * sizeof(double); break;
-        case MRNNT_DBG_LP: src = w.lp; bytes = rows * sizeof(double2); break;
+        case MRNNT_DBG_DENOM:
+        case MRNNT_DBG_LP: {
+            // K1 leaves (x_blank, x_label, denominator) per live row; handed out as denominators / log-probs
+            const size_t per_row = what == MRNNT_DBG_LP ? 2 : 1;
+            if (dst_bytes < rows * per_row * sizeof(double)) return RNNT_STATUS_INVALID_VALUE;
+            std::vector<mrnnt::RawRow> tmp(rows);
+            if (cudaDeviceSynchronize() != cudaSuccess) return RNNT_STATUS_EXECUTION_FAILED;
+            if (cudaMemcpy(tmp.data(), w.lp, rows * sizeof(mrnnt::RawRow), cudaMemcpyDeviceToHost) != cudaSuccess)
+                return RNNT_STATUS_MEMOPS_FAILED;
+            double *d = static_cast<double *>(dst_host);
+            for (size_t i = 0; i < rows; ++i) {
+                const double den = (static_cast<double>(tmp[i].dh) + static_cast<double>(tmp[i].dl)) * mrnnt::kLn2D;
+                if (what == MRNNT_DBG_DENOM) {
+                    d[i] = den;
+                } else {
+                    d[2 * i] = static_cast<double>(tmp[i].xb) + den;
+                    d[2 * i + 1] = static_cast<double>(tmp[i].xl) + den;
+                }
+            }
+            return RNNT_STATUS_SUCCESS;
+        }
+        case MRNNT_DBG_ALPHA:
+        case MRNNT_DBG_BETA: {
+            // stored as (float mantissa, int exponent) cells; handed out as natural logs in double
+            if (dst_bytes < rows * sizeof(double)) return RNNT_STATUS_INVALID_VALUE;
+            std::vector<mrnnt::Cell> tmp(rows);
+            if (cudaDeviceSynchronize() != cudaSuccess) return RNNT_STATUS_EXECUTION_FAILED;
+            if (cudaMemcpy(tmp.data(), what == MRNNT_DBG_ALPHA ? w.alpha : w.beta, rows * sizeof(mrnnt::Cell),
+                           cudaMemcpyDeviceToHost) != cudaSuccess)
+                return RNNT_STATUS_MEMOPS_FAILED;
+            double *d = static_cast<double *>(dst_host);
+            for (size_t i = 0; i < rows; ++i) d[i] = mrnnt::cell_log(tmp[i].m, tmp[i].e);
+            return RNNT_STATUS_SUCCESS;
+        }
         case MRNNT_DBG_BAND: src = w.band; bytes = B * static_cast<size_t>(sh.T_max) * sizeof(int2); break;
         case MRNNT_DBG_ROWMETA: src = w.rowmeta; bytes = rows * sizeof(int); break;
         case MRNNT_DBG_ROWSTART: src = w.row_start; bytes = (B + 1) * sizeof(int64_t); break;

@@ -1,64 +1,80 @@
-// Development aid: cycles per frame of the REAL K2 alpha/beta passes (k2_lattice.cuh) on synthetic lp data,
-// one CTA, with clock64 around each pass.
+// Development aid: where the time of the REAL lattice kernel (k2_lattice.cuh) goes, on synthetic weights.
+//   k2_probe [T] [S] [B] [parts]   -> event time of the kernel, clock64 stamps of the alpha pass of utterance 0
+#define MRNNT_K2_TRACE
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 #include <cuda_runtime.h>
 #include "../include/mrnnt_b200/k2_lattice.cuh"
 using namespace mrnnt;
 
 template <int K>
-__global__ void __launch_bounds__(kK2Threads) probe(K2Args a, long long *cyc) {
-    extern __shared__ __align__(128) unsigned char sm[];
-    const int warp = threadIdx.x >> 5;
-    long long t0 = clock64();
-    if (warp == 0) { k2_alpha_pass<K>(a, 0, sm); if ((threadIdx.x & 31) == 0) cyc[0] = clock64() - t0; }
-    else if (warp == 1 && a.need_beta) { k2_beta_pass<K>(a, 0, sm + (kK2ChunkBufs * (size_t)a.chunk_frames * (a.S_max + 1) * sizeof(double2) + 64)); if ((threadIdx.x & 31) == 0) cyc[1] = clock64() - t0; }
-    __syncthreads();
-    long long t1 = clock64();
-    if (a.need_beta) k2_coef_rows(a, 0);
-    __syncthreads();
-    if (threadIdx.x == 0) { cyc[2] = clock64() - t1; cyc[3] = clock64() - t0; }
+static float run(const K2Args &a, int B, size_t sm, int reps) {
+    cudaFuncSetAttribute(k2_lattice_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    K2Args b = a;
+    float best = 1e9f;
+    for (int r = 0; r < reps; ++r) {
+        b.epoch = a.epoch + r;
+        cudaEventRecord(e0);
+        k2_lattice_kernel<K><<<B * a.parts, kK2Threads, sm>>>(b);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    return best;
 }
 
 int main(int argc, char **argv) {
     const int T = argc > 1 ? atoi(argv[1]) : 150, S = argc > 2 ? atoi(argv[2]) : 40, W = S + 1;
-    const size_t rows = (size_t)T * W, slack = 8 * W;
-    std::vector<double2> lp(rows + 2 * slack, make_double2(-1.2, -7.1));
-    std::vector<int2> band(T + 64, make_int2(0, S));
-    std::vector<double> denom(rows, -7.0);
-    std::vector<int> labels(S, 3);
-    int hT = T, hS = S; int64_t rs[2] = {0, (int64_t)rows};
+    const int B = argc > 3 ? atoi(argv[3]) : 32, parts = argc > 4 ? atoi(argv[4]) : 4;
+    const size_t rows1 = (size_t)T * W, rows = rows1 * B, slack = 8 * W;
+    RawRow w0; w0.xb = 5.5f; w0.xl = 0.3f; w0.dh = -10.1f; w0.dl = 1e-9f;
+    std::vector<RawRow> lp(rows + 2 * slack, w0);
+    std::vector<int2> band((size_t)B * T + 64, make_int2(0, S));
+        std::vector<int> labels((size_t)B * S, 3), hT(B, T), hS(B, S);
+    std::vector<int64_t> rs(B + 1);
+    for (int b = 0; b <= B; ++b) rs[b] = (int64_t)b * rows1;
     K2Args a{};
-    int *dT, *dS, *dl; int64_t *drs; int2 *dband; double2 *dlp; double *dden, *dal, *dbe, *dll; float4 *dco; float *dc; long long *dcyc;
-    cudaMalloc(&dT, 4); cudaMalloc(&dS, 4); cudaMalloc(&dl, 4 * S); cudaMalloc(&drs, 16);
-    cudaMalloc(&dband, band.size() * 8); cudaMalloc(&dlp, lp.size() * 16); cudaMalloc(&dden, rows * 8);
-    cudaMalloc(&dal, rows * 8); cudaMalloc(&dbe, rows * 8); cudaMalloc(&dll, 32); cudaMalloc(&dco, rows * 16);
-    cudaMalloc(&dc, 16); cudaMalloc(&dcyc, 64);
-    cudaMemcpy(dT, &hT, 4, cudaMemcpyHostToDevice); cudaMemcpy(dS, &hS, 4, cudaMemcpyHostToDevice);
-    cudaMemcpy(dl, labels.data(), 4 * S, cudaMemcpyHostToDevice); cudaMemcpy(drs, rs, 16, cudaMemcpyHostToDevice);
+    int *dT, *dS, *dl; int64_t *drs; int2 *dband; RawRow *dlp; Weight *dw; double *dll; Cell *dal, *dbe; float4 *dco; float *dc; unsigned *dfl;
+    cudaMalloc(&dT, 4 * B); cudaMalloc(&dS, 4 * B); cudaMalloc(&dl, 4 * B * S); cudaMalloc(&drs, 8 * (B + 1));
+    cudaMalloc(&dband, band.size() * 8); cudaMalloc(&dlp, lp.size() * 16);
+    cudaMalloc(&dal, rows * 8); cudaMalloc(&dbe, rows * 8); cudaMalloc(&dll, 16 * B); cudaMalloc(&dco, rows * 16);
+    cudaMalloc(&dc, 4 * B); cudaMalloc(&dfl, 8 * B); cudaMemset(dfl, 0, 8 * B); cudaMalloc(&dw, rows * 16);
+    cudaMemcpy(dT, hT.data(), 4 * B, cudaMemcpyHostToDevice); cudaMemcpy(dS, hS.data(), 4 * B, cudaMemcpyHostToDevice);
+    cudaMemcpy(dl, labels.data(), 4 * B * S, cudaMemcpyHostToDevice); cudaMemcpy(drs, rs.data(), 8 * (B + 1), cudaMemcpyHostToDevice);
     cudaMemcpy(dband, band.data(), band.size() * 8, cudaMemcpyHostToDevice);
     cudaMemcpy(dlp, lp.data(), lp.size() * 16, cudaMemcpyHostToDevice);
-    cudaMemcpy(dden, denom.data(), rows * 8, cudaMemcpyHostToDevice);
-    a.T = dT; a.S = dS; a.labels = dl; a.row_start = drs; a.band = dband + 32; a.lp = dlp + slack; a.denom = dden;
-    a.alpha = dal; a.beta = dbe; a.coef = dco; a.ll_fwd = dll; a.ll_bwd = dll + 1; a.costs = dc;
+    a.T = dT; a.S = dS; a.labels = dl; a.row_start = drs; a.band = dband + 32; a.lp = dlp + slack; a.wts = dw;
+    a.alpha = dal; a.beta = dbe; a.coef = dco; a.ll_fwd = dll; a.ll_bwd = dll + B; a.costs = dc; a.flags = dfl;
     a.T_max = T; a.S_max = S; a.V = 1000; a.blank = 0;
+    a.chunk_frames = k2_chunk_frames(S);
+    const int K = argc > 5 ? atoi(argv[5]) : k2_states_per_lane(W);  // optional: force the states per lane
+    a.row_warps = k2_row_warps(W, K);
+    a.chunk_bufs = k2_chunk_bufs(a.row_warps);
+    const size_t sm = k2_smem_bytes(S, a.row_warps);
+    unsigned epoch = 1;
     for (int nb = 0; nb < 2; ++nb) {
-        a.need_beta = nb;
-        long long h[4] = {0, 0, 0, 0};
-        for (int rep = 0; rep < 2; ++rep) {
-            const size_t sm = k2_smem_bytes(S);
-            a.chunk_frames = k2_chunk_frames(S);
-            cudaFuncSetAttribute(probe<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-            cudaFuncSetAttribute(probe<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-            cudaFuncSetAttribute(probe<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-            if (W <= 32) probe<1><<<1, kK2Threads, sm>>>(a, dcyc);
-            else if (W <= 64) probe<2><<<1, kK2Threads, sm>>>(a, dcyc);
-            else probe<4><<<1, kK2Threads, sm>>>(a, dcyc);
-            cudaDeviceSynchronize();
-        }
-        cudaMemcpy(h, dcyc, 32, cudaMemcpyDeviceToHost);
-        printf("T=%d S=%d need_beta=%d: alpha %.1f cyc/frame, beta %.1f cyc/frame, coef epilogue %lld cyc, total %lld cyc (%s)\n",
-               T, S, nb, (double)h[0] / T, (double)h[1] / T, h[2], h[3], cudaGetErrorString(cudaGetLastError()));
+        a.need_beta = nb; a.parts = nb ? parts : 1; a.epoch = epoch; epoch += 100;
+        float ms;
+        if (K == 1) ms = run<1>(a, B, sm, 10);
+        else if (K == 2) ms = run<2>(a, B, sm, 10);
+        else ms = run<4>(a, B, sm, 10);
+        long long h[64];
+        cudaMemcpyFromSymbol(h, g_k2_trace, sizeof(h));
+        double ll;
+        cudaMemcpy(&ll, dll, 8, cudaMemcpyDeviceToHost);
+        printf("T=%d S=%d B=%d parts=%d need_beta=%d K=%d row_warps=%d: kernel %.2f us (best of 10), ll=%.6f (%s)\n", T, S, B, a.parts, nb, K, a.row_warps,
+               ms * 1e3, ll, cudaGetErrorString(cudaGetLastError()));
+        const int nch = (T + a.chunk_frames - 1) / a.chunk_frames;
+        printf("  alpha pass of utterance 0: setup %lld cyc, total %lld cyc = %.1f cyc/frame; per chunk (wait, run): ",
+               h[1] - h[0], h[50] - h[0], (double)(h[50] - h[3]) / T);
+        for (int c = 0; c < nch && c < 20; ++c)
+            printf("(%lld, %lld) ", h[3 + 2 * c] - h[2 + 2 * c], (c + 1 < nch && c < 19 ? h[4 + 2 * c] : h[50]) - h[3 + 2 * c]);
+        printf("\n  phase A (own share) %lld cyc, wait for the other parts %lld cyc, both passes done at %lld cyc, coefficient phase %lld cyc\n",
+               h[60] - h[0], h[61] - h[60], h[51] - h[0], h[52] - h[51]);
     }
     return 0;
 }

@@ -3,6 +3,51 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 #include "../include/mrnnt_b200/common.cuh"
+namespace mrnnt {
+// log-domain log-sum-exp of the first K2 design (kept here for the latency comparison only)
+// log(exp(x) + exp(y)) for the lattice recursion (reference rnnt_helper.h:21-30).  The large
+// parts are kept in double (|alpha| grows like T*log V, where a float ulp is already ~6e-5),
+// only the bounded correction log1p(exp(-|x-y|)) in (0, ln 2] is evaluated in float.
+__device__ __forceinline__ double lse_pair(double x, double y) {
+    const double mx = fmax(x, y);
+    const double mn = fmin(x, y);
+    const float d = static_cast<float>(mn - mx);  // <= 0; NaN only when both are -inf
+    const float r = log1pf(expf(d));
+    const double out = mx + static_cast<double>(r);
+    return (mn == kNegInf) ? mx : out;
+}
+
+// Same, with the correction term from the MUFU units: 2^(d log2 e) and log2(1 + u) in float
+// (absolute error of the term ~1e-7; it enters a double accumulator, so errors add up like a random
+// walk over the T frames instead of being amplified by |alpha|).  ~70 cycles of dependent latency
+// instead of ~250 for expf + log1pf; the lattice recursion is a pure latency chain, so this is what
+// sets the duration of K2.
+__device__ __forceinline__ double lse_pair_fast(double x, double y) {
+    const bool gt = x > y;
+    const double mx = gt ? x : y;
+    const double mn = gt ? y : x;
+    const float d = __double2float_rn(mn - mx);  // <= 0, -inf when only one side is -inf, NaN when both are
+    const float u = ex2_approx(d * kLog2e);
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + u));
+    const double out = mx + static_cast<double>(r * 0.69314718055994531f);
+    return (mx == kNegInf) ? kNegInf : out;
+}
+
+// lse_pair_fast with the band mask folded into the same select: -inf when the cell is outside the band.
+__device__ __forceinline__ double lse_pair_masked(double x, double y, bool in_band) {
+    const bool gt = x > y;
+    const double mx = gt ? x : y;
+    const double mn = gt ? y : x;
+    const float d = __double2float_rn(mn - mx);
+    const float u = ex2_approx(d * kLog2e);
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + u));
+    const double out = mx + static_cast<double>(r * 0.69314718055994531f);
+    return (in_band && mx != kNegInf) ? out : kNegInf;
+}
+
+}  // namespace mrnnt
 using namespace mrnnt;
 #define STEPS 2048
 
