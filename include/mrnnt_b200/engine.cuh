@@ -158,6 +158,7 @@ class Engine {
         plan_dirty_ = true;
         band_dirty_ = true;
         alignment_ = nullptr;
+        coef_blank_ = -1;
         return RNNT_STATUS_SUCCESS;
     }
 
@@ -207,23 +208,44 @@ class Engine {
 
     // Launch everything on `stream` without synchronising; costs stay in workspace().costs.
     RNNTStatus enqueue(int blank, cudaStream_t stream, float *grads_dev) {
+        RNNTStatus st = enqueue_forward(blank, stream, grads_dev != nullptr);
+        if (st != RNNT_STATUS_SUCCESS || grads_dev == nullptr) return st;
+        return enqueue_backward(stream, grads_dev, nullptr);
+    }
+
+    // First half of a call: K1 and K2.  With want_grads the lattice kernel also leaves the per-row gradient
+    // coefficients in the workspace, and enqueue_backward() may follow at any later time (same or another
+    // stream-ordered point) as long as acts and the workspace are untouched: a training framework calls this
+    // from its forward pass and enqueue_backward() from its backward pass.
+    RNNTStatus enqueue_forward(int blank, cudaStream_t stream, bool want_grads) {
         const DeviceInfo &dev = device_info();
         if (!dev.ok) return RNNT_STATUS_EXECUTION_FAILED;
+        coef_blank_ = -1;
         RNNTStatus st = setup(stream);
         if (st != RNNT_STATUS_SUCCESS) return st;
         mark(0, stream);
         st = launch_k1(blank, stream, dev);
         if (st != RNNT_STATUS_SUCCESS) return st;
         mark(1, stream);
-        st = launch_k2(blank, stream, dev, grads_dev != nullptr);
+        st = launch_k2(blank, stream, dev, want_grads);
         if (st != RNNT_STATUS_SUCCESS) return st;
         mark(2, stream);
-        if (grads_dev != nullptr) {
-            st = launch_k3(blank, stream, dev, grads_dev);
-            if (st != RNNT_STATUS_SUCCESS) return st;
-        }
         mark(3, stream);
+        if (want_grads) coef_blank_ = blank;
         return RNNT_STATUS_SUCCESS;
+    }
+
+    // Second half: K3, the gradient w.r.t. the logits.  scale_dev (optional, B floats on the device): utterance
+    // b's gradient rows are multiplied by scale_dev[b] as they are written -- the upstream gradient of the
+    // per-utterance costs (reference glue: pytorch_binding/monotonic_rnnt_op.py:97-118).
+    RNNTStatus enqueue_backward(cudaStream_t stream, float *grads_dev, const float *scale_dev) {
+        const DeviceInfo &dev = device_info();
+        if (!dev.ok) return RNNT_STATUS_EXECUTION_FAILED;
+        if (grads_dev == nullptr || coef_blank_ < 0) return RNNT_STATUS_INVALID_VALUE;
+        mark(2, stream);
+        const RNNTStatus st = launch_k3(coef_blank_, stream, dev, grads_dev, scale_dev);
+        mark(3, stream);
+        return st;
     }
 
     // Per-kernel device timing for the bench (CUDA events on the launch stream).  Off by default.
@@ -257,8 +279,8 @@ class Engine {
     void set_k2_parts(int parts) { k2_parts_ = parts < 0 ? 0 : parts; }
     // Consumer warps per CTA of the streaming kernels (8 or 16); tuning knob for the bench.
     void set_stream_warps(int k1, int k3) {
-        if (k1 == 8 || k1 == 16) k1_warps_ = k1;
-        if (k3 == 8 || k3 == 16) k3_warps_ = k3;
+        if (k1 == 8 || k1 == 16 || k1 == 24) k1_warps_ = k1;
+        if (k3 == 8 || k3 == 16 || k3 == 24) k3_warps_ = k3;
     }
 
    private:
@@ -286,7 +308,7 @@ class Engine {
             const int64_t blocks64 = (shape_.rows + 255) / 256;
             const int blocks = static_cast<int>(blocks64 > 65535 * 8 ? 65535 * 8 : blocks64);
             rowmeta_kernel<<<blocks, 256, 0, stream>>>(T_dev_, S_dev_, B_, shape_.T_max, shape_.S_max, ws_.row_start,
-                                                       ws_.band, ws_.rowmeta);
+                                                       ws_.band, ws_.rowmeta, ws_.rowutt);
             if (launched() != RNNT_STATUS_SUCCESS) return RNNT_STATUS_EXECUTION_FAILED;
             band_dirty_ = false;
         }
@@ -299,7 +321,7 @@ class Engine {
                     StreamTiling *tl) const {
         if (force_generic_) return false;
         if ((reinterpret_cast<uintptr_t>(p0) & 15) || (reinterpret_cast<uintptr_t>(p1) & 15)) return false;
-        const int order[2] = {preferred_warps, 8};
+        const int order[3] = {preferred_warps, 16, 8};
         for (int w : order) {
             if (stream_tiling(V_, extra_per_row, w, tl) && tl->smem_bytes <= static_cast<size_t>(dev.max_smem_optin))
                 return true;
@@ -332,8 +354,13 @@ class Engine {
 
     RNNTStatus launch_k1(int blank, cudaStream_t stream, const DeviceInfo &dev) {
         StreamTiling tl;
-        if (can_stream(acts_, acts_, 0, k1_warps_, dev, &tl)) {
-            return tl.warps == 8 ? launch_k1_nw<8>(blank, stream, dev, tl) : launch_k1_nw<16>(blank, stream, dev, tl);
+        // rows of 1028..2048 logits are held in 64 registers per lane: too many for 25 warps on one SM
+        const int V4 = V_ / 4;
+        const int want = (k1_warps_ == 24 && V4 > 8 * kWarp && V4 <= 16 * kWarp) ? 16 : k1_warps_;
+        if (can_stream(acts_, acts_, 0, want, dev, &tl)) {
+            return tl.warps == 8    ? launch_k1_nw<8>(blank, stream, dev, tl)
+                   : tl.warps == 16 ? launch_k1_nw<16>(blank, stream, dev, tl)
+                                    : launch_k1_nw<24>(blank, stream, dev, tl);
         }
         k1_lse_generic_kernel<<<generic_grid(dev), kGenericWarps * kWarp, 0, stream>>>(
             acts_, labels_, ws_.rowmeta, ws_.lp, shape_.rows, V_, blank);
@@ -383,24 +410,29 @@ class Engine {
         return launched();
     }
 
-    template <int NW>
+    template <int NW, bool SCALED>
     RNNTStatus launch_k3_tma(int blank, cudaStream_t stream, const DeviceInfo &dev, const StreamTiling &tl,
-                             float *grads) {
-        auto kern = k3_grad_tma_kernel<NW>;
+                             float *grads, const float *scale) {
+        auto kern = k3_grad_tma_kernel<NW, SCALED>;
         if (!ensure_dynamic_smem(kern, tl.smem_bytes)) return RNNT_STATUS_EXECUTION_FAILED;
         kern<<<dev.sm_count, (NW + 1) * kWarp, tl.smem_bytes, stream>>>(acts_, ws_.coef, grads, shape_.rows, V_, blank,
-                                                                         tl.G, tl.stages);
+                                                                         tl.G, tl.stages, ws_.rowutt, scale);
         return launched();
     }
 
-    RNNTStatus launch_k3(int blank, cudaStream_t stream, const DeviceInfo &dev, float *grads) {
+    RNNTStatus launch_k3(int blank, cudaStream_t stream, const DeviceInfo &dev, float *grads, const float *scale) {
         StreamTiling tl;
         if (can_stream(acts_, grads, sizeof(float4), k3_warps_, dev, &tl)) {
-            return tl.warps == 8 ? launch_k3_tma<8>(blank, stream, dev, tl, grads)
-                                 : launch_k3_tma<16>(blank, stream, dev, tl, grads);
+            if (scale != nullptr)
+                return tl.warps == 8    ? launch_k3_tma<8, true>(blank, stream, dev, tl, grads, scale)
+                       : tl.warps == 16 ? launch_k3_tma<16, true>(blank, stream, dev, tl, grads, scale)
+                                        : launch_k3_tma<24, true>(blank, stream, dev, tl, grads, scale);
+            return tl.warps == 8    ? launch_k3_tma<8, false>(blank, stream, dev, tl, grads, scale)
+                   : tl.warps == 16 ? launch_k3_tma<16, false>(blank, stream, dev, tl, grads, scale)
+                                    : launch_k3_tma<24, false>(blank, stream, dev, tl, grads, scale);
         }
-        k3_grad_generic_kernel<<<generic_grid(dev), kGenericWarps * kWarp, 0, stream>>>(acts_, ws_.coef, grads,
-                                                                                         shape_.rows, V_, blank);
+        k3_grad_generic_kernel<<<generic_grid(dev), kGenericWarps * kWarp, 0, stream>>>(
+            acts_, ws_.coef, grads, shape_.rows, V_, blank, ws_.rowutt, scale);
         return launched();
     }
 
@@ -424,10 +456,11 @@ class Engine {
     int max_shift_ = 0;
     int align_blank_ = 0;
     bool force_generic_ = false;
-    int k1_warps_ = 16;
-    int k3_warps_ = 16;
+    int k1_warps_ = 24;
+    int k3_warps_ = 24;
     int k2_parts_ = 0;     // 0: automatic
     unsigned epoch_ = 0u;  // launch counter published through Workspace::k2_flags
+    int coef_blank_ = -1;  // blank label of the forward pass whose coefficients sit in the workspace (-1: none)
     bool timing_ = false;
     cudaEvent_t ev_[4] = {};
 };

@@ -168,13 +168,14 @@ constexpr int kStreamTileTarget = 32 * 1024;      // bytes per ring slot we aim 
 // "an earlier tile was issued first" proves nothing).  Hence G is a power of two and the ring depth is a
 // multiple of the stride NW/G: every warp then cycles through a fixed subset of the stages.
 inline bool stream_tiling(int V, size_t extra_per_row, int warps, StreamTiling *out) {
-    if (V <= 0 || (V % 4) != 0 || (warps != 8 && warps != 16)) return false;
+    if (V <= 0 || (V % 4) != 0 || (warps != 8 && warps != 16 && warps != 24)) return false;
     const size_t row_bytes = static_cast<size_t>(V) * 4;
     int G = 1;
     while (G < 32 && static_cast<size_t>(2 * G) * row_bytes <= static_cast<size_t>(kStreamTileTarget)) G *= 2;
     const size_t slot = static_cast<size_t>(G) * row_bytes + 32 * (sizeof(int) + extra_per_row) + 16;
     int stages = static_cast<int>(kStreamSmemBudget / slot);
     if (stages > kStreamMaxStages) stages = kStreamMaxStages;
+    if (warps > G && warps % G != 0) return false;  // (24 warps with 16-row tiles: no regular stride)
     const int stride = warps > G ? warps / G : 1;
     stages = stages / stride * stride;
     if (stages < 3) return false;

@@ -32,6 +32,7 @@ struct Workspace {
     int64_t *row_start = nullptr;  // [B+1]   first row of each utterance
     int2 *band = nullptr;          // [B*T_max] (min_allowed_s, max_allowed_s) per frame
     int *rowmeta = nullptr;        // [rows]  >=0: index into labels[], kRowNoLabel, kRowDead
+    int *rowutt = nullptr;         // [rows]  utterance of the row (the gradient kernel's per-utterance scale)
     RawRow *lp = nullptr;          // [rows]  (x[blank], x[label_s], -log2 sum_v exp x[v]) per live row, from K1
     Weight *wts = nullptr;         // [rows]  transition weights (m * 2^e pairs, band folded in), K2 phase A
     Cell *alpha = nullptr;         // [rows]  full T x (S+1) grid per utterance (m * 2^e), zero outside the band
@@ -61,7 +62,7 @@ inline size_t workspace_bytes(const Shape &sh) {
     size_t n = 256;  // slack to align an arbitrarily aligned base pointer
     n += align_up((B + 1) * sizeof(int64_t), 256);
     n += align_up(B * static_cast<size_t>(sh.T_max) * sizeof(int2), 256) + 2 * kBandSlackBytes;
-    n += align_up(rows * sizeof(int), 256);
+    n += 2 * align_up(rows * sizeof(int), 256);
     n += align_up(rows * sizeof(RawRow), 256) + 2 * lp_slack_bytes(sh);
     n += align_up(rows * sizeof(Weight), 256);
     n += 2 * align_up(rows * sizeof(Cell), 256);
@@ -87,6 +88,7 @@ inline Workspace carve_workspace(void *base, const Shape &sh) {
     w.band = reinterpret_cast<int2 *>(take(B * static_cast<size_t>(sh.T_max) * sizeof(int2)));
     take(kBandSlackBytes);
     w.rowmeta = reinterpret_cast<int *>(take(rows * sizeof(int)));
+    w.rowutt = reinterpret_cast<int *>(take(rows * sizeof(int)));
     take(lp_slack_bytes(sh));
     w.lp = reinterpret_cast<RawRow *>(take(rows * sizeof(RawRow)));
     take(lp_slack_bytes(sh));
@@ -233,7 +235,8 @@ __device__ __forceinline__ int find_utterance(const int64_t *__restrict__ row_st
 static __global__ void __launch_bounds__(256) rowmeta_kernel(const int *__restrict__ T, const int *__restrict__ S, int B,
                                                        int T_max, int S_max,
                                                        const int64_t *__restrict__ row_start,
-                                                       const int2 *__restrict__ band, int *__restrict__ rowmeta) {
+                                                       const int2 *__restrict__ band, int *__restrict__ rowmeta,
+                                                       int *__restrict__ rowutt) {
     const int64_t rows = row_start[B];
     for (int64_t row = blockIdx.x * 256ll + threadIdx.x; row < rows; row += 256ll * gridDim.x) {
         const int b = find_utterance(row_start, B, row);
@@ -249,6 +252,7 @@ static __global__ void __launch_bounds__(256) rowmeta_kernel(const int *__restri
             live = s >= lh.x && s <= lh.y && s <= t && (Sb - s) <= (Tb - t);
         }
         rowmeta[row] = live ? (s < Sb ? b * S_max + s : kRowNoLabel) : kRowDead;
+        rowutt[row] = b;
     }
 }
 

@@ -57,6 +57,15 @@ RNNTStatus mrnnt_cost_and_grad(mrnnt_handle_t h, int blank_label, void *stream, 
 RNNTStatus mrnnt_enqueue(mrnnt_handle_t h, int blank_label, void *stream, float *gradients);
 const float *mrnnt_device_costs(mrnnt_handle_t h);
 
+/* The same call in two halves, for frameworks that compute gradients in their backward pass:
+ *   forward : K1 + K2 (costs on the device, per-row gradient coefficients in the workspace when want_grads != 0)
+ *   backward: K3 writes d(sum_b scale[b] * cost_b)/d(acts) into `gradients`; scale_dev_or_null = NULL means 1.
+ * Replaces the reference's autograd glue around cost_and_grad (pytorch_binding/monotonic_rnnt_op.py:61-118: a
+ * zeros_like memset before the call and a repeat_interleave * grads pass in backward, 3 more passes over
+ * the logits-sized arrays).  acts and the workspace must stay untouched between the two halves. */
+RNNTStatus mrnnt_enqueue_forward(mrnnt_handle_t h, int blank_label, void *stream, int want_grads);
+RNNTStatus mrnnt_enqueue_backward(mrnnt_handle_t h, void *stream, float *gradients, const float *scale_dev_or_null);
+
 /* One-shot convenience: size check + set_workspace + optional restrict_to_alignment + cost_and_grad. */
 RNNTStatus rnnt_loss_grad_gpu(const float *acts, const int *labels, const int *T_dev, const int *S_dev,
                               const int *T_host, const int *S_host, int B, int V, int blank_label,
@@ -67,8 +76,8 @@ RNNTStatus rnnt_loss_grad_gpu(const float *acts, const int *labels, const int *T
 enum {
     MRNNT_OPT_FORCE_GENERIC = 1, /* value != 0: use the generic (non-TMA) streaming kernels */
     MRNNT_OPT_TIMING = 2,        /* value != 0: record CUDA events around K1 / K2 / K3 of every call */
-    MRNNT_OPT_K1_WARPS = 3,      /* consumer warps per CTA of K1 (8 or 16)                              */
-    MRNNT_OPT_K3_WARPS = 4,      /* consumer warps per CTA of K3 (8 or 16)                              */
+    MRNNT_OPT_K1_WARPS = 3,      /* consumer warps per CTA of K1 (8, 16, 24)                            */
+    MRNNT_OPT_K3_WARPS = 4,      /* consumer warps per CTA of K3 (8, 16, 24)                            */
     MRNNT_OPT_K2_PARTS = 5       /* upper limit of CTAs per utterance in K2's coefficient phase (0: auto) */
 };
 RNNTStatus mrnnt_set_option(mrnnt_handle_t h, int option, int value);

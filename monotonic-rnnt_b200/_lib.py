@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = (
     "mrnnt_set_workspace", "mrnnt_create_workspace", "mrnnt_free_workspace", "mrnnt_restrict_to_alignment",
     "mrnnt_cost_and_grad", "mrnnt_enqueue", "mrnnt_device_costs", "rnnt_loss_grad_gpu", "mrnnt_set_option",
     "mrnnt_debug_copy", "mrnnt_synth_uniform", "mrnnt_build_info", "mrnnt_last_timings",
+    "mrnnt_enqueue_forward", "mrnnt_enqueue_backward",
 )
 
 
@@ -53,6 +54,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mrnnt_restrict_to_alignment.argtypes = [vp, vp, ci, ci]
     lib.mrnnt_cost_and_grad.argtypes = [vp, ci, vp, vp, vp]
     lib.mrnnt_enqueue.argtypes = [vp, ci, vp, vp]
+    lib.mrnnt_enqueue_forward.argtypes = [vp, ci, vp, ci]
+    lib.mrnnt_enqueue_backward.argtypes = [vp, vp, vp, vp]
     lib.mrnnt_device_costs.argtypes = [vp]
     lib.mrnnt_device_costs.restype = vp
     lib.rnnt_loss_grad_gpu.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, vp, ci, vp, sz, vp, vp, vp]
@@ -65,7 +68,7 @@ def _declare(lib: ctypes.CDLL) -> None:
     for name in ("mrnnt_get_workspace_size", "mrnnt_create", "mrnnt_workspace_size", "mrnnt_set_workspace",
                  "mrnnt_create_workspace", "mrnnt_restrict_to_alignment", "mrnnt_cost_and_grad", "mrnnt_enqueue",
                  "rnnt_loss_grad_gpu", "mrnnt_set_option", "mrnnt_debug_copy", "mrnnt_synth_uniform",
-                 "mrnnt_last_timings"):
+                 "mrnnt_last_timings", "mrnnt_enqueue_forward", "mrnnt_enqueue_backward"):
         getattr(lib, name).restype = ci
 
 

@@ -125,6 +125,22 @@ RNNTStatus mrnnt_enqueue(mrnnt_handle_t h, int blank_label, void *stream, float 
     return e.enqueue(blank_label, static_cast<cudaStream_t>(stream), gradients);
 }
 
+RNNTStatus mrnnt_enqueue_forward(mrnnt_handle_t h, int blank_label, void *stream, int want_grads) {
+    if (h == nullptr) return RNNT_STATUS_INVALID_VALUE;
+    mrnnt::Engine &e = h->manager.engine();
+    const RNNTStatus st = e.ensure_shape();
+    if (st != RNNT_STATUS_SUCCESS) return st;
+    if (!e.has_workspace() || blank_label < 0 || blank_label >= e.shape().V) return RNNT_STATUS_INVALID_VALUE;
+    return e.enqueue_forward(blank_label, static_cast<cudaStream_t>(stream), want_grads != 0);
+}
+
+RNNTStatus mrnnt_enqueue_backward(mrnnt_handle_t h, void *stream, float *gradients, const float *scale_dev_or_null) {
+    if (h == nullptr || gradients == nullptr) return RNNT_STATUS_INVALID_VALUE;
+    mrnnt::Engine &e = h->manager.engine();
+    if (!e.has_workspace()) return RNNT_STATUS_INVALID_VALUE;
+    return e.enqueue_backward(static_cast<cudaStream_t>(stream), gradients, scale_dev_or_null);
+}
+
 const float *mrnnt_device_costs(mrnnt_handle_t h) {
     return (h != nullptr && h->manager.engine().has_workspace()) ? h->manager.engine().workspace().costs : nullptr;
 }

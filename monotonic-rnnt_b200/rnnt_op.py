@@ -146,6 +146,27 @@ class LossHandle:
         _lib.check(st, "mrnnt_enqueue")
         return self.device_costs()
 
+    def enqueue_forward(self, blank_label: int = 0, want_grads: bool = True) -> torch.Tensor:
+        """First half of a call (K1 + K2); returns a device VIEW of the costs.  With want_grads the workspace
+        keeps what enqueue_backward() needs; acts and the workspace must stay untouched until then."""
+        with torch.cuda.device(self.acts.device):
+            st = self._lib.mrnnt_enqueue_forward(self._h, int(blank_label), self._stream(), 1 if want_grads else 0)
+        _lib.check(st, "mrnnt_enqueue_forward")
+        return self.device_costs()
+
+    def enqueue_backward(self, grads: torch.Tensor, scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Second half (K3): grads[i, :] = scale[b(i)] * d cost_b / d acts[i, :], written exactly once."""
+        assert grads.is_cuda and grads.dtype == torch.float32 and grads.is_contiguous()
+        assert grads.numel() == self.acts.numel()
+        sptr = None
+        if scale is not None:
+            assert scale.is_cuda and scale.dtype == torch.float32 and scale.is_contiguous() and scale.numel() == self.B
+            sptr = scale.data_ptr()
+        with torch.cuda.device(self.acts.device):
+            st = self._lib.mrnnt_enqueue_backward(self._h, self._stream(), grads.data_ptr(), sptr)
+        _lib.check(st, "mrnnt_enqueue_backward")
+        return grads
+
     def device_costs(self) -> torch.Tensor:
         ptr = self._lib.mrnnt_device_costs(self._h)
         off = int(ptr) - self.workspace.data_ptr()
@@ -171,7 +192,14 @@ class LossHandle:
 
 
 class MonotonicRNNTFunction(torch.autograd.Function):
-    """Same call signature as the reference's autograd function (monotonic_rnnt_op.py:19-118)."""
+    """Same call signature as the reference's autograd function (monotonic_rnnt_op.py:19-118).
+
+    The reference computes the gradients inside forward (into a zeros_like buffer) and multiplies them by the
+    upstream gradient in backward: a memset, a read and a write of logits-sized arrays on top of the loss
+    itself.  Here forward runs K1 + K2 only and backward runs K3 with the upstream gradient folded into its
+    single write, so a training step moves 12 bytes per logit in total and an inference call (no backward)
+    never touches the gradient array at all.
+    """
 
     @staticmethod
     def forward(ctx, acts, labels, input_lengths, label_lengths, alignment=None, max_distance_from_alignment=0,
@@ -179,23 +207,30 @@ class MonotonicRNNTFunction(torch.autograd.Function):
         handle = LossHandle(acts, labels, input_lengths, label_lengths)
         if alignment is not None:
             handle.restrict_to_alignment(alignment, max_distance_from_alignment, blank_label)
-        grads = torch.empty_like(acts) if acts.requires_grad else None
-        costs = handle.enqueue(blank_label, grads).clone()
+        want_grads = bool(acts.requires_grad)
+        costs = handle.enqueue_forward(blank_label, want_grads).clone()
+        stream = torch.cuda.current_stream(acts.device)
         # the workspace and alignment must outlive the kernels that are still in flight on this stream
-        handle.workspace.record_stream(torch.cuda.current_stream(acts.device))
-        handle.close()
-        if grads is None:
-            grads = torch.zeros(0, dtype=acts.dtype, device=acts.device)
-        ctx.save_for_backward(grads, input_lengths, label_lengths)
+        handle.workspace.record_stream(stream)
+        if want_grads:
+            ctx.handle = handle          # keeps the workspace (coefficients) alive until backward
+            ctx.save_for_backward(acts)  # backward re-streams the logits: they must not be modified in between
+        else:
+            handle.close()
         return costs
 
     @staticmethod
     def backward(ctx, grad_outputs):
-        # every logit of utterance b receives grads[i] * grad_outputs[b] (monotonic_rnnt_op.py:97-118)
-        grads, input_lengths, label_lengths = ctx.saved_tensors
-        repeats = (input_lengths * (label_lengths + 1)).to(torch.int64)
-        scale = grad_outputs.to(grads.dtype).repeat_interleave(repeats, output_size=grads.shape[0]).unsqueeze(1)
-        return grads * scale, None, None, None, None, None, None
+        # every logit of utterance b receives d cost_b / d logit * grad_outputs[b] (monotonic_rnnt_op.py:97-118)
+        (acts,) = ctx.saved_tensors
+        handle = ctx.handle
+        grads = torch.empty_like(acts)
+        scale = grad_outputs.detach().to(device=acts.device, dtype=torch.float32).contiguous()
+        handle.enqueue_backward(grads, scale)
+        stream = torch.cuda.current_stream(acts.device)
+        handle.workspace.record_stream(stream)
+        scale.record_stream(stream)
+        return grads, None, None, None, None, None, None
 
 
 def monotonic_rnnt_loss(acts, labels, input_lengths, label_lengths, alignment: Optional[torch.Tensor] = None,

@@ -101,4 +101,8 @@ def workload(name: str, B: Optional[int] = None) -> Workload:
         T = np.full(B, 300, np.int32); S = np.full(B, 60, np.int32); V = 2000
         labels = labels_for(B, 60, V)
         return Workload("c5", B, V, T, S, labels, _alignment(T, S, labels, seed=7), max_shift=5)
+    if name == "dense":   # tools only: the size of c2 with (almost) no dead rows, to separate streaming efficiency
+        B = B or 32       # from the effect of skipping rows
+        T = np.full(B, 1500, np.int32); S = np.full(B, 3, np.int32); V = 1000
+        return Workload("dense", B, V, T, S, labels_for(B, 3, V))
     raise KeyError(name)

@@ -20,6 +20,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "liboracle.so")
 _REF = os.path.join(_HERE, "_ref", "libmrnnt_ref.so")
+_REF_GPU = os.path.join(_HERE, "_ref", "ref_gpu_time")
 
 _c_int_p = ctypes.POINTER(ctypes.c_int)
 
@@ -33,6 +34,29 @@ def build(force: bool = False) -> None:
     ref_dir = os.environ.get("RNNT_REF_DIR", "/root/reference")
     if os.path.isdir(os.path.join(ref_dir, "include")) and (force or not os.path.exists(_REF)):
         subprocess.check_call(["make", "-C", _HERE, "ref", f"RNNT_REF_DIR={ref_dir}"], stdout=subprocess.DEVNULL)
+    if os.path.isdir(os.path.join(ref_dir, "include")) and (force or not os.path.exists(_REF_GPU)):
+        subprocess.call(["make", "-C", _HERE, "ref_gpu", f"RNNT_REF_DIR={ref_dir}"], stdout=subprocess.DEVNULL)
+
+
+def run_ref_gpu(B: int, T: int, S: int, V: int, timeout: float = 180.0) -> Optional[dict]:
+    """Run the reference's own CUDA timing program (tests/test_time.cu, unmodified, compiled for sm_100a) on the
+    current GPU: 10 calls of GpuRNNTComputer<float>::cost_and_grad on its own generated inputs, each timed by
+    the program itself with the host clock around the (synchronous) call.  Returns None if the binary is absent
+    or fails.  The first call carries one-time CUDA initialisation and is reported separately."""
+    if not os.path.exists(_REF_GPU):
+        return None
+    try:
+        out = subprocess.run([_REF_GPU, str(B), str(T), str(S), str(V)], capture_output=True, text=True,
+                             timeout=timeout)
+    except (subprocess.TimeoutExpired, OSError):
+        return None
+    times = [float(line.rsplit(":", 1)[1].split()[0]) for line in out.stdout.splitlines()
+             if line.startswith("compute_rnnt_loss elapsed time")]
+    if out.returncode != 0 or len(times) < 2:
+        return None
+    steady = sorted(times[1:])
+    return {"ms_first_call": times[0], "ms_median": steady[len(steady) // 2], "ms_min": steady[0],
+            "calls": len(times)}
 
 
 _lib = None

@@ -221,3 +221,39 @@ def test_autograd_op_matches_reference_semantics(gu):
     loss_mod = mr.MonotonicRNNTLoss(blank_label=case.blank)
     c2 = loss_mod(acts.detach(), labels, T, S)
     assert torch.equal(c2, costs.detach())
+
+
+@pytest.mark.parametrize("name", ["rand_v17", "rand_wide_shift3", "rand_v32"])
+def test_backward_half_scales_per_utterance(gu, name):
+    """enqueue_forward + enqueue_backward(scale): negative, zero and fractional upstream gradients, generic and
+    streaming gradient kernels, repeated backward on one forward (the coefficients are not consumed)."""
+    import monotonic_rnnt_b200 as mr
+    import gpu_util
+    case, ref = golden_io.load(name)
+    acts = gpu_util.to_dev(case.acts, torch.float32)
+    labels = gpu_util.to_dev(case.labels, torch.int32)
+    T = gpu_util.to_dev(case.T, torch.int32); S = gpu_util.to_dev(case.S, torch.int32)
+    h = mr.LossHandle(acts, labels, T, S)
+    if case.alignment is not None:
+        h.restrict_to_alignment(gpu_util.to_dev(case.alignment, torch.int32), case.max_shift, case.blank)
+    costs = h.enqueue_forward(case.blank, want_grads=True).clone()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(costs.cpu().numpy(), ref["costs_f64"], rtol=COST_RTOL)
+    rows = case.T.astype(np.int64) * (case.S + 1)
+    w = np.array([(-2.0, 0.0, 0.5, 3.0, -0.25)[b % 5] for b in range(case.B)], dtype=np.float32)
+    scale = np.repeat(w.astype(np.float64), rows)[:, None]
+    g = torch.full_like(acts, float("nan"))
+    for _ in range(2):
+        h.enqueue_backward(g, torch.from_numpy(w).cuda())
+        torch.cuda.synchronize()
+        assert np.abs(g.cpu().numpy() - ref["grads_f64"] * scale).max() <= GRAD_ATOL * 3
+    h.enqueue_backward(g, None)                                   # no scale: the plain gradient
+    torch.cuda.synchronize()
+    assert np.abs(g.cpu().numpy() - ref["grads_f64"]).max() <= GRAD_ATOL
+    h2 = mr.LossHandle(acts, labels, T, S)
+    with pytest.raises(mr.RNNTError):
+        h2.enqueue_backward(g, None)                              # backward without a forward
+    h2.enqueue_forward(case.blank, want_grads=False)
+    with pytest.raises(mr.RNNTError):
+        h2.enqueue_backward(g, None)                              # the forward kept no coefficients
+    h.close(); h2.close()
