@@ -10,8 +10,8 @@
 // RNNT_STATUS_INVALID_VALUE), workspace = one opaque device buffer whose size depends on (B, T[], S[])
 // only, caller-owned via set_workspace or manager-owned via create_workspace/free_workspace.
 // Not kept (private to the reference's own gpu_rnnt.h): the public data members and *_host() debug
-// mirrors, and the byte count itself (ours is larger: 64-bit offsets, double lattice, per-row
-// coefficients -- see mrnnt_b200/plan.cuh).
+// mirrors, and the byte count itself (ours is larger: 64-bit offsets, mantissa/exponent lattice cells,
+// transition weights, per-row coefficients -- see mrnnt_b200/plan.cuh).
 //
 // Host synchronisation: the FIRST of get_workspace_size / create_workspace / set_workspace copies
 // T[] and S[] to the host once (2*B ints); nothing else in this class blocks.  The reference does
@@ -48,6 +48,10 @@ class GpuRNNTWorkspaceManager : public RNNTWorkspaceManager {
     RNNTStatus set_host_lengths(const int *T_host, const int *S_host) {
         return engine_.set_host_lengths(T_host, S_host);
     }
+
+    // Extension with no reference equivalent: acts / gradients are the joint network's padded
+    // [B, T_dim, U, V] tensor (U = label positions + 1) and labels is [B, label_stride]; call before anything else.
+    void set_padded_layout(int T_dim, int U, int label_stride) { engine_.set_padded_layout(T_dim, U, label_stride); }
 
     RNNTStatus get_workspace_size(size_t *size_bytes) const { return engine_.workspace_size(size_bytes); }
 

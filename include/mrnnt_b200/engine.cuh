@@ -88,7 +88,10 @@ inline bool ensure_dynamic_smem(Kern kern, size_t bytes) {
 }
 
 // Validation rules of the reference (gpu_workspace_manager.h:232-239, cpu twin :99-107).
-inline RNNTStatus validate_lengths(const int *T_host, const int *S_host, int B, int V, Shape *shape) {
+// Padded layout: T_dim / U (= label positions + 1) are the tensor's own dimensions and must cover every
+// utterance; label_stride is the width of the labels array (0: the reference's rule, max_b S_b).
+inline RNNTStatus validate_lengths(const int *T_host, const int *S_host, int B, int V, Shape *shape, int T_dim = 0,
+                                   int U = 0, int label_stride = 0) {
     if (B <= 0 || V <= 0 || T_host == nullptr || S_host == nullptr) return RNNT_STATUS_INVALID_VALUE;
     Shape sh;
     sh.B = B;
@@ -99,6 +102,15 @@ inline RNNTStatus validate_lengths(const int *T_host, const int *S_host, int B, 
         sh.T_max = t > sh.T_max ? t : sh.T_max;
         sh.S_max = s > sh.S_max ? s : sh.S_max;
         sh.rows += static_cast<int64_t>(t) * (s + 1);
+    }
+    sh.label_stride = label_stride > 0 ? label_stride : sh.S_max;
+    if (sh.label_stride < sh.S_max) return RNNT_STATUS_INVALID_VALUE;
+    if (T_dim > 0 || U > 0) {
+        if (T_dim < sh.T_max || U < sh.S_max + 1) return RNNT_STATUS_INVALID_VALUE;
+        if (static_cast<int64_t>(T_dim) * U > 0x7fffffff) return RNNT_STATUS_INVALID_VALUE;  // per-utterance int index
+        sh.T_dim = T_dim;
+        sh.U = U;
+        sh.rows = static_cast<int64_t>(B) * T_dim * U;
     }
     *shape = sh;
     return RNNT_STATUS_SUCCESS;
@@ -112,12 +124,21 @@ class Engine {
     Engine(const Engine &) = delete;
     Engine &operator=(const Engine &) = delete;
 
+    // acts (and gradients) are a padded [B, T_dim, U, V] tensor, labels [B, label_stride] (see Shape).  Must be
+    // called before the first size query.
+    void set_padded_layout(int T_dim, int U, int label_stride) {
+        pad_T_ = T_dim;
+        pad_U_ = U;
+        label_stride_ = label_stride;
+        have_shape_ = false;
+    }
+
     // Supply host copies of the length arrays (skips the one D2H fetch).
     RNNTStatus set_host_lengths(const int *T_host, const int *S_host) {
         if (B_ <= 0) return RNNT_STATUS_INVALID_VALUE;
         T_h_.assign(T_host, T_host + B_);
         S_h_.assign(S_host, S_host + B_);
-        shape_status_ = validate_lengths(T_h_.data(), S_h_.data(), B_, V_, &shape_);
+        shape_status_ = validate_lengths(T_h_.data(), S_h_.data(), B_, V_, &shape_, pad_T_, pad_U_, label_stride_);
         have_shape_ = true;
         return shape_status_;
     }
@@ -136,7 +157,7 @@ class Engine {
             have_shape_ = true;
             return shape_status_ = RNNT_STATUS_MEMOPS_FAILED;
         }
-        shape_status_ = validate_lengths(T_h_.data(), S_h_.data(), B_, V_, &shape_);
+        shape_status_ = validate_lengths(T_h_.data(), S_h_.data(), B_, V_, &shape_, pad_T_, pad_U_, label_stride_);
         have_shape_ = true;
         return shape_status_;
     }
@@ -292,7 +313,8 @@ class Engine {
 
     RNNTStatus setup(cudaStream_t stream) {
         if (plan_dirty_) {
-            plan_row_start_kernel<<<1, kPlanThreads, 0, stream>>>(T_dev_, S_dev_, B_, ws_.row_start, ws_.k2_flags);
+            plan_row_start_kernel<<<1, kPlanThreads, 0, stream>>>(
+                T_dev_, S_dev_, B_, ws_.row_start, ws_.k2_flags, static_cast<int64_t>(shape_.T_dim) * shape_.U);
             if (launched() != RNNT_STATUS_SUCCESS) return RNNT_STATUS_EXECUTION_FAILED;
             plan_dirty_ = false;
         }
@@ -307,8 +329,8 @@ class Engine {
             if (launched() != RNNT_STATUS_SUCCESS) return RNNT_STATUS_EXECUTION_FAILED;
             const int64_t blocks64 = (shape_.rows + 255) / 256;
             const int blocks = static_cast<int>(blocks64 > 65535 * 8 ? 65535 * 8 : blocks64);
-            rowmeta_kernel<<<blocks, 256, 0, stream>>>(T_dev_, S_dev_, B_, shape_.T_max, shape_.S_max, ws_.row_start,
-                                                       ws_.band, ws_.rowmeta, ws_.rowutt);
+            rowmeta_kernel<<<blocks, 256, 0, stream>>>(T_dev_, S_dev_, B_, shape_.T_max, shape_.label_stride, shape_.U,
+                                                       ws_.row_start, ws_.band, ws_.rowmeta, ws_.rowutt);
             if (launched() != RNNT_STATUS_SUCCESS) return RNNT_STATUS_EXECUTION_FAILED;
             band_dirty_ = false;
         }
@@ -370,7 +392,7 @@ class Engine {
     template <int K>
     RNNTStatus launch_k2_warp(const K2Args &args, cudaStream_t stream) {
         auto kern = k2_lattice_kernel<K>;
-        const size_t smem = k2_smem_bytes(shape_.S_max, args.row_warps);
+        const size_t smem = k2_smem_bytes(shape_.width(), args.row_warps);
         if (!ensure_dynamic_smem(kern, smem)) return RNNT_STATUS_EXECUTION_FAILED;
         kern<<<B_ * args.parts, kK2Threads, smem, stream>>>(args);
         return launched();
@@ -382,8 +404,9 @@ class Engine {
         a.lp = ws_.lp; a.wts = ws_.wts; a.alpha = ws_.alpha; a.beta = ws_.beta; a.coef = ws_.coef;
         a.ll_fwd = ws_.ll_fwd; a.ll_bwd = ws_.ll_bwd; a.costs = ws_.costs;
         a.T_max = shape_.T_max; a.S_max = shape_.S_max; a.V = V_; a.blank = blank;
+        a.ld = shape_.U; a.T_dim = shape_.T_dim; a.label_stride = shape_.label_stride;
         a.need_beta = need_beta ? 1 : 0;
-        a.chunk_frames = k2_chunk_frames(shape_.S_max);
+        a.chunk_frames = k2_chunk_frames(shape_.width());
         // Coefficient phase: spread every utterance over `parts` CTAs while the whole grid still fits on the
         // machine at one CTA per SM (the extra CTAs wait for their utterance's recursion on idle SMs).
         int parts = need_beta ? dev.sm_count / B_ : 1;
@@ -442,6 +465,7 @@ class Engine {
     const int *S_dev_;
     int B_, V_;
 
+    int pad_T_ = 0, pad_U_ = 0, label_stride_ = 0;  // padded layout (0: packed)
     std::vector<int> T_h_, S_h_;
     Shape shape_;
     bool have_shape_ = false;

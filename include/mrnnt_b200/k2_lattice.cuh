@@ -78,6 +78,9 @@ struct K2Args {
     unsigned epoch;    // value published by this launch (never 0)
     int T_max;
     int S_max;
+    int ld;            // rows per frame: 0 = packed layout (S_b + 1 per utterance), else the fixed U of a padded tensor
+    int T_dim;         // padded layout: frames per utterance block (0 = packed)
+    int label_stride;  // ints per utterance in labels[]
     int V;
     int blank;
     int need_beta;     // 0: cost only (alpha pass), 1: alpha + beta + coefficients
@@ -97,9 +100,9 @@ inline int k2_states_per_lane(int states) {
     return 0;
 }
 inline int k2_row_warps(int states, int K) { return (states + kWarp * K - 1) / (kWarp * K); }
-// frames per chunk
-inline int k2_chunk_frames(int S_max) {
-    const int frame_bytes = (S_max + 1) * static_cast<int>(sizeof(Weight));
+// frames per chunk; `width` = rows per frame in memory (S_max + 1 packed, U padded)
+inline int k2_chunk_frames(int width) {
+    const int frame_bytes = width * static_cast<int>(sizeof(Weight));
     int ch = kK2ChunkTargetBytes / frame_bytes;
     if (ch < 1) ch = 1;
     if (ch > kK2MaxChunkFrames) ch = kK2MaxChunkFrames;
@@ -117,8 +120,8 @@ __host__ __device__ inline size_t k2_dir_bytes(size_t chunk_bytes, int bufs, int
     return bufs * chunk_bytes + 2 * kK2MaxChunkBufs * sizeof(uint64_t) + 64 +
            static_cast<size_t>(row_warps > 1 ? row_warps - 1 : 0) * kK2FifoDepth * sizeof(Cell);
 }
-inline size_t k2_smem_bytes(int S_max, int row_warps) {
-    return 2 * k2_dir_bytes(static_cast<size_t>(k2_chunk_frames(S_max)) * (S_max + 1) * sizeof(Weight),
+inline size_t k2_smem_bytes(int width, int row_warps) {
+    return 2 * k2_dir_bytes(static_cast<size_t>(k2_chunk_frames(width)) * width * sizeof(Weight),
                             k2_chunk_bufs(row_warps), row_warps);
 }
 
@@ -146,6 +149,9 @@ struct K2Dir {
 };
 
 constexpr int kK2NoProgress = -(1 << 30);
+
+// rows per frame of utterance b in memory
+__device__ __forceinline__ int k2_ld(const K2Args &a, int Sb) { return a.ld > 0 ? a.ld : Sb + 1; }
 
 // Frames of chunk c.  Direction 0 (alpha) walks the frames upwards, direction 1 (beta) downwards.
 __device__ __forceinline__ int k2_chunk_lo(int dir, int c, int CH, int Tb) {
@@ -183,7 +189,7 @@ __device__ __forceinline__ Weight k2_make_weight(const RawRow &raw, bool stay_ok
 // ---- phase A: rows [part*n/parts, (part+1)*n/parts) of utterance b, whole CTA ---------------------------
 __device__ __forceinline__ void k2_weight_rows(const K2Args &a, int b, int part, int parts) {
     const int Tb = a.T[b], Sb = a.S[b];
-    const int W = Sb + 1;
+    const int W = Sb + 1, ld = k2_ld(a, Sb);
     const int64_t R = a.row_start[b];
     const RawRow *lp = a.lp + R;
     Weight *wts = a.wts + R;
@@ -204,21 +210,22 @@ __device__ __forceinline__ void k2_weight_rows(const K2Args &a, int b, int part,
             ss[u] = i - t * W;
             lh[u] = band[t];
             lq[u] = band[max(t - 1, 0)];
-            raw[u] = lp[i];  // never written for dead rows: whatever is there is masked by the flags below
+            // never written for dead rows: whatever is there is masked by the flags below
+            raw[u] = lp[static_cast<int64_t>(t) * ld + ss[u]];
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             bool stay_ok, emit_ok;
             k2_row_flags(tt[u], ss[u], lh[u], lq[u], Tb, Sb, false, stay_ok, emit_ok);
             const int i = base + u * kK2Threads;
-            if (i < i_end) wts[i] = k2_make_weight(raw[u], stay_ok, emit_ok);
+            if (i < i_end) wts[static_cast<int64_t>(tt[u]) * ld + ss[u]] = k2_make_weight(raw[u], stay_ok, emit_ok);
         }
     }
 }
 
 // ---- phase B, one lane per direction: keep the chunk ring full --------------------------------------------
 __device__ __forceinline__ void k2_issue_chunks(const K2Args &a, int b, int dir, K2Dir &ring) {
-    const int Tb = a.T[b], W = a.S[b] + 1;
+    const int Tb = a.T[b], W = a.S[b] + 1, ld = k2_ld(a, a.S[b]);
     const int CH = a.chunk_frames;
     const Weight *wts = a.wts + a.row_start[b];
     const int nchunks = (Tb + CH - 1) / CH;
@@ -227,9 +234,11 @@ __device__ __forceinline__ void k2_issue_chunks(const K2Args &a, int b, int dir,
         const int lap = c / ring.bufs;
         if (lap > 0) mbar_wait(ring.empty + slot, static_cast<uint32_t>((lap - 1) & 1));  // chain warps released it
         const int lo = k2_chunk_lo(dir, c, CH, Tb), hi = k2_chunk_hi(dir, c, CH, Tb);
-        const uint32_t bytes = static_cast<uint32_t>(hi - lo) * W * sizeof(Weight);
+        // whole frames as they lie in memory (in a padded tensor: with the unused states behind S_b), except that
+        // the last frame stops at its last state so that the copy never leaves the utterance's block
+        const uint32_t bytes = static_cast<uint32_t>((hi - lo - 1) * ld + W) * sizeof(Weight);
         mbar_arrive_expect_tx(ring.w_full + slot, bytes);
-        bulk_g2s(ring.slot(slot), wts + static_cast<int64_t>(lo) * W, bytes, ring.w_full + slot);
+        bulk_g2s(ring.slot(slot), wts + static_cast<int64_t>(lo) * ld, bytes, ring.w_full + slot);
     }
 }
 
@@ -244,7 +253,7 @@ template <int K, int DIR, bool HAS_IN, bool HAS_OUT>
 __device__ __forceinline__ void k2_chain_warp(const K2Args &a, int b, K2Dir &ring, int wi) {
     const int lane = threadIdx.x & 31;
     const int Tb = a.T[b], Sb = a.S[b];
-    const int W = Sb + 1;
+    const int ld = k2_ld(a, Sb);
     const int CH = a.chunk_frames;
     const int64_t R = a.row_start[b];
     const int s0 = (wi * kWarp + lane) * K;
@@ -278,7 +287,7 @@ __device__ __forceinline__ void k2_chain_warp(const K2Args &a, int b, K2Dir &rin
     bool st[K];
 #pragma unroll
     for (int j = 0; j < K; ++j) st[j] = store && (s0 + j <= Sb);
-    const int wstep = (DIR == 0) ? W : -W;
+    const int wstep = (DIR == 0) ? ld : -ld;
 
     int slot = 0;
     uint32_t parity = 0;
@@ -289,8 +298,8 @@ __device__ __forceinline__ void k2_chain_warp(const K2Args &a, int b, K2Dir &rin
         if (DIR == 0 && wi == 0) MRNNT_K2_STAMP(2 + 2 * min(c, 20));
         mbar_wait(ring.w_full + slot, parity);
         if (DIR == 0 && wi == 0) MRNNT_K2_STAMP(3 + 2 * min(c, 20));
-        const Weight *wp = reinterpret_cast<const Weight *>(ring.slot(slot)) + static_cast<size_t>(t_first - tlo) * W;
-        Cell *out = grid + static_cast<int64_t>(t_first) * W;
+        const Weight *wp = reinterpret_cast<const Weight *>(ring.slot(slot)) + static_cast<size_t>(t_first - tlo) * ld;
+        Cell *out = grid + static_cast<int64_t>(t_first) * ld;
         // sequence number of the exchange with the neighbour warp, counted from alpha's / beta's first frame
         // (beta numbers its first frame -1: what it sends there is its initial state beta(T, .))
         int seq = (DIR == 0) ? t_first : Tb - 2 - t_first;
@@ -316,7 +325,7 @@ __device__ __forceinline__ void k2_chain_warp(const K2Args &a, int b, K2Dir &rin
                 RawRow raw;
                 raw.xb = raw.xl = kNegInfF;
                 raw.dh = raw.dl = 0.0f;
-                if (stay_ok || emit_ok) raw = a.lp[R + static_cast<int64_t>(Tb - 1) * W + col[j]];
+                if (stay_ok || emit_ok) raw = a.lp[R + static_cast<int64_t>(Tb - 1) * ld + col[j]];
                 wn[j] = k2_make_weight(raw, stay_ok, emit_ok);
             }
         }
@@ -451,15 +460,18 @@ __device__ __forceinline__ float k2_coef(const Cell &x, float ratio, int base_e,
 
 __device__ __forceinline__ void k2_coef_rows(const K2Args &a, int b, int part, int parts) {
     const int Tb = a.T[b], Sb = a.S[b];
-    const int W = Sb + 1;
+    const int ld = k2_ld(a, Sb);
     const int64_t R = a.row_start[b];
     const Cell *alpha = a.alpha + R;
     const Cell *beta = a.beta + R;
     const RawRow *lp = a.lp + R;
-    const int *labels = a.labels + static_cast<size_t>(b) * a.S_max;
+    const int *labels = a.labels + static_cast<size_t>(b) * a.label_stride;
     float4 *coef = a.coef + R;
-    const int n = Tb * W;
-    const Cell Z = alpha[n - 1];  // alpha(T-1, S); zero when the band excludes the terminal state
+    // every row of the utterance's block gets a coefficient record (K3 takes row liveness from it); in a padded
+    // tensor that includes the rows behind T_b and the states behind S_b, which are dead
+    const int n = (a.ld > 0 ? a.T_dim : Tb) * ld;
+    const int n_valid = (Tb - 1) * ld + Sb + 1;  // one past the last row that belongs to the lattice
+    const Cell Z = alpha[n_valid - 1];           // alpha(T-1, S); zero when the band excludes the terminal state
     const bool feasible = Z.m > 0.0f;
     const float inv_mz = feasible ? 1.0f / Z.m : 0.0f;
     const int i_begin = static_cast<int>(static_cast<int64_t>(n) * part / parts);
@@ -479,16 +491,17 @@ __device__ __forceinline__ void k2_coef_rows(const K2Args &a, int b, int part, i
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int i = min(base + u * kK2Threads, i_end - 1);  // clamped: loads are unconditional, stores are not
-            const int t = i / W;
-            const int s = i - t * W;
+            const int t = i / ld;
+            const int s = i - t * ld;
             tt[u] = t;
             ss[u] = s;
-            al[u] = alpha[max(i - W, 0)];
-            b0[u] = beta[i];
-            b1[u] = beta[min(i + W, n - 1)];
-            b2[u] = beta[min(i + W + 1, n - 1)];
+            // clamped into the lattice's own rows: whatever a clamped load returns is replaced or unused below
+            al[u] = alpha[min(max(i - ld, 0), n_valid - 1)];
+            b0[u] = beta[min(i, n_valid - 1)];
+            b1[u] = beta[min(i + ld, n_valid - 1)];
+            b2[u] = beta[min(i + ld + 1, n_valid - 1)];
             // (dh, dl): garbage for dead rows, but only used when alpha(t-1,s) != 0, i.e. when the row is live
-            dn[u] = *reinterpret_cast<const float2 *>(&lp[i].dh);
+            dn[u] = *reinterpret_cast<const float2 *>(&lp[min(i, n_valid - 1)].dh);
             lab[u] = (Sb > 0) ? labels[min(s, Sb - 1)] : -1;
         }
 #pragma unroll
@@ -496,20 +509,21 @@ __device__ __forceinline__ void k2_coef_rows(const K2Args &a, int b, int part, i
             const int i = base + u * kK2Threads;
             if (i >= i_end) break;
             const int t = tt[u], s = ss[u];
+            const bool inside = t < Tb && s <= Sb;
             const bool last = (t == Tb - 1);
-            const Cell av = (t == 0) ? (s == 0 ? one : zero) : al[u];
+            const Cell av = !inside ? zero : (t == 0) ? (s == 0 ? one : zero) : al[u];
             const Cell v1 = last ? (s == Sb ? one : zero) : b1[u];
             const Cell v2 = (s == Sb) ? zero : (last ? (s + 1 == Sb ? one : zero) : b2[u]);
             int lb = lab[u];
             if (s >= Sb || lb == a.blank || lb < 0 || lb >= a.V) lb = -1;  // blank branch wins (cpu_rnnt.h:224-232)
             float4 c;
             c.w = __int_as_float(lb);
-            if (!feasible) {
+            if (!inside || (feasible && av.m == 0.0f)) {
+                c.x = c.y = c.z = kNegInfF;
+            } else if (!feasible) {
                 // infeasible utterance (e.g. the alignment band excludes the terminal state): cost = +inf and,
                 // as in the reference, no finite gradient exists.  NaN is written on purpose.
                 c.x = c.y = c.z = qnan;
-            } else if (av.m == 0.0f) {
-                c.x = c.y = c.z = kNegInfF;
             } else {
                 const float ratio = av.m * inv_mz;
                 const int base_e = av.e - Z.e;
@@ -562,7 +576,7 @@ static __global__ void __launch_bounds__(kK2Threads) k2_lattice_kernel(K2Args a)
         MRNNT_K2_STAMP(60);
         const int ndir = a.need_beta ? 2 : 1;
         const int nrw = a.row_warps;
-        const size_t chunk_bytes = static_cast<size_t>(a.chunk_frames) * (a.S_max + 1) * sizeof(Weight);
+        const size_t chunk_bytes = static_cast<size_t>(a.chunk_frames) * (a.ld > 0 ? a.ld : a.S_max + 1) * sizeof(Weight);
         const int bufs = a.chunk_bufs;
         const size_t dir_bytes = k2_dir_bytes(chunk_bytes, bufs, nrw);
         for (int d = 0; d < ndir; ++d) {
@@ -629,7 +643,7 @@ static __global__ void __launch_bounds__(kK2Threads) k2_lattice_wide_kernel(K2Ar
     Cell *prev = reinterpret_cast<Cell *>(k2w_smem);  // [S_max + 2]
     const int b = blockIdx.x;
     const int Tb = a.T[b], Sb = a.S[b];
-    const int W = Sb + 1;
+    const int W = k2_ld(a, Sb);  // rows per frame in memory
     const int64_t R = a.row_start[b];
     const RawRow *lp = a.lp + R;
     const int2 *band = a.band + static_cast<size_t>(b) * a.T_max;

@@ -24,7 +24,13 @@ struct Shape {
     int V = 0;
     int T_max = 0;
     int S_max = 0;
-    int64_t rows = 0;  // sum_b T_b * (S_b + 1)
+    int64_t rows = 0;  // rows of acts / gradients: sum_b T_b * (S_b + 1) packed, B * T_dim * U padded
+    // Padded layout: acts is the joint network's own [B, T_dim, U, V] tensor, row of (b,t,s) =
+    // (b*T_dim + t)*U + s; rows with t >= T_b or s > S_b are dead (never read, gradient zero).  0 = packed.
+    int T_dim = 0;
+    int U = 0;
+    int label_stride = 0;  // ints per utterance in labels[] (packed reference layout: max_b S_b)
+    int width() const { return U > 0 ? U : S_max + 1; }  // rows per frame at most
 };
 
 // Device arrays carved out of the caller's workspace buffer (all 256-byte aligned).
@@ -50,7 +56,7 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 // (k2_lattice.cuh); the two arrays therefore carry this much never-consumed slack on both sides.
 constexpr int kPrefetchFrames = 8;
 inline size_t lp_slack_bytes(const Shape &sh) {
-    return align_up(static_cast<size_t>(kPrefetchFrames) * (static_cast<size_t>(sh.S_max) + 1) * sizeof(RawRow), 256);
+    return align_up(static_cast<size_t>(kPrefetchFrames) * static_cast<size_t>(sh.width()) * sizeof(RawRow), 256);
 }
 constexpr size_t kBandSlackBytes = 256;  // >= kPrefetchFrames * sizeof(int2)
 
@@ -113,12 +119,17 @@ constexpr int kPlanThreads = 1024;
 static __global__ void __launch_bounds__(kPlanThreads) plan_row_start_kernel(const int *__restrict__ T,
                                                                        const int *__restrict__ S, int B,
                                                                        int64_t *__restrict__ row_start,
-                                                                       unsigned *__restrict__ k2_flags) {
+                                                                       unsigned *__restrict__ k2_flags,
+                                                                       int64_t padded_block_rows) {
     __shared__ int64_t warp_tot[kPlanThreads / kWarp];
     const int tid = threadIdx.x;
     const int per = (B + kPlanThreads - 1) / kPlanThreads;
     const int b0 = tid * per;
     for (int b = tid; b < 2 * B; b += kPlanThreads) k2_flags[b] = 0u;
+    if (padded_block_rows > 0) {  // padded layout: every utterance owns a block of T_dim * U rows
+        for (int b = tid; b <= B; b += kPlanThreads) row_start[b] = b * padded_block_rows;
+        return;
+    }
     int64_t local = 0;
     for (int i = 0; i < per; ++i) {
         const int b = b0 + i;
@@ -233,7 +244,7 @@ __device__ __forceinline__ int find_utterance(const int64_t *__restrict__ row_st
 }
 
 static __global__ void __launch_bounds__(256) rowmeta_kernel(const int *__restrict__ T, const int *__restrict__ S, int B,
-                                                       int T_max, int S_max,
+                                                       int T_max, int label_stride, int ld_fixed,
                                                        const int64_t *__restrict__ row_start,
                                                        const int2 *__restrict__ band, int *__restrict__ rowmeta,
                                                        int *__restrict__ rowutt) {
@@ -242,16 +253,19 @@ static __global__ void __launch_bounds__(256) rowmeta_kernel(const int *__restri
         const int b = find_utterance(row_start, B, row);
         const int Tb = T[b], Sb = S[b];
         const int local = static_cast<int>(row - row_start[b]);
-        const int t = local / (Sb + 1);
-        const int s = local - t * (Sb + 1);
+        const int ld = ld_fixed > 0 ? ld_fixed : Sb + 1;
+        const int t = local / ld;
+        const int s = local - t * ld;
         bool live;
-        if (t == 0) {
+        if (t >= Tb || s > Sb) {
+            live = false;  // padding of a padded tensor
+        } else if (t == 0) {
             live = (s == 0);
         } else {
             const int2 lh = band[static_cast<size_t>(b) * T_max + (t - 1)];
             live = s >= lh.x && s <= lh.y && s <= t && (Sb - s) <= (Tb - t);
         }
-        rowmeta[row] = live ? (s < Sb ? b * S_max + s : kRowNoLabel) : kRowDead;
+        rowmeta[row] = live ? (s < Sb ? b * label_stride + s : kRowNoLabel) : kRowDead;
         rowutt[row] = b;
     }
 }

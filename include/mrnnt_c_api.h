@@ -35,6 +35,17 @@ RNNTStatus mrnnt_get_workspace_size(const int *T_host, const int *S_host, int B,
  * T_host / S_host may be NULL; the lengths are then fetched from the device once (blocking). */
 RNNTStatus mrnnt_create(mrnnt_handle_t *out, const float *acts, const int *labels, int B, const int *T_dev,
                         const int *S_dev, int V, const int *T_host, const int *S_host);
+/* Same, for the joint network's own PADDED tensor (no reference equivalent; the reference makes its callers
+ * gather the valid rows into the packed layout first, pytorch_binding/monotonic_rnnt_op.py:133-140, and scatter
+ * the gradients back):
+ *   acts / gradients  float32 [B, T_dim, U, V], row of (b,t,s) = (b*T_dim + t)*U + s,  T_dim >= max T_b, U >= max S_b + 1
+ *   labels            int32   [B, label_stride], label_stride >= max S_b;   alignments stay [B, max_b T_b]
+ * Rows with t >= T_b or s > S_b are never read and their gradient rows are written as zeros. */
+RNNTStatus mrnnt_get_workspace_size_padded(const int *T_host, const int *S_host, int B, int V, int T_dim, int U,
+                                           int label_stride, size_t *size_bytes);
+RNNTStatus mrnnt_create_padded(mrnnt_handle_t *out, const float *acts, const int *labels, int B, const int *T_dev,
+                               const int *S_dev, int V, int T_dim, int U, int label_stride, const int *T_host,
+                               const int *S_host);
 void mrnnt_destroy(mrnnt_handle_t h);
 
 /* gpu_workspace_manager.h:228 (get_workspace_size), :256 (set_workspace), :331-342 (create/free). */

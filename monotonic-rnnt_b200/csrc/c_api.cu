@@ -84,6 +84,36 @@ RNNTStatus mrnnt_create(mrnnt_handle_t *out, const float *acts, const int *label
     return RNNT_STATUS_SUCCESS;
 }
 
+RNNTStatus mrnnt_get_workspace_size_padded(const int *T_host, const int *S_host, int B, int V, int T_dim, int U,
+                                           int label_stride, size_t *size_bytes) {
+    if (size_bytes == nullptr || T_dim <= 0 || U <= 0 || label_stride < 0) return RNNT_STATUS_INVALID_VALUE;
+    mrnnt::Shape sh;
+    const RNNTStatus st = mrnnt::validate_lengths(T_host, S_host, B, V, &sh, T_dim, U, label_stride);
+    if (st != RNNT_STATUS_SUCCESS) return st;
+    *size_bytes = mrnnt::workspace_bytes(sh);
+    return RNNT_STATUS_SUCCESS;
+}
+
+RNNTStatus mrnnt_create_padded(mrnnt_handle_t *out, const float *acts, const int *labels, int B, const int *T_dev,
+                               const int *S_dev, int V, int T_dim, int U, int label_stride, const int *T_host,
+                               const int *S_host) {
+    if (out == nullptr) return RNNT_STATUS_INVALID_VALUE;
+    *out = nullptr;
+    if (B <= 0 || V <= 0 || T_dim <= 0 || U <= 0 || label_stride < 0) return RNNT_STATUS_INVALID_VALUE;
+    auto *h = new (std::nothrow) mrnnt_handle_st(acts, labels, B, T_dev, S_dev, V);
+    if (h == nullptr) return RNNT_STATUS_UNKNOWN_ERROR;
+    h->manager.set_padded_layout(T_dim, U, label_stride);
+    if (T_host != nullptr && S_host != nullptr) {
+        const RNNTStatus st = h->manager.set_host_lengths(T_host, S_host);
+        if (st != RNNT_STATUS_SUCCESS) {
+            delete h;
+            return st;
+        }
+    }
+    *out = h;
+    return RNNT_STATUS_SUCCESS;
+}
+
 void mrnnt_destroy(mrnnt_handle_t h) { delete h; }
 
 RNNTStatus mrnnt_workspace_size(mrnnt_handle_t h, size_t *size_bytes) {

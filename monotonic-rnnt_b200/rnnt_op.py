@@ -35,8 +35,11 @@ def _check_inputs(acts, labels, input_lengths, label_lengths) -> None:
             raise TypeError(f"{name} must be int32")             # data_ptr<int>() in monotonic_rnnt.cu:99-101
     if acts.dtype != torch.float32:
         raise TypeError("acts must be float32")                  # monotonic_rnnt.cu:84
-    if acts.dim() != 2:
-        raise ValueError("acts must be the packed 2-D tensor [sum_b T_b*(S_b+1), V]")
+    if acts.dim() not in (2, 4):
+        raise ValueError("acts must be the packed 2-D tensor [sum_b T_b*(S_b+1), V] or the padded 4-D tensor "
+                         "[B, T, U, V]")
+    if acts.dim() == 4 and (acts.shape[0] != input_lengths.shape[0] or labels.dim() != 2):
+        raise ValueError("padded acts [B, T, U, V] need labels [B, S] and one length per utterance")
     if not (acts.is_contiguous() and labels.is_contiguous() and input_lengths.is_contiguous()
             and label_lengths.is_contiguous()):
         raise ValueError("inputs must be contiguous")
@@ -58,6 +61,10 @@ class LossHandle:
     Mirrors how the reference bindings drive the C++ classes (pytorch_binding/monotonic_rnnt.cu:99-111):
     construct on (acts, labels, B, T, S, V), size and attach the workspace, optionally
     ``restrict_to_alignment``, then ``cost_and_grad``.  Reusable across calls on the same tensors.
+
+    ``acts`` is either the reference's packed 2-D tensor or (extension) the joint network's own
+    padded 4-D tensor [B, T, U, V] with U >= max S_b + 1: no gather into the packed layout, no scatter of the
+    gradients back; gradients then have the same 4-D shape with exact zeros in the padding.
     """
 
     def __init__(self, acts: torch.Tensor, labels: torch.Tensor, input_lengths: torch.Tensor,
@@ -67,7 +74,8 @@ class LossHandle:
         self.acts, self.labels = acts, labels
         self.input_lengths, self.label_lengths = input_lengths, label_lengths
         self.B = int(input_lengths.shape[0])
-        self.V = int(acts.shape[1])
+        self.V = int(acts.shape[-1])
+        self.padded = acts.dim() == 4
         self._alignment = None
         if label_lengths.shape[0] != self.B or labels.shape[0] != self.B:
             raise ValueError("labels / input_lengths / label_lengths disagree on the batch size")
@@ -78,9 +86,16 @@ class LossHandle:
             th, sh = self._T_h.ctypes.data, self._S_h.ctypes.data
         h = ctypes.c_void_p()
         with torch.cuda.device(acts.device):
-            st = self._lib.mrnnt_create(ctypes.byref(h), acts.data_ptr(), labels.data_ptr(), self.B,
-                                        input_lengths.data_ptr(), label_lengths.data_ptr(), self.V, th, sh)
-            _lib.check(st, "mrnnt_create")
+            if self.padded:
+                st = self._lib.mrnnt_create_padded(ctypes.byref(h), acts.data_ptr(), labels.data_ptr(), self.B,
+                                                   input_lengths.data_ptr(), label_lengths.data_ptr(), self.V,
+                                                   int(acts.shape[1]), int(acts.shape[2]), int(labels.shape[1]),
+                                                   th, sh)
+                _lib.check(st, "mrnnt_create_padded")
+            else:
+                st = self._lib.mrnnt_create(ctypes.byref(h), acts.data_ptr(), labels.data_ptr(), self.B,
+                                            input_lengths.data_ptr(), label_lengths.data_ptr(), self.V, th, sh)
+                _lib.check(st, "mrnnt_create")
             self._h = h
             size = ctypes.c_size_t(0)
             _lib.check(self._lib.mrnnt_workspace_size(self._h, ctypes.byref(size)), "mrnnt_workspace_size")
@@ -177,7 +192,7 @@ class LossHandle:
         """Intermediate arrays for kernel-level parity tests (blocking)."""
         T = self.input_lengths.cpu().numpy().astype(np.int64)
         S = self.label_lengths.cpu().numpy().astype(np.int64)
-        rows = int((T * (S + 1)).sum())
+        rows = int(self.acts.numel() // self.V) if self.padded else int((T * (S + 1)).sum())
         shapes = {
             _lib.DBG_DENOM: (np.float64, (rows,)), _lib.DBG_ALPHA: (np.float64, (rows,)),
             _lib.DBG_BETA: (np.float64, (rows,)), _lib.DBG_LP: (np.float64, (rows, 2)),
@@ -240,6 +255,8 @@ def monotonic_rnnt_loss(acts, labels, input_lengths, label_lengths, alignment: O
     Arguments as in the reference (monotonic_rnnt_op.py:121-152): ``acts`` packed
     [sum_b T_b*(S_b+1), V] float32, ``labels`` [B, max_b S_b] int32, ``input_lengths`` / ``label_lengths``
     [B] int32, optional ``alignment`` [B, max_b T_b] int32 with ``max_distance_from_alignment``.
+    Extension: ``acts`` may be the padded joint-network output [B, T, U, V] (then ``labels`` is [B, S] with any
+    S >= max_b S_b); its gradient has the same shape, zero in the padding.
     Returns a float32 tensor [B] on ``acts.device``.
     """
     result = MonotonicRNNTFunction.apply(acts, labels, input_lengths, label_lengths, alignment,

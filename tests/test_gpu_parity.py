@@ -127,7 +127,8 @@ SHAPES = [
     ("s_gt_64", 2, 12, (150, 170), (70, 120), "uniform"),
     ("s_gt_128", 2, 8, (300, 310), (130, 250), "uniform"),
     ("s_gt_256", 1, 8, (530, 540), (260, 500), "uniform"),
-    ("s_gt_512_wide_kernel", 1, 8, (620, 640), (520, 600), "uniform"),
+    ("s_gt_512_k4", 1, 8, (620, 640), (520, 600), "uniform"),
+    ("s_gt_768_wide_kernel", 1, 8, (830, 840), (770, 800), "normal3"),
 ]
 
 
@@ -257,3 +258,110 @@ def test_backward_half_scales_per_utterance(gu, name):
     with pytest.raises(mr.RNNTError):
         h2.enqueue_backward(g, None)                              # the forward kept no coefficients
     h.close(); h2.close()
+
+
+def _pad_case(case, extra_T, extra_U, extra_S):
+    """The packed case as the joint network would hold it: [B, T_dim, U, V] with NaN in every padded row (nothing
+    there may ever be read), labels [B, S_dim] with an out-of-range label in the padding."""
+    T, S = case.T.astype(np.int64), case.S.astype(np.int64)
+    T_dim, U = int(T.max()) + extra_T, int(S.max()) + 1 + extra_U
+    S_dim = max(int(S.max()) + extra_S, 1)
+    acts4 = np.full((case.B, T_dim, U, case.V), np.nan, dtype=np.float32)
+    packed = case.acts.reshape(case.rows, case.V)
+    labels = np.full((case.B, S_dim), 2 ** 30, dtype=np.int32)
+    off = 0
+    for b in range(case.B):
+        n = int(T[b] * (S[b] + 1))
+        acts4[b, :T[b], :S[b] + 1] = packed[off:off + n].reshape(T[b], S[b] + 1, case.V)
+        labels[b, :S[b]] = case.labels[b, :S[b]]
+        off += n
+    return acts4, labels
+
+
+@pytest.mark.parametrize("name,extra", [("rand_v32", (0, 0, 0)), ("rand_v32", (3, 2, 4)), ("rand_v17_shift1", (1, 5, 0)),
+                                        ("rand_edges", (2, 1, 1)), ("rand_wide_shift3", (0, 3, 2)), ("readme", (0, 0, 0))])
+def test_padded_layout_matches_packed(gu, name, extra):
+    """the padded [B,T,U,V] entry gives the packed results, never reads the padding (NaN there) and
+    writes exact zeros into the padded gradient rows; forward/backward halves and the autograd op included."""
+    import monotonic_rnnt_b200 as mr
+    import gpu_util
+    case, ref = golden_io.load(name)
+    acts4, labels = _pad_case(case, *extra)
+    T64, S64 = case.T.astype(np.int64), case.S.astype(np.int64)
+    acts = torch.from_numpy(acts4).cuda()
+    lab = torch.from_numpy(labels).cuda()
+    T = gpu_util.to_dev(case.T, torch.int32); S = gpu_util.to_dev(case.S, torch.int32)
+    h = mr.LossHandle(acts, lab, T, S)
+    if case.alignment is not None:
+        h.restrict_to_alignment(gpu_util.to_dev(case.alignment, torch.int32), case.max_shift, case.blank)
+    grads = torch.full_like(acts, float("nan"))
+    costs = h.cost_and_grad(case.blank, grads).numpy()
+    np.testing.assert_allclose(costs, ref["costs_f64"], rtol=COST_RTOL)
+    g = grads.cpu().numpy()
+    want = np.zeros_like(g, dtype=np.float64)
+    off = 0
+    for b in range(case.B):
+        n = int(T64[b] * (S64[b] + 1))
+        want[b, :T64[b], :S64[b] + 1] = ref["grads_f64"][off:off + n].reshape(T64[b], S64[b] + 1, case.V)
+        off += n
+    assert np.isfinite(g).all()
+    assert np.abs(g - want).max() <= GRAD_ATOL
+    pad = np.ones(g.shape[:3], dtype=bool)
+    for b in range(case.B):
+        pad[b, :T64[b], :S64[b] + 1] = False
+    assert np.all(g[pad] == 0.0)                                   # exact zeros, written (the buffer held NaN)
+    c2 = h.cost(case.blank).numpy()
+    assert np.array_equal(c2, costs)
+    h.close()
+    if case.alignment is None:
+        a = acts.clone().requires_grad_(True)
+        w = torch.linspace(-1.0, 2.0, case.B, device="cuda")
+        (mr.monotonic_rnnt_loss(a, lab, T, S, blank_label=case.blank) * w).sum().backward()
+        assert a.grad.shape == acts.shape
+        scale = w.cpu().numpy().astype(np.float64)[:, None, None, None]
+        assert np.abs(a.grad.cpu().numpy() - want * scale).max() <= GRAD_ATOL * 2
+
+
+def test_padded_layout_validation(gu):
+    import monotonic_rnnt_b200 as mr
+    import gpu_util
+    case, _ = golden_io.load("rand_v32")
+    acts4, labels = _pad_case(case, 0, 0, 0)
+    T = gpu_util.to_dev(case.T, torch.int32); S = gpu_util.to_dev(case.S, torch.int32)
+    with pytest.raises(mr.RNNTError):                              # U smaller than max S + 1
+        mr.LossHandle(torch.from_numpy(acts4[:, :, :-1].copy()).cuda(), torch.from_numpy(labels).cuda(), T, S)
+    with pytest.raises(mr.RNNTError):                              # fewer frames than max T
+        mr.LossHandle(torch.from_numpy(acts4[:, :-1].copy()).cuda(), torch.from_numpy(labels).cuda(), T, S)
+    if labels.shape[1] > 1:
+        with pytest.raises(mr.RNNTError):                          # labels narrower than max S
+            mr.LossHandle(torch.from_numpy(acts4).cuda(), torch.from_numpy(labels[:, :-1].copy()).cuda(), T, S)
+
+
+@pytest.mark.parametrize("shape", [("pad_s_gt_32", 3, 16, (70, 90), (33, 60), "normal3"),
+                                   ("pad_s_gt_128", 2, 8, (300, 310), (130, 250), "uniform"),
+                                   ("pad_wide_kernel", 1, 8, (830, 840), (770, 800), "uniform")], ids=lambda s: s[0])
+def test_padded_layout_multi_warp_rows(gu, shape):
+    """Padded layout through the multi-warp lattice rows and the wide fallback kernel."""
+    import monotonic_rnnt_b200 as mr
+    import gpu_util
+    name, B, V, tr, sr, dist = shape
+    case = fixtures.random_case(name, 77, B=B, V=V, T_range=tr, S_range=sr, dist=dist)
+    o64 = _oracle(case, "f64_from_f32")
+    acts4, labels = _pad_case(case, 2, 3, 1)
+    acts = torch.from_numpy(acts4).cuda()
+    h = mr.LossHandle(acts, torch.from_numpy(labels).cuda(), gpu_util.to_dev(case.T, torch.int32),
+                      gpu_util.to_dev(case.S, torch.int32))
+    grads = torch.full_like(acts, float("nan"))
+    costs = h.cost_and_grad(case.blank, grads).numpy()
+    _check_costs(costs, o64.costs)
+    g = grads.cpu().numpy()
+    T64, S64 = case.T.astype(np.int64), case.S.astype(np.int64)
+    off = 0
+    for b in range(case.B):
+        n = int(T64[b] * (S64[b] + 1))
+        blk = g[b, :T64[b], :S64[b] + 1].reshape(n, case.V)
+        assert np.abs(blk - o64.grads.reshape(-1, case.V)[off:off + n]).max() <= GRAD_ATOL
+        g[b, :T64[b], :S64[b] + 1] = 0.0
+        off += n
+    assert np.all(g == 0.0)
+    h.close()

@@ -69,6 +69,27 @@ def test_workspace_size_query_and_validation():
     assert lib.mrnnt_create(ctypes.byref(h), None, None, 0, None, None, 3, None, None) == 2
 
 
+def test_padded_layout_size_query_and_validation():
+    """mrnnt_get_workspace_size_padded: the tensor dimensions must cover every utterance."""
+    lib = _lib.load()
+    T = np.array([5, 9, 7], np.int32); S = np.array([2, 4, 0], np.int32)
+    out = ctypes.c_size_t(0)
+
+    def q(T_dim, U, stride):
+        return lib.mrnnt_get_workspace_size_padded(T.ctypes.data, S.ctypes.data, 3, 11, T_dim, U, stride, ctypes.byref(out))
+
+    assert q(9, 5, 4) == 0
+    exact = out.value
+    assert exact > 3 * 9 * 5 * 56
+    assert q(12, 8, 6) == 0 and out.value > exact                   # sized by the padded extent
+    assert q(8, 5, 4) == 2 and q(9, 4, 4) == 2 and q(9, 5, 3) == 2  # too few frames / states / label columns
+    assert q(9, 5, 0) == 0                                          # label stride 0: the reference rule, max S
+    assert q(0, 5, 4) == 2 and q(9, 0, 4) == 2
+    h = ctypes.c_void_p()
+    assert lib.mrnnt_create_padded(ctypes.byref(h), None, None, 3, None, None, 11, 8, 5, 4, T.ctypes.data,
+                                   S.ctypes.data) == 2              # validated at creation when lengths are given
+
+
 def test_no_cpu_fallback():
     c = fixtures.readme_case()
     t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt)

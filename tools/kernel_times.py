@@ -18,12 +18,19 @@ import monotonic_rnnt_b200 as mr  # noqa: E402
 from monotonic_rnnt_b200 import _lib  # noqa: E402
 
 
-def run(name: str, iters: int, combos) -> None:
+def run(name: str, iters: int, combos, padded: bool = False) -> None:
     wl = mr.synth.workload(name)
     dev = torch.device("cuda", 0)
     lib = _lib.load()
-    acts = torch.empty((wl.rows, wl.V), dtype=torch.float32, device=dev)
-    _lib.check(lib.mrnnt_synth_uniform(acts.data_ptr(), wl.elements, 0, 0, torch.cuda.current_stream().cuda_stream), "s")
+    if padded:   # the joint network's own [B, T_max, S_max+1, V] tensor; the padding holds ordinary numbers too
+        shape = (wl.B, int(wl.T.max()), int(wl.S.max()) + 1, wl.V)
+        acts = torch.empty(shape, dtype=torch.float32, device=dev)
+        _lib.check(lib.mrnnt_synth_uniform(acts.data_ptr(), acts.numel(), 0, 0,
+                                           torch.cuda.current_stream().cuda_stream), "s")
+    else:
+        acts = torch.empty((wl.rows, wl.V), dtype=torch.float32, device=dev)
+        _lib.check(lib.mrnnt_synth_uniform(acts.data_ptr(), wl.elements, 0, 0,
+                                           torch.cuda.current_stream().cuda_stream), "s")
     labels = torch.from_numpy(wl.labels).to(dev)
     T = torch.from_numpy(wl.T).to(dev)
     S = torch.from_numpy(wl.S).to(dev)
@@ -49,7 +56,8 @@ def run(name: str, iters: int, combos) -> None:
                 wall.append(ev0.elapsed_time(ev1))
         k = np.median(np.array(ts), axis=0)
         w = float(np.median(wall))
-        print(f"{wl.name} B={wl.B} V={wl.V} rows={wl.rows} k1w={k1w} k3w={k3w}: "
+        print(f"{wl.name}{' PADDED rows=' + str(acts.numel() // wl.V) if padded else ''} B={wl.B} V={wl.V} rows={wl.rows} "
+              f"k1w={k1w} k3w={k3w}: "
               f"K1 {k[0]*1e3:7.1f} us ({n4/k[0]/1e6:6.0f} GB/s of 4N)  K2 {k[1]*1e3:7.1f} us  "
               f"K3 {k[2]*1e3:7.1f} us ({2*n4/k[2]/1e6:6.0f} GB/s of 8N)  call {w*1e3:7.1f} us "
               f"({3*n4/w/1e6:6.0f} GB/s of 12N, {wl.B/w*1e3:8.0f} utt/s)", flush=True)
@@ -67,8 +75,9 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("workloads", nargs="*", default=["c2"])
     ap.add_argument("--iters", type=int, default=20)
-    ap.add_argument("--combos", default="8:8,16:8,8:16,16:16")
+    ap.add_argument("--combos", default="24:24")
+    ap.add_argument("--padded", action="store_true", help="feed the padded [B,T,S+1,V] tensor instead of packed rows")
     a = ap.parse_args()
     combos = [tuple(int(x) for x in c.split(":")) for c in a.combos.split(",")]
     for name in a.workloads:
-        run(name, a.iters, combos)
+        run(name, a.iters, combos, a.padded)
