@@ -236,16 +236,21 @@ def run_b200(args) -> None:
         if world == 1:
             handle.cost_and_grad(wl.blank, grads, costs_host)  # the C-ABI call: costs on the host on return
             return
-        # N > 1: the same three kernels without a host round trip in between, then the path's only collective
-        # (all-reduce of the summed cost, 4 bytes over NVLink) in stream order, and ONE synchronisation at
+        # N > 1: the same three kernels without a host round trip in between.  The costs are final after K2, so the
+        # path's only collective (all-reduce of the summed cost, 4 bytes over NVLink) runs on NCCL's stream WHILE
+        # K3 streams the gradients (measured: no SM needs to be set aside for it); ONE synchronisation at the end, at
         # which the per-utterance costs and the global sum are on the host.
-        dev_costs = handle.enqueue(wl.blank, grads)
+        dev_costs = handle.enqueue_forward(wl.blank, want_grads=True)
         total = dev_costs.sum()
-        dist.all_reduce(total)
+        work = dist.all_reduce(total, async_op=True)
+        handle.enqueue_backward(grads)
+        work.wait()
         costs_host.copy_(dev_costs, non_blocking=True)
         cost_sum_host.copy_(total, non_blocking=True)
         stream.synchronize()
 
+    if world > 1:
+        handle.set_option(_lib.OPT_RESERVED_SMS, args.reserve_sms)
     clocks = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         one_step()
@@ -418,6 +423,8 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-CPU baseline/checker leg")
+    ap.add_argument("--reserve-sms", type=int, default=0,
+                    help="N > 1: SMs the gradient kernel leaves to the concurrent all-reduce")
     args = ap.parse_args()
     args.out_fd = _claim_stdout()
     if args.impl == "reference":

@@ -296,6 +296,8 @@ class Engine {
 
     // Force the generic (non-TMA) streaming kernels; used by the tests to cross-check both variants.
     void set_force_generic(bool v) { force_generic_ = v; }
+    // SMs the gradient kernel leaves free for a concurrent collective (0: none).
+    void set_reserved_sms(int n) { reserved_sms_ = n < 0 ? 0 : n; }
     // Upper limit for the CTAs per utterance of the lattice kernel's coefficient phase (0: automatic).
     void set_k2_parts(int parts) { k2_parts_ = parts < 0 ? 0 : parts; }
     // Consumer warps per CTA of the streaming kernels (8 or 16); tuning knob for the bench.
@@ -438,8 +440,11 @@ class Engine {
                              float *grads, const float *scale) {
         auto kern = k3_grad_tma_kernel<NW, SCALED>;
         if (!ensure_dynamic_smem(kern, tl.smem_bytes)) return RNNT_STATUS_EXECUTION_FAILED;
-        kern<<<dev.sm_count, (NW + 1) * kWarp, tl.smem_bytes, stream>>>(acts_, ws_.coef, grads, shape_.rows, V_, blank,
-                                                                         tl.G, tl.stages, ws_.rowutt, scale);
+        // K3 is persistent with one CTA per SM; `reserved_sms_` of them can be left to a collective that runs
+        // concurrently on another stream (the all-reduce of the summed cost, which is final after K2)
+        const int grid = dev.sm_count - reserved_sms_ > 0 ? dev.sm_count - reserved_sms_ : 1;
+        kern<<<grid, (NW + 1) * kWarp, tl.smem_bytes, stream>>>(acts_, ws_.coef, grads, shape_.rows, V_, blank, tl.G,
+                                                                 tl.stages, ws_.rowutt, scale);
         return launched();
     }
 
@@ -483,6 +488,7 @@ class Engine {
     int k1_warps_ = 24;
     int k3_warps_ = 24;
     int k2_parts_ = 0;     // 0: automatic
+    int reserved_sms_ = 0;
     unsigned epoch_ = 0u;  // launch counter published through Workspace::k2_flags
     int coef_blank_ = -1;  // blank label of the forward pass whose coefficients sit in the workspace (-1: none)
     bool timing_ = false;

@@ -89,7 +89,8 @@ enum {
     MRNNT_OPT_TIMING = 2,        /* value != 0: record CUDA events around K1 / K2 / K3 of every call */
     MRNNT_OPT_K1_WARPS = 3,      /* consumer warps per CTA of K1 (8, 16, 24)                            */
     MRNNT_OPT_K3_WARPS = 4,      /* consumer warps per CTA of K3 (8, 16, 24)                            */
-    MRNNT_OPT_K2_PARTS = 5       /* upper limit of CTAs per utterance in K2's coefficient phase (0: auto) */
+    MRNNT_OPT_K2_PARTS = 5,      /* upper limit of CTAs per utterance in K2's coefficient phase (0: auto) */
+    MRNNT_OPT_RESERVED_SMS = 6   /* SMs the gradient kernel leaves free for a concurrent collective (0)    */
 };
 RNNTStatus mrnnt_set_option(mrnnt_handle_t h, int option, int value);
 /* Durations in ms of K1, K2, K3 of the last call (MRNNT_OPT_TIMING on, stream synchronised). */
