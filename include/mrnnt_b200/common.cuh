@@ -158,6 +158,15 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 
 // ---------------------------------------------------------------------------------------------
+// programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start (launch latency, prologue) while its predecessor in the stream is still draining; it must not touch the
+// predecessor's results before pdl_wait() (which returns once the predecessor has completed and flushed).  Both
+// are no-ops in a kernel launched the ordinary way.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
 // streaming global stores / loads
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void st_stream_f4(float4 *p, const float4 &v) {

@@ -87,6 +87,23 @@ inline bool ensure_dynamic_smem(Kern kern, size_t bytes) {
     return true;
 }
 
+// Kernel launch, optionally as a programmatic dependent of the previous kernel in the stream (common.cuh).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, bool pdl,
+                                 Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(static_cast<unsigned>(block));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // Validation rules of the reference (gpu_workspace_manager.h:232-239, cpu twin :99-107).
 // Padded layout: T_dim / U (= label positions + 1) are the tensor's own dimensions and must cover every
 // utterance; label_stride is the width of the labels array (0: the reference's rule, max_b S_b).
@@ -231,7 +248,10 @@ class Engine {
     RNNTStatus enqueue(int blank, cudaStream_t stream, float *grads_dev) {
         RNNTStatus st = enqueue_forward(blank, stream, grads_dev != nullptr);
         if (st != RNNT_STATUS_SUCCESS || grads_dev == nullptr) return st;
-        return enqueue_backward(stream, grads_dev, nullptr);
+        k3_follows_k2_ = !timing_;  // (the timing events between the kernels would break the dependent launch)
+        st = enqueue_backward(stream, grads_dev, nullptr);
+        k3_follows_k2_ = false;
+        return st;
     }
 
     // First half of a call: K1 and K2.  With want_grads the lattice kernel also leaves the per-row gradient
@@ -296,6 +316,7 @@ class Engine {
 
     // Force the generic (non-TMA) streaming kernels; used by the tests to cross-check both variants.
     void set_force_generic(bool v) { force_generic_ = v; }
+    void set_pdl(bool on) { pdl_ = on; }
     // SMs the gradient kernel leaves free for a concurrent collective (0: none).
     void set_reserved_sms(int n) { reserved_sms_ = n < 0 ? 0 : n; }
     // Upper limit for the CTAs per utterance of the lattice kernel's coefficient phase (0: automatic).
@@ -396,7 +417,8 @@ class Engine {
         auto kern = k2_lattice_kernel<K>;
         const size_t smem = k2_smem_bytes(shape_.width(), args.row_warps);
         if (!ensure_dynamic_smem(kern, smem)) return RNNT_STATUS_EXECUTION_FAILED;
-        kern<<<B_ * args.parts, kK2Threads, smem, stream>>>(args);
+        if (launch_kernel(kern, B_ * args.parts, kK2Threads, smem, stream, pdl_ && !timing_, args) != cudaSuccess)
+            return RNNT_STATUS_EXECUTION_FAILED;
         return launched();
     }
 
@@ -443,8 +465,11 @@ class Engine {
         // K3 is persistent with one CTA per SM; `reserved_sms_` of them can be left to a collective that runs
         // concurrently on another stream (the all-reduce of the summed cost, which is final after K2)
         const int grid = dev.sm_count - reserved_sms_ > 0 ? dev.sm_count - reserved_sms_ : 1;
-        kern<<<grid, (NW + 1) * kWarp, tl.smem_bytes, stream>>>(acts_, ws_.coef, grads, shape_.rows, V_, blank, tl.G,
-                                                                 tl.stages, ws_.rowutt, scale);
+        // (a dependent launch only right behind the lattice kernel: a backward pass called on its own has no such
+        // predecessor to wait for, and an ordinary launch orders it behind whatever precedes it in the stream)
+        if (launch_kernel(kern, grid, (NW + 1) * kWarp, tl.smem_bytes, stream, pdl_ && k3_follows_k2_, acts_, ws_.coef,
+                          grads, shape_.rows, V_, blank, tl.G, tl.stages, ws_.rowutt, scale) != cudaSuccess)
+            return RNNT_STATUS_EXECUTION_FAILED;
         return launched();
     }
 
@@ -489,6 +514,8 @@ class Engine {
     int k3_warps_ = 24;
     int k2_parts_ = 0;     // 0: automatic
     int reserved_sms_ = 0;
+    bool pdl_ = true;             // programmatic dependent launch of K2 behind K1 and of K3 behind K2
+    bool k3_follows_k2_ = false;  // K3 is being enqueued directly behind K2 (enqueue(), not a separate backward)
     unsigned epoch_ = 0u;  // launch counter published through Workspace::k2_flags
     int coef_blank_ = -1;  // blank label of the forward pass whose coefficients sit in the workspace (-1: none)
     bool timing_ = false;

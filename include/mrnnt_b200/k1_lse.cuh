@@ -221,6 +221,8 @@ static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
         mbar_init_fence();
     }
     __syncthreads();
+    pdl_launch_dependents();  // the lattice kernel may be scheduled as our CTAs retire (it waits for all of us)
+    pdl_wait();               // (first kernel of a call: its predecessor is the previous call or a set-up kernel)
 
     const int64_t ntiles = (rows + G - 1) / G;
     const int64_t nloc = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;

@@ -562,6 +562,8 @@ static __global__ void __launch_bounds__(kK2Threads) k2_lattice_kernel(K2Args a)
     unsigned *arrived = a.flags + 2 * b;  // phase-A arrivals of this utterance's parts
     unsigned *done = arrived + 1;         // epoch of the last finished recursion
     MRNNT_K2_STAMP(0);
+    pdl_launch_dependents();  // the gradient kernel may be scheduled as our CTAs retire (it waits for all of us)
+    pdl_wait();               // K1's records
 
     // ---- phase A: transition weights, all parts ----
     k2_weight_rows(a, b, part, parts);

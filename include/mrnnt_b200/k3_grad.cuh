@@ -93,6 +93,7 @@ static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
         mbar_init_fence();
     }
     __syncthreads();
+    pdl_wait();  // the coefficients come from the lattice kernel; everything above overlapped its tail
 
     const int64_t ntiles = (rows + G - 1) / G;
     const int64_t nloc = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
