@@ -5,6 +5,7 @@
 // nothing but `-I include`, so the whole hot path has to be reachable that way.
 #pragma once
 
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
@@ -158,6 +159,53 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Element types of the logits / gradients.  The reference computes on float32 only
+// (pytorch_binding/monotonic_rnnt.cu:84); bfloat16 is an extension that halves the bytes the two
+// streaming kernels move.  All arithmetic stays in float: a 16-byte vector is unpacked to kPerVec floats on
+// arrival and packed (round to nearest even) on the way out.
+// ---------------------------------------------------------------------------------------------
+template <typename E>
+struct Elem;
+template <>
+struct Elem<float> {
+    static constexpr int kPerVec = 4;
+    static __device__ __forceinline__ void unpack(const uint4 &r, float (&f)[4]) {
+        f[0] = __uint_as_float(r.x);
+        f[1] = __uint_as_float(r.y);
+        f[2] = __uint_as_float(r.z);
+        f[3] = __uint_as_float(r.w);
+    }
+    static __device__ __forceinline__ uint4 pack(const float (&f)[4]) {
+        return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+    }
+    static __device__ __forceinline__ float to_float(float v) { return v; }
+    static __device__ __forceinline__ float from_float(float v) { return v; }
+};
+template <>
+struct Elem<__nv_bfloat16> {
+    static constexpr int kPerVec = 8;
+    static __device__ __forceinline__ void unpack(const uint4 &r, float (&f)[8]) {
+        const unsigned w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {  // a bfloat16 is the upper half of the float with the same value
+            f[2 * i] = __uint_as_float(w[i] << 16);
+            f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+    static __device__ __forceinline__ uint4 pack(const float (&f)[8]) {
+        unsigned w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const __nv_bfloat162 p = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+            w[i] = *reinterpret_cast<const unsigned *>(&p);
+        }
+        return make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    static __device__ __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+    static __device__ __forceinline__ __nv_bfloat16 from_float(float v) { return __float2bfloat16_rn(v); }
+};
+
+// ---------------------------------------------------------------------------------------------
 // programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
 // start (launch latency, prologue) while its predecessor in the stream is still draining; it must not touch the
 // predecessor's results before pdl_wait() (which returns once the predecessor has completed and flushed).  Both
@@ -171,6 +219,10 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void st_stream_f4(float4 *p, const float4 &v) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void st_stream_u4(uint4 *p, const uint4 &v) {
+    asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                  : "memory");
 }
 

@@ -135,11 +135,15 @@ inline RNNTStatus validate_lengths(const int *T_host, const int *S_host, int B, 
 
 class Engine {
    public:
-    Engine(const float *acts, const int *labels, int B, const int *T_dev, const int *S_dev, int V)
+    Engine(const void *acts, const int *labels, int B, const int *T_dev, const int *S_dev, int V)
         : acts_(acts), labels_(labels), T_dev_(T_dev), S_dev_(S_dev), B_(B), V_(V) {}
 
     Engine(const Engine &) = delete;
     Engine &operator=(const Engine &) = delete;
+
+    // Extension: acts and gradients are bfloat16 instead of float32; arithmetic stays float.
+    void set_bf16(bool on) { bf16_ = on; }
+    bool bf16() const { return bf16_; }
 
     // acts (and gradients) are a padded [B, T_dim, U, V] tensor, labels [B, label_stride] (see Shape).  Must be
     // called before the first size query.
@@ -231,7 +235,7 @@ class Engine {
     int B() const { return B_; }
 
     // costs_host: B floats on the host (valid on return).  grads_dev: packed like acts, or nullptr.
-    RNNTStatus compute(int blank, cudaStream_t stream, float *costs_host, float *grads_dev) {
+    RNNTStatus compute(int blank, cudaStream_t stream, float *costs_host, void *grads_dev) {
         if (costs_host == nullptr) return RNNT_STATUS_INVALID_VALUE;
         RNNTStatus st = ensure_shape();
         if (st != RNNT_STATUS_SUCCESS) return st;
@@ -245,7 +249,7 @@ class Engine {
     }
 
     // Launch everything on `stream` without synchronising; costs stay in workspace().costs.
-    RNNTStatus enqueue(int blank, cudaStream_t stream, float *grads_dev) {
+    RNNTStatus enqueue(int blank, cudaStream_t stream, void *grads_dev) {
         RNNTStatus st = enqueue_forward(blank, stream, grads_dev != nullptr);
         if (st != RNNT_STATUS_SUCCESS || grads_dev == nullptr) return st;
         k3_follows_k2_ = !timing_;  // (the timing events between the kernels would break the dependent launch)
@@ -279,7 +283,7 @@ class Engine {
     // Second half: K3, the gradient w.r.t. the logits.  scale_dev (optional, B floats on the device): utterance
     // b's gradient rows are multiplied by scale_dev[b] as they are written -- the upstream gradient of the
     // per-utterance costs (reference glue: pytorch_binding/monotonic_rnnt_op.py:97-118).
-    RNNTStatus enqueue_backward(cudaStream_t stream, float *grads_dev, const float *scale_dev) {
+    RNNTStatus enqueue_backward(cudaStream_t stream, void *grads_dev, const float *scale_dev) {
         const DeviceInfo &dev = device_info();
         if (!dev.ok) return RNNT_STATUS_EXECUTION_FAILED;
         if (grads_dev == nullptr || coef_blank_ < 0) return RNNT_STATUS_INVALID_VALUE;
@@ -368,7 +372,8 @@ class Engine {
         if ((reinterpret_cast<uintptr_t>(p0) & 15) || (reinterpret_cast<uintptr_t>(p1) & 15)) return false;
         const int order[3] = {preferred_warps, 16, 8};
         for (int w : order) {
-            if (stream_tiling(V_, extra_per_row, w, tl) && tl->smem_bytes <= static_cast<size_t>(dev.max_smem_optin))
+            if (stream_tiling(V_, elem_bytes(), extra_per_row, w, tl) &&
+                tl->smem_bytes <= static_cast<size_t>(dev.max_smem_optin))
                 return true;
         }
         return false;
@@ -380,36 +385,47 @@ class Engine {
         return static_cast<int>(want < cap ? (want < 1 ? 1 : want) : cap);
     }
 
-    template <int NW, int C>
+    template <typename E, int NW, int C>
     RNNTStatus launch_k1_tma(int blank, cudaStream_t stream, const DeviceInfo &dev, const StreamTiling &tl) {
-        auto kern = k1_lse_tma_kernel<NW, C>;
+        auto kern = k1_lse_tma_kernel<E, NW, C>;
         if (!ensure_dynamic_smem(kern, tl.smem_bytes)) return RNNT_STATUS_EXECUTION_FAILED;
-        kern<<<dev.sm_count, (NW + 1) * kWarp, tl.smem_bytes, stream>>>(acts_, labels_, ws_.rowmeta, ws_.lp, shape_.rows,
-                                                                         V_, blank, tl.G, tl.stages);
+        kern<<<dev.sm_count, (NW + 1) * kWarp, tl.smem_bytes, stream>>>(static_cast<const E *>(acts_), labels_, ws_.rowmeta,
+                                                                         ws_.lp, shape_.rows, V_, blank, tl.G, tl.stages);
         return launched();
     }
 
-    template <int NW>
+    // C = 16-byte vectors a lane keeps in registers: a row in 32 floats per lane, in 64, or two passes over smem
+    template <typename E, int NW>
     RNNTStatus launch_k1_nw(int blank, cudaStream_t stream, const DeviceInfo &dev, const StreamTiling &tl) {
-        const int V4 = V_ / 4;
-        if (V4 <= 8 * kWarp) return launch_k1_tma<NW, 8>(blank, stream, dev, tl);    // row in 32 registers / lane
-        if (V4 <= 16 * kWarp) return launch_k1_tma<NW, 16>(blank, stream, dev, tl);  // 64 registers / lane
-        return launch_k1_tma<NW, 0>(blank, stream, dev, tl);                         // two passes over smem
+        constexpr int NE = Elem<E>::kPerVec;
+        const int NV = V_ / NE;
+        if (NV <= (32 / NE) * kWarp) return launch_k1_tma<E, NW, 32 / NE>(blank, stream, dev, tl);
+        if constexpr (NW < 24) {  // (launch_k1_typed never asks for 24 warps with 64 registers of row per lane)
+            if (NV <= (64 / NE) * kWarp) return launch_k1_tma<E, NW, 64 / NE>(blank, stream, dev, tl);
+        }
+        return launch_k1_tma<E, NW, 0>(blank, stream, dev, tl);
+    }
+
+    template <typename E>
+    RNNTStatus launch_k1_typed(int blank, cudaStream_t stream, const DeviceInfo &dev) {
+        StreamTiling tl;
+        // rows held in 64 registers per lane are too many for 25 warps on one SM
+        constexpr int NE = Elem<E>::kPerVec;
+        const int NV = V_ / NE;
+        const bool wide_regs = NV > (32 / NE) * kWarp && NV <= (64 / NE) * kWarp;
+        const int want = (k1_warps_ == 24 && wide_regs) ? 16 : k1_warps_;
+        if (can_stream(acts_, acts_, 0, want, dev, &tl)) {
+            return tl.warps == 8    ? launch_k1_nw<E, 8>(blank, stream, dev, tl)
+                   : tl.warps == 16 ? launch_k1_nw<E, 16>(blank, stream, dev, tl)
+                                    : launch_k1_nw<E, 24>(blank, stream, dev, tl);
+        }
+        k1_lse_generic_kernel<E><<<generic_grid(dev), kGenericWarps * kWarp, 0, stream>>>(
+            static_cast<const E *>(acts_), labels_, ws_.rowmeta, ws_.lp, shape_.rows, V_, blank);
+        return launched();
     }
 
     RNNTStatus launch_k1(int blank, cudaStream_t stream, const DeviceInfo &dev) {
-        StreamTiling tl;
-        // rows of 1028..2048 logits are held in 64 registers per lane: too many for 25 warps on one SM
-        const int V4 = V_ / 4;
-        const int want = (k1_warps_ == 24 && V4 > 8 * kWarp && V4 <= 16 * kWarp) ? 16 : k1_warps_;
-        if (can_stream(acts_, acts_, 0, want, dev, &tl)) {
-            return tl.warps == 8    ? launch_k1_nw<8>(blank, stream, dev, tl)
-                   : tl.warps == 16 ? launch_k1_nw<16>(blank, stream, dev, tl)
-                                    : launch_k1_nw<24>(blank, stream, dev, tl);
-        }
-        k1_lse_generic_kernel<<<generic_grid(dev), kGenericWarps * kWarp, 0, stream>>>(
-            acts_, labels_, ws_.rowmeta, ws_.lp, shape_.rows, V_, blank);
-        return launched();
+        return bf16_ ? launch_k1_typed<__nv_bfloat16>(blank, stream, dev) : launch_k1_typed<float>(blank, stream, dev);
     }
 
     template <int K>
@@ -457,39 +473,49 @@ class Engine {
         return launched();
     }
 
-    template <int NW, bool SCALED>
-    RNNTStatus launch_k3_tma(int blank, cudaStream_t stream, const DeviceInfo &dev, const StreamTiling &tl,
-                             float *grads, const float *scale) {
-        auto kern = k3_grad_tma_kernel<NW, SCALED>;
+    template <typename E, int NW, bool SCALED>
+    RNNTStatus launch_k3_tma(int blank, cudaStream_t stream, const DeviceInfo &dev, const StreamTiling &tl, void *grads,
+                             const float *scale) {
+        auto kern = k3_grad_tma_kernel<E, NW, SCALED>;
         if (!ensure_dynamic_smem(kern, tl.smem_bytes)) return RNNT_STATUS_EXECUTION_FAILED;
         // K3 is persistent with one CTA per SM; `reserved_sms_` of them can be left to a collective that runs
         // concurrently on another stream (the all-reduce of the summed cost, which is final after K2)
         const int grid = dev.sm_count - reserved_sms_ > 0 ? dev.sm_count - reserved_sms_ : 1;
         // (a dependent launch only right behind the lattice kernel: a backward pass called on its own has no such
         // predecessor to wait for, and an ordinary launch orders it behind whatever precedes it in the stream)
-        if (launch_kernel(kern, grid, (NW + 1) * kWarp, tl.smem_bytes, stream, pdl_ && k3_follows_k2_, acts_, ws_.coef,
-                          grads, shape_.rows, V_, blank, tl.G, tl.stages, ws_.rowutt, scale) != cudaSuccess)
+        if (launch_kernel(kern, grid, (NW + 1) * kWarp, tl.smem_bytes, stream, pdl_ && k3_follows_k2_,
+                          static_cast<const E *>(acts_), ws_.coef, static_cast<E *>(grads), shape_.rows, V_, blank, tl.G,
+                          tl.stages, ws_.rowutt, scale) != cudaSuccess)
             return RNNT_STATUS_EXECUTION_FAILED;
         return launched();
     }
 
-    RNNTStatus launch_k3(int blank, cudaStream_t stream, const DeviceInfo &dev, float *grads, const float *scale) {
+    template <typename E>
+    RNNTStatus launch_k3_typed(int blank, cudaStream_t stream, const DeviceInfo &dev, void *grads, const float *scale) {
         StreamTiling tl;
         if (can_stream(acts_, grads, sizeof(float4), k3_warps_, dev, &tl)) {
             if (scale != nullptr)
-                return tl.warps == 8    ? launch_k3_tma<8, true>(blank, stream, dev, tl, grads, scale)
-                       : tl.warps == 16 ? launch_k3_tma<16, true>(blank, stream, dev, tl, grads, scale)
-                                        : launch_k3_tma<24, true>(blank, stream, dev, tl, grads, scale);
-            return tl.warps == 8    ? launch_k3_tma<8, false>(blank, stream, dev, tl, grads, scale)
-                   : tl.warps == 16 ? launch_k3_tma<16, false>(blank, stream, dev, tl, grads, scale)
-                                    : launch_k3_tma<24, false>(blank, stream, dev, tl, grads, scale);
+                return tl.warps == 8    ? launch_k3_tma<E, 8, true>(blank, stream, dev, tl, grads, scale)
+                       : tl.warps == 16 ? launch_k3_tma<E, 16, true>(blank, stream, dev, tl, grads, scale)
+                                        : launch_k3_tma<E, 24, true>(blank, stream, dev, tl, grads, scale);
+            return tl.warps == 8    ? launch_k3_tma<E, 8, false>(blank, stream, dev, tl, grads, scale)
+                   : tl.warps == 16 ? launch_k3_tma<E, 16, false>(blank, stream, dev, tl, grads, scale)
+                                    : launch_k3_tma<E, 24, false>(blank, stream, dev, tl, grads, scale);
         }
-        k3_grad_generic_kernel<<<generic_grid(dev), kGenericWarps * kWarp, 0, stream>>>(
-            acts_, ws_.coef, grads, shape_.rows, V_, blank, ws_.rowutt, scale);
+        k3_grad_generic_kernel<E><<<generic_grid(dev), kGenericWarps * kWarp, 0, stream>>>(
+            static_cast<const E *>(acts_), ws_.coef, static_cast<E *>(grads), shape_.rows, V_, blank, ws_.rowutt, scale);
         return launched();
     }
 
-    const float *acts_;
+    RNNTStatus launch_k3(int blank, cudaStream_t stream, const DeviceInfo &dev, void *grads, const float *scale) {
+        return bf16_ ? launch_k3_typed<__nv_bfloat16>(blank, stream, dev, grads, scale)
+                     : launch_k3_typed<float>(blank, stream, dev, grads, scale);
+    }
+
+    size_t elem_bytes() const { return bf16_ ? 2 : 4; }
+
+    const void *acts_;   // float32 (the reference's type) or bfloat16 (set_bf16)
+    bool bf16_ = false;
     const int *labels_;
     const int *T_dev_;
     const int *S_dev_;

@@ -25,7 +25,14 @@
 
 namespace mrnnt {
 
-__device__ __forceinline__ float max4(const float4 &a) { return fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)); }
+// max over / exp-sum of the NE floats of one unpacked 16-byte vector
+template <int NE>
+__device__ __forceinline__ float vec_max(const float (&f)[NE]) {
+    float m = fmaxf(f[0], f[1]);
+#pragma unroll
+    for (int i = 2; i < NE; i += 2) m = fmaxf(m, fmaxf(f[i], f[i + 1]));
+    return m;
+}
 
 // Warp-wide float max with ONE redux.sync: floats are mapped to signed ints that sort the same way.
 __device__ __forceinline__ float warp_max_redux(float v) {
@@ -42,12 +49,11 @@ __device__ __forceinline__ float warp_sum_f(float v) {
     return v;
 }
 
-// sum over the lane's 4 components of 2^(x*log2e + neg)
-__device__ __forceinline__ void exp_acc(const float4 &a, float neg, float &s0, float &s1, float &s2, float &s3) {
-    s0 += ex2_approx(fmaf(a.x, kLog2e, neg));
-    s1 += ex2_approx(fmaf(a.y, kLog2e, neg));
-    s2 += ex2_approx(fmaf(a.z, kLog2e, neg));
-    s3 += ex2_approx(fmaf(a.w, kLog2e, neg));
+// four running sums of 2^(x*log2e + neg) over the NE floats of a vector
+template <int NE>
+__device__ __forceinline__ void exp_acc(const float (&f)[NE], float neg, float (&s)[4]) {
+#pragma unroll
+    for (int i = 0; i < NE; ++i) s[i & 3] += ex2_approx(fmaf(f[i], kLog2e, neg));
 }
 
 // From the warp-wide max (times log2 e, rounded once and used for every term) and the warp-wide sum of
@@ -68,37 +74,51 @@ __device__ __forceinline__ Denominator lse_finish(float ML, float sum) {
     return d;
 }
 
-// One row resident in shared memory (16-byte aligned, V4 float4).  C > 0: the lane's <= C float4 live
-// in registers (V4 <= 32*C); C == 0: two passes over shared memory, any V4.
-template <int C>
-__device__ __forceinline__ Denominator row_denominator(const float4 *__restrict__ x4, int V4, int lane) {
-    const float4 ninf = make_float4(kNegInfF, kNegInfF, kNegInfF, kNegInfF);
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+// One row resident in shared memory (16-byte aligned, NV vectors of 16 bytes = NV * Elem<E>::kPerVec logits).
+// C > 0: the lane's <= C vectors live in registers, unpacked (NV <= 32*C); C == 0: two passes over shared
+// memory, any NV.
+template <typename E, int C>
+__device__ __forceinline__ Denominator row_denominator(const uint4 *__restrict__ xv, int NV, int lane) {
+    constexpr int NE = Elem<E>::kPerVec;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
     float ML;
     if constexpr (C > 0) {
-        float4 v[C];
+        float f[C][NE];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const int j = lane + c * kWarp;
-            v[c] = (j < V4) ? x4[j] : ninf;
-        }
-        float m = max4(v[0]);
+            if ((c + 1) * kWarp <= NV || j < NV) {  // (the first test is warp-uniform: no per-lane selects for full vectors)
+                Elem<E>::unpack(xv[j], f[c]);
+            } else {
 #pragma unroll
-        for (int c = 1; c < C; ++c) m = fmaxf(m, max4(v[c]));
+                for (int i = 0; i < NE; ++i) f[c][i] = kNegInfF;
+            }
+        }
+        float m = vec_max<NE>(f[0]);
+#pragma unroll
+        for (int c = 1; c < C; ++c) m = fmaxf(m, vec_max<NE>(f[c]));
         ML = warp_max_redux(m) * kLog2e;
         const float neg = -ML;
 #pragma unroll
-        for (int c = 0; c < C; ++c) exp_acc(v[c], neg, s0, s1, s2, s3);
+        for (int c = 0; c < C; ++c) exp_acc<NE>(f[c], neg, s);
     } else {
         float m = kNegInfF;
 #pragma unroll 4
-        for (int j = lane; j < V4; j += kWarp) m = fmaxf(m, max4(x4[j]));
+        for (int j = lane; j < NV; j += kWarp) {
+            float f[NE];
+            Elem<E>::unpack(xv[j], f);
+            m = fmaxf(m, vec_max<NE>(f));
+        }
         ML = warp_max_redux(m) * kLog2e;
         const float neg = -ML;
 #pragma unroll 4
-        for (int j = lane; j < V4; j += kWarp) exp_acc(x4[j], neg, s0, s1, s2, s3);
+        for (int j = lane; j < NV; j += kWarp) {
+            float f[NE];
+            Elem<E>::unpack(xv[j], f);
+            exp_acc<NE>(f, neg, s);
+        }
     }
-    return lse_finish(ML, warp_sum_f((s0 + s1) + (s2 + s3)));
+    return lse_finish(ML, warp_sum_f((s[0] + s[1]) + (s[2] + s[3])));
 }
 
 // What lane 0 writes for one live row: the two gathered logits and the denominator (one 16-byte store).  The
@@ -119,8 +139,9 @@ __device__ __forceinline__ void k1_store_row(RawRow *__restrict__ lp, int64_t ro
 // ---------------------------------------------------------------------------------------------
 constexpr int kGenericWarps = 8;
 
+template <typename E>
 static __global__ void __launch_bounds__(kGenericWarps * kWarp)
-    k1_lse_generic_kernel(const float *__restrict__ acts, const int *__restrict__ labels,
+    k1_lse_generic_kernel(const E *__restrict__ acts, const int *__restrict__ labels,
                           const int *__restrict__ rowmeta, RawRow *__restrict__ lp, int64_t rows, int V, int blank) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * kGenericWarps + (threadIdx.x >> 5);
@@ -128,26 +149,35 @@ static __global__ void __launch_bounds__(kGenericWarps * kWarp)
     for (int64_t row = warp0; row < rows; row += nwarps) {
         const int meta = rowmeta[row];
         if (meta == kRowDead) continue;
-        const float *x = acts + row * V;
+        const E *x = acts + row * V;
         float m = kNegInfF;
-        for (int v = lane; v < V; v += kWarp) m = fmaxf(m, __ldg(x + v));
+        for (int v = lane; v < V; v += kWarp) m = fmaxf(m, Elem<E>::to_float(x[v]));
         const float ML = warp_max_redux(m) * kLog2e;
         float s = 0.f;
-        for (int v = lane; v < V; v += kWarp) s += ex2_approx(fmaf(__ldg(x + v), kLog2e, -ML));
+        for (int v = lane; v < V; v += kWarp) s += ex2_approx(fmaf(Elem<E>::to_float(x[v]), kLog2e, -ML));
         const Denominator den = lse_finish(ML, warp_sum_f(s));
         if (lane == 0) {
             const int lab = meta >= 0 ? __ldg(labels + meta) : -1;
             const bool has = lab >= 0 && lab < V;
-            k1_store_row(lp, row, den, __ldg(x + blank), has ? __ldg(x + lab) : kNegInfF);
+            k1_store_row(lp, row, den, Elem<E>::to_float(x[blank]), has ? Elem<E>::to_float(x[lab]) : kNegInfF);
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// TMA-staged variant.  Requirements (checked on the host): V % 4 == 0, acts 16-byte aligned,
-// G*V*4 <= ring slot size.
-// Shared memory: [stages][G*V] floats | full[stages] | empty[stages] | meta[stages][32]
+// TMA-staged variant.  Requirements (checked on the host): rows are whole 16-byte vectors (V % 4 == 0 for
+// float, V % 8 == 0 for bfloat16), acts 16-byte aligned, a tile fits a ring slot.
+// Shared memory: [stages][G*V] elements | full[stages] | empty[stages] | meta[stages][32]
 // ---------------------------------------------------------------------------------------------
+#ifdef MRNNT_K1_TRACE  // development aid (tools/k1_probe.cu): where the warps of CTA 0 spend their cycles
+__device__ long long g_k1_trace[32][4];  // per warp: cycles waiting, cycles working, rows/tiles, -
+#define MRNNT_K1_CLOCK() clock64()
+#define MRNNT_K1_ADD(w, i, v) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_k1_trace[w][i] += (v); } while (0)
+#else
+#define MRNNT_K1_CLOCK() 0ll
+#define MRNNT_K1_ADD(w, i, v) do { } while (0)
+#endif
+
 struct StreamTiling {
     int G = 0;       // rows per tile: a power of two in 1..32
     int stages = 0;  // ring depth
@@ -167,9 +197,9 @@ constexpr int kStreamTileTarget = 32 * 1024;      // bytes per ring slot we aim 
 // waiting warp also consumed the PREVIOUS use of that ring stage (bulk copies complete out of order, so
 // "an earlier tile was issued first" proves nothing).  Hence G is a power of two and the ring depth is a
 // multiple of the stride NW/G: every warp then cycles through a fixed subset of the stages.
-inline bool stream_tiling(int V, size_t extra_per_row, int warps, StreamTiling *out) {
-    if (V <= 0 || (V % 4) != 0 || (warps != 8 && warps != 16 && warps != 24)) return false;
-    const size_t row_bytes = static_cast<size_t>(V) * 4;
+inline bool stream_tiling(int V, size_t elem_bytes, size_t extra_per_row, int warps, StreamTiling *out) {
+    const size_t row_bytes = static_cast<size_t>(V) * elem_bytes;
+    if (V <= 0 || (row_bytes % 16) != 0 || (warps != 8 && warps != 16 && warps != 24)) return false;
     int G = 1;
     while (G < 32 && static_cast<size_t>(2 * G) * row_bytes <= static_cast<size_t>(kStreamTileTarget)) G *= 2;
     const size_t slot = static_cast<size_t>(G) * row_bytes + 32 * (sizeof(int) + extra_per_row) + 16;
@@ -187,9 +217,10 @@ inline bool stream_tiling(int V, size_t extra_per_row, int warps, StreamTiling *
 }
 
 // Issue one bulk copy per maximal run of live rows of a tile (called by one lane).
-__device__ __forceinline__ void issue_live_runs(uint32_t mask, float *tile, const float *src_row0, int V,
-                                                uint64_t *bar, uint64_t policy) {
-    const uint32_t row_bytes = static_cast<uint32_t>(V) * 4u;
+template <typename E>
+__device__ __forceinline__ void issue_live_runs(uint32_t mask, E *tile, const E *src_row0, int V, uint64_t *bar,
+                                                uint64_t policy) {
+    const uint32_t row_bytes = static_cast<uint32_t>(V) * static_cast<uint32_t>(sizeof(E));
     while (mask) {
         const int r0 = __ffs(mask) - 1;
         const uint32_t inv = ~(mask >> r0);
@@ -200,15 +231,15 @@ __device__ __forceinline__ void issue_live_runs(uint32_t mask, float *tile, cons
     }
 }
 
-template <int NW, int C>
+template <typename E, int NW, int C>
 static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
-    k1_lse_tma_kernel(const float *__restrict__ acts, const int *__restrict__ labels,
+    k1_lse_tma_kernel(const E *__restrict__ acts, const int *__restrict__ labels,
                       const int *__restrict__ rowmeta, RawRow *__restrict__ lp, int64_t rows, int V, int blank,
                       int G, int stages) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const size_t tile_floats = static_cast<size_t>(G) * V;
-    float *tiles = reinterpret_cast<float *>(smem_raw);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + static_cast<size_t>(stages) * tile_floats * 4);
+    const size_t tile_elems = static_cast<size_t>(G) * V;
+    E *tiles = reinterpret_cast<E *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + static_cast<size_t>(stages) * tile_elems * sizeof(E));
     uint64_t *empty = full + stages;
     int *meta_sh = reinterpret_cast<int *>(empty + stages);
 
@@ -242,12 +273,16 @@ static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
             m_next = load_meta(k + 1);  // one tile ahead: its latency hides behind this tile's wait
             const int64_t row0 = (blockIdx.x + k * gridDim.x) * G;
             const uint32_t mask = __ballot_sync(0xffffffffu, m != kRowDead);
+            const long long tw0 = MRNNT_K1_CLOCK();
             mbar_wait(empty + stage, phase ^ 1u);
+            MRNNT_K1_ADD(NW, 0, MRNNT_K1_CLOCK() - tw0);
+            MRNNT_K1_ADD(NW, 2, 1);
             meta_sh[stage * 32 + lane] = m;
             __syncwarp();
             if (lane == 0) {
-                mbar_arrive_expect_tx(full + stage, static_cast<uint32_t>(__popc(mask)) * static_cast<uint32_t>(V) * 4u);
-                issue_live_runs(mask, tiles + stage * tile_floats, acts + row0 * V, V, full + stage, policy);
+                mbar_arrive_expect_tx(full + stage, static_cast<uint32_t>(__popc(mask)) * static_cast<uint32_t>(V) *
+                                                        static_cast<uint32_t>(sizeof(E)));
+                issue_live_runs<E>(mask, tiles + stage * tile_elems, acts + row0 * V, V, full + stage, policy);
             }
             if (++stage == stages) {
                 stage = 0;
@@ -256,7 +291,7 @@ static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
         }
     } else {
         // ---------------- consumer warps: one row at a time ----------------
-        const int V4 = V >> 2;
+        const int NV = V / Elem<E>::kPerVec;
         const int64_t nq = nloc * G;
         for (int64_t q = warp; q < nq; q += NW) {
             const int64_t k = q / G;
@@ -264,20 +299,26 @@ static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
             const int stage = static_cast<int>(k % stages);
             const uint32_t phase = static_cast<uint32_t>((k / stages) & 1);
             const int64_t row = (blockIdx.x + k * gridDim.x) * G + r;
+            const long long tw0 = MRNNT_K1_CLOCK();
             mbar_wait(full + stage, phase);
+            const long long tw1 = MRNNT_K1_CLOCK();
+            MRNNT_K1_ADD(warp, 0, tw1 - tw0);
+            MRNNT_K1_ADD(warp, 2, 1);
             const int meta = meta_sh[stage * 32 + r];
             if (row < rows && meta != kRowDead) {
-                const float *xrow = tiles + stage * tile_floats + static_cast<size_t>(r) * V;
+                const E *xrow = tiles + stage * tile_elems + static_cast<size_t>(r) * V;
                 int lab = -1;
                 if (lane == 0 && meta >= 0) lab = __ldg(labels + meta);  // latency hides under the row math
-                const Denominator den = row_denominator<C>(reinterpret_cast<const float4 *>(xrow), V4, lane);
+                const Denominator den = row_denominator<E, C>(reinterpret_cast<const uint4 *>(xrow), NV, lane);
                 if (lane == 0) {
                     const bool has = lab >= 0 && lab < V;
-                    k1_store_row(lp, row, den, xrow[blank], has ? xrow[lab] : kNegInfF);
+                    k1_store_row(lp, row, den, Elem<E>::to_float(xrow[blank]),
+                                 has ? Elem<E>::to_float(xrow[lab]) : kNegInfF);
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty + stage);
+            MRNNT_K1_ADD(warp, 1, MRNNT_K1_CLOCK() - tw1);
         }
     }
 }

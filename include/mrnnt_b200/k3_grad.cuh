@@ -26,59 +26,63 @@ namespace mrnnt {
 
 __device__ __forceinline__ float grad_elem(float x, float c) { return ex2_approx(fmaf(x, kLog2e, c)); }
 
-// subtract the blank / label term from component (idx & 3) of a vector whose first element is 4*j
-__device__ __forceinline__ void patch_component(float4 &g, const float4 &x, int j, int idx, float c) {
-    if ((idx >> 2) == j) {
-        const int k = idx & 3;
-        const float xv = k == 0 ? x.x : (k == 1 ? x.y : (k == 2 ? x.z : x.w));
-        const float d = grad_elem(xv, c);
-        if (k == 0) g.x -= d; else if (k == 1) g.y -= d; else if (k == 2) g.z -= d; else g.w -= d;
-    }
+// subtract the blank / label term from component k of a vector of NE gradients (k is warp-divergent, so the
+// component is picked with selects instead of a dynamically indexed register array)
+template <int NE>
+__device__ __forceinline__ void patch_component(float (&g)[NE], const float (&x)[NE], int k, float c) {
+    float xv = x[0];
+#pragma unroll
+    for (int i = 1; i < NE; ++i) xv = (k == i) ? x[i] : xv;
+    const float d = grad_elem(xv, c);
+#pragma unroll
+    for (int i = 0; i < NE; ++i) g[i] -= (k == i) ? d : 0.0f;
 }
 
 // ---------------------------------------------------------------------------------------------
 // Generic variant: one warp per row, scalar accesses.  Any V, any alignment.
 // ---------------------------------------------------------------------------------------------
+template <typename E>
 static __global__ void __launch_bounds__(kGenericWarps * kWarp)
-    k3_grad_generic_kernel(const float *__restrict__ acts, const float4 *__restrict__ coef,
-                           float *__restrict__ grads, int64_t rows, int V, int blank,
-                           const int *__restrict__ rowutt, const float *__restrict__ scale) {
+    k3_grad_generic_kernel(const E *__restrict__ acts, const float4 *__restrict__ coef, E *__restrict__ grads,
+                           int64_t rows, int V, int blank, const int *__restrict__ rowutt,
+                           const float *__restrict__ scale) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * kGenericWarps + (threadIdx.x >> 5);
     const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kGenericWarps;
     for (int64_t row = warp0; row < rows; row += nwarps) {
         const float4 c = __ldg(coef + row);
-        float *g = grads + row * V;
+        E *g = grads + row * V;
         if (c.x == kNegInfF) {
-            for (int v = lane; v < V; v += kWarp) g[v] = 0.0f;
+            for (int v = lane; v < V; v += kWarp) g[v] = Elem<E>::from_float(0.0f);
             continue;
         }
-        const float *x = acts + row * V;
+        const E *x = acts + row * V;
         const int lab = __float_as_int(c.w);
         const float sc = scale != nullptr ? __ldg(scale + __ldg(rowutt + row)) : 1.0f;
         for (int v = lane; v < V; v += kWarp) {
-            const float xv = __ldg(x + v);
+            const float xv = Elem<E>::to_float(x[v]);
             float gv = grad_elem(xv, c.x);
             if (v == blank) gv -= grad_elem(xv, c.y);
             else if (v == lab) gv -= grad_elem(xv, c.z);
-            g[v] = gv * sc;
+            g[v] = Elem<E>::from_float(gv * sc);
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// TMA-staged variant.  Requirements: V % 4 == 0, acts and grads 16-byte aligned.
-// Shared memory: [stages][G*V] floats | full[stages] | empty[stages] | scale[stages][32] floats | coef[stages][32] float4
+// TMA-staged variant.  Requirements: rows are whole 16-byte vectors, acts and grads 16-byte aligned.
+// Shared memory: [stages][G*V] elements | full[stages] | empty[stages] | scale[stages][32] floats | coef[stages][32] float4
 // ---------------------------------------------------------------------------------------------
-template <int NW, bool SCALED>
+template <typename E, int NW, bool SCALED>
 static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
-    k3_grad_tma_kernel(const float *__restrict__ acts, const float4 *__restrict__ coef, float *__restrict__ grads,
+    k3_grad_tma_kernel(const E *__restrict__ acts, const float4 *__restrict__ coef, E *__restrict__ grads,
                        int64_t rows, int V, int blank, int G, int stages, const int *__restrict__ rowutt,
                        const float *__restrict__ scale) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const size_t tile_floats = static_cast<size_t>(G) * V;
-    float *tiles = reinterpret_cast<float *>(smem_raw);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + static_cast<size_t>(stages) * tile_floats * 4);
+    constexpr int NE = Elem<E>::kPerVec;
+    const size_t tile_elems = static_cast<size_t>(G) * V;
+    E *tiles = reinterpret_cast<E *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + static_cast<size_t>(stages) * tile_elems * sizeof(E));
     uint64_t *empty = full + stages;
     float *scale_sh = reinterpret_cast<float *>(empty + stages);
     float4 *coef_sh = reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(empty + stages) +
@@ -125,8 +129,9 @@ static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
             if (SCALED) scale_sh[stage * 32 + lane] = sc;
             __syncwarp();
             if (lane == 0) {
-                mbar_arrive_expect_tx(full + stage, static_cast<uint32_t>(__popc(mask)) * static_cast<uint32_t>(V) * 4u);
-                issue_live_runs(mask, tiles + stage * tile_floats, acts + row0 * V, V, full + stage, policy);
+                mbar_arrive_expect_tx(full + stage, static_cast<uint32_t>(__popc(mask)) * static_cast<uint32_t>(V) *
+                                                        static_cast<uint32_t>(sizeof(E)));
+                issue_live_runs<E>(mask, tiles + stage * tile_elems, acts + row0 * V, V, full + stage, policy);
             }
             if (++stage == stages) {
                 stage = 0;
@@ -135,7 +140,7 @@ static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
         }
     } else {
         // ---------------- consumer warps ----------------
-        const int V4 = V >> 2;
+        const int NV = V / NE;
         const int64_t nq = nloc * G;
         for (int64_t q = warp; q < nq; q += NW) {
             const int64_t k = q / G;
@@ -146,33 +151,30 @@ static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
             mbar_wait(full + stage, phase);
             if (row < rows) {
                 const float4 c = coef_sh[stage * 32 + r];
-                float4 *g4 = reinterpret_cast<float4 *>(grads + row * V);
+                uint4 *gv = reinterpret_cast<uint4 *>(grads + row * V);
                 if (c.x == kNegInfF) {
-                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int j = lane; j < V4; j += kWarp) st_stream_f4(g4 + j, z);
+                    const uint4 z = make_uint4(0u, 0u, 0u, 0u);  // +0.0 in either element type
+                    for (int j = lane; j < NV; j += kWarp) st_stream_u4(gv + j, z);
                 } else {
-                    const float4 *x4 = reinterpret_cast<const float4 *>(tiles + stage * tile_floats +
-                                                                        static_cast<size_t>(r) * V);
+                    const uint4 *xv = reinterpret_cast<const uint4 *>(tiles + stage * tile_elems +
+                                                                      static_cast<size_t>(r) * V);
                     const int lab = __float_as_int(c.w);  // -1 when the row has no (non-blank) label
-                    const int jb = blank >> 2, jl = lab >> 2;
+                    const int jb = blank / NE, kb = blank - jb * NE;
+                    const int jl = lab >= 0 ? lab / NE : -1, kl = lab - jl * NE;
                     const float sc = SCALED ? scale_sh[stage * 32 + r] : 1.0f;
 #pragma unroll 2
-                    for (int j = lane; j < V4; j += kWarp) {
-                        const float4 x = x4[j];
-                        float4 g;
-                        g.x = grad_elem(x.x, c.x);
-                        g.y = grad_elem(x.y, c.x);
-                        g.z = grad_elem(x.z, c.x);
-                        g.w = grad_elem(x.w, c.x);
-                        if (j == jb) patch_component(g, x, j, blank, c.y);
-                        if (j == jl) patch_component(g, x, j, lab, c.z);
+                    for (int j = lane; j < NV; j += kWarp) {
+                        float x[NE], g[NE];
+                        Elem<E>::unpack(xv[j], x);
+#pragma unroll
+                        for (int i = 0; i < NE; ++i) g[i] = grad_elem(x[i], c.x);
+                        if (j == jb) patch_component<NE>(g, x, kb, c.y);
+                        if (j == jl) patch_component<NE>(g, x, kl, c.z);
                         if (SCALED) {
-                            g.x *= sc;
-                            g.y *= sc;
-                            g.z *= sc;
-                            g.w *= sc;
+#pragma unroll
+                            for (int i = 0; i < NE; ++i) g[i] *= sc;
                         }
-                        st_stream_f4(g4 + j, g);
+                        st_stream_u4(gv + j, Elem<E>::pack(g));
                     }
                 }
             }

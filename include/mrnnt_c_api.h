@@ -46,6 +46,12 @@ RNNTStatus mrnnt_get_workspace_size_padded(const int *T_host, const int *S_host,
 RNNTStatus mrnnt_create_padded(mrnnt_handle_t *out, const float *acts, const int *labels, int B, const int *T_dev,
                                const int *S_dev, int V, int T_dim, int U, int label_stride, const int *T_host,
                                const int *S_host);
+/* Extension (no reference equivalent; the reference is float32 only, pytorch_binding/monotonic_rnnt.cu:84):
+ * dtype 1 declares acts AND gradients of this handle to be bfloat16 arrays (same layouts; pass the pointers through
+ * the float* parameters); all arithmetic stays float32, costs stay float32.  dtype 0 = float32 (default).
+ * Call right after mrnnt_create / mrnnt_create_padded. */
+enum { MRNNT_DTYPE_F32 = 0, MRNNT_DTYPE_BF16 = 1 };
+RNNTStatus mrnnt_set_dtype(mrnnt_handle_t h, int dtype);
 void mrnnt_destroy(mrnnt_handle_t h);
 
 /* gpu_workspace_manager.h:228 (get_workspace_size), :256 (set_workspace), :331-342 (create/free). */

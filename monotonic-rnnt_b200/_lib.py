@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = (
     "mrnnt_cost_and_grad", "mrnnt_enqueue", "mrnnt_device_costs", "rnnt_loss_grad_gpu", "mrnnt_set_option",
     "mrnnt_debug_copy", "mrnnt_synth_uniform", "mrnnt_build_info", "mrnnt_last_timings",
     "mrnnt_enqueue_forward", "mrnnt_enqueue_backward", "mrnnt_create_padded",
-    "mrnnt_get_workspace_size_padded",
+    "mrnnt_get_workspace_size_padded", "mrnnt_set_dtype",
 )
 
 
@@ -49,6 +49,7 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mrnnt_create.argtypes = [ctypes.POINTER(vp), vp, vp, ci, vp, vp, ci, vp, vp]
     lib.mrnnt_get_workspace_size_padded.argtypes = [vp, vp, ci, ci, ci, ci, ci, szp]
     lib.mrnnt_create_padded.argtypes = [ctypes.POINTER(vp), vp, vp, ci, vp, vp, ci, ci, ci, ci, vp, vp]
+    lib.mrnnt_set_dtype.argtypes = [vp, ci]
     lib.mrnnt_destroy.argtypes = [vp]
     lib.mrnnt_destroy.restype = None
     lib.mrnnt_workspace_size.argtypes = [vp, szp]
@@ -74,7 +75,7 @@ def _declare(lib: ctypes.CDLL) -> None:
                  "mrnnt_create_workspace", "mrnnt_restrict_to_alignment", "mrnnt_cost_and_grad", "mrnnt_enqueue",
                  "rnnt_loss_grad_gpu", "mrnnt_set_option", "mrnnt_debug_copy", "mrnnt_synth_uniform",
                  "mrnnt_last_timings", "mrnnt_enqueue_forward", "mrnnt_enqueue_backward", "mrnnt_create_padded",
-                 "mrnnt_get_workspace_size_padded"):
+                 "mrnnt_get_workspace_size_padded", "mrnnt_set_dtype"):
         getattr(lib, name).restype = ci
 
 

@@ -114,6 +114,12 @@ RNNTStatus mrnnt_create_padded(mrnnt_handle_t *out, const float *acts, const int
     return RNNT_STATUS_SUCCESS;
 }
 
+RNNTStatus mrnnt_set_dtype(mrnnt_handle_t h, int dtype) {
+    if (h == nullptr || (dtype != MRNNT_DTYPE_F32 && dtype != MRNNT_DTYPE_BF16)) return RNNT_STATUS_INVALID_VALUE;
+    h->manager.engine().set_bf16(dtype == MRNNT_DTYPE_BF16);
+    return RNNT_STATUS_SUCCESS;
+}
+
 void mrnnt_destroy(mrnnt_handle_t h) { delete h; }
 
 RNNTStatus mrnnt_workspace_size(mrnnt_handle_t h, size_t *size_bytes) {

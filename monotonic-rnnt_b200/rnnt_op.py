@@ -33,8 +33,8 @@ def _check_inputs(acts, labels, input_lengths, label_lengths) -> None:
             raise RuntimeError(f"{name} must be a CUDA tensor")  # monotonic_rnnt.cu:85-88
         if t.dtype != torch.int32:
             raise TypeError(f"{name} must be int32")             # data_ptr<int>() in monotonic_rnnt.cu:99-101
-    if acts.dtype != torch.float32:
-        raise TypeError("acts must be float32")                  # monotonic_rnnt.cu:84
+    if acts.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError("acts must be float32 (the reference's type, monotonic_rnnt.cu:84) or bfloat16 (extension)")
     if acts.dim() not in (2, 4):
         raise ValueError("acts must be the packed 2-D tensor [sum_b T_b*(S_b+1), V] or the padded 4-D tensor "
                          "[B, T, U, V]")
@@ -98,6 +98,8 @@ class LossHandle:
                 _lib.check(st, "mrnnt_create")
             self._h = h
             size = ctypes.c_size_t(0)
+            if acts.dtype == torch.bfloat16:
+                _lib.check(self._lib.mrnnt_set_dtype(self._h, 1), "mrnnt_set_dtype")
             _lib.check(self._lib.mrnnt_workspace_size(self._h, ctypes.byref(size)), "mrnnt_workspace_size")
             self.workspace_bytes = int(size.value)
             # caller-owned workspace, as the TensorFlow op does with allocate_temp (monotonic_rnnt_op.cu:117-123)
@@ -142,7 +144,7 @@ class LossHandle:
         assert costs_host.device.type == "cpu" and costs_host.dtype == torch.float32 and costs_host.numel() == self.B
         gptr = None
         if grads is not None:
-            assert grads.is_cuda and grads.dtype == torch.float32 and grads.is_contiguous()
+            assert grads.is_cuda and grads.dtype == self.acts.dtype and grads.is_contiguous()
             assert grads.numel() == self.acts.numel()
             gptr = grads.data_ptr()
         with torch.cuda.device(self.acts.device):
@@ -171,7 +173,7 @@ class LossHandle:
 
     def enqueue_backward(self, grads: torch.Tensor, scale: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Second half (K3): grads[i, :] = scale[b(i)] * d cost_b / d acts[i, :], written exactly once."""
-        assert grads.is_cuda and grads.dtype == torch.float32 and grads.is_contiguous()
+        assert grads.is_cuda and grads.dtype == self.acts.dtype and grads.is_contiguous()
         assert grads.numel() == self.acts.numel()
         sptr = None
         if scale is not None:

@@ -365,3 +365,57 @@ def test_padded_layout_multi_warp_rows(gu, shape):
         off += n
     assert np.all(g == 0.0)
     h.close()
+
+
+def _bf16_round(a):
+    """float32 array rounded to the nearest bfloat16 (ties to even), still held as float32."""
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+BF16_SHAPES = [
+    # name, B, V, T_range, S_range, dist           streaming kernels need V % 8 == 0 in bfloat16
+    ("bf16_v1000", 4, 1000, (30, 60), (5, 20), "uniform"),
+    ("bf16_v1000_peaky", 3, 1000, (30, 60), (5, 20), "normal3"),
+    ("bf16_v64_g32", 7, 64, (10, 60), (3, 30), "normal3"),
+    ("bf16_v2048_64regs", 2, 2048, (12, 20), (3, 8), "uniform"),
+    ("bf16_v5000_two_pass", 2, 5000, (20, 30), (4, 9), "uniform"),
+    ("bf16_v12_generic", 5, 12, (5, 40), (1, 20), "normal3"),
+    ("bf16_s_gt_32", 3, 16, (70, 90), (33, 60), "normal3"),
+]
+
+
+@pytest.mark.parametrize("shape", BF16_SHAPES, ids=lambda s: s[0])
+def test_bf16_logits(gu, shape):
+    """bfloat16 logits and gradients, float arithmetic.  The oracle runs in double on the SAME
+    (bfloat16-representable) inputs: costs to the float tolerance, gradients to half a bfloat16 ulp of the output."""
+    import monotonic_rnnt_b200 as mr
+    import gpu_util
+    name, B, V, tr, sr, dist = shape
+    case = fixtures.random_case(name, 4242, B=B, V=V, T_range=tr, S_range=sr, dist=dist)
+    acts32 = _bf16_round(case.acts)
+    o = oracle.run(acts32, case.labels, case.T, case.S, case.V, blank=case.blank, precision="f64_from_f32")
+    acts = torch.from_numpy(acts32.reshape(case.rows, case.V)).to(torch.bfloat16).cuda()
+    labels = gpu_util.to_dev(case.labels, torch.int32)
+    T = gpu_util.to_dev(case.T, torch.int32); S = gpu_util.to_dev(case.S, torch.int32)
+    for generic in (False, True):
+        h = mr.LossHandle(acts, labels, T, S)
+        if generic:
+            h.set_option(mr._lib.OPT_FORCE_GENERIC, 1)
+        grads = torch.full_like(acts, float("nan"))
+        costs = h.cost_and_grad(case.blank, grads).numpy()
+        _check_costs(costs, o.costs)
+        g = grads.to(torch.float32).cpu().numpy().astype(np.float64)
+        want = o.grads.reshape(case.rows, case.V)
+        assert np.isfinite(g).all()
+        assert np.all(np.abs(g - want) <= np.abs(want) * 2.0 ** -8 + GRAD_ATOL)
+        assert np.all(g[want == 0.0] == 0.0)
+        h.close()
+    # the autograd op on bfloat16 logits: gradient in bfloat16, scaled per utterance
+    a = acts.clone().requires_grad_(True)
+    w = torch.linspace(0.5, 2.0, case.B, device="cuda")
+    (mr.monotonic_rnnt_loss(a, labels, T, S, blank_label=case.blank) * w).sum().backward()
+    assert a.grad.dtype == torch.bfloat16
+    rows = case.T.astype(np.int64) * (case.S + 1)
+    scale = np.repeat(w.cpu().numpy().astype(np.float64), rows)[:, None]
+    ga = a.grad.to(torch.float32).cpu().numpy().astype(np.float64)
+    assert np.all(np.abs(ga - want * scale) <= np.abs(want * scale) * 2.0 ** -7 + GRAD_ATOL * 2)

@@ -18,7 +18,7 @@ import monotonic_rnnt_b200 as mr  # noqa: E402
 from monotonic_rnnt_b200 import _lib  # noqa: E402
 
 
-def run(name: str, iters: int, combos, padded: bool = False) -> None:
+def run(name: str, iters: int, combos, padded: bool = False, bf16: bool = False) -> None:
     wl = mr.synth.workload(name)
     dev = torch.device("cuda", 0)
     lib = _lib.load()
@@ -31,6 +31,8 @@ def run(name: str, iters: int, combos, padded: bool = False) -> None:
         acts = torch.empty((wl.rows, wl.V), dtype=torch.float32, device=dev)
         _lib.check(lib.mrnnt_synth_uniform(acts.data_ptr(), wl.elements, 0, 0,
                                            torch.cuda.current_stream().cuda_stream), "s")
+    if bf16:
+        acts = acts.to(torch.bfloat16)
     labels = torch.from_numpy(wl.labels).to(dev)
     T = torch.from_numpy(wl.T).to(dev)
     S = torch.from_numpy(wl.S).to(dev)
@@ -40,7 +42,7 @@ def run(name: str, iters: int, combos, padded: bool = False) -> None:
         h.restrict_to_alignment(torch.from_numpy(wl.alignment).to(dev), wl.max_shift, wl.blank)
     h.set_option(_lib.OPT_TIMING, 1)
     costs = torch.empty(wl.B, dtype=torch.float32).pin_memory()
-    n4 = wl.elements * 4
+    n4 = wl.elements * (2 if bf16 else 4)
     for k1w, k3w in combos:
         h.set_option(_lib.OPT_K1_WARPS, k1w)
         h.set_option(_lib.OPT_K3_WARPS, k3w)
@@ -56,11 +58,11 @@ def run(name: str, iters: int, combos, padded: bool = False) -> None:
                 wall.append(ev0.elapsed_time(ev1))
         k = np.median(np.array(ts), axis=0)
         w = float(np.median(wall))
-        print(f"{wl.name}{' PADDED rows=' + str(acts.numel() // wl.V) if padded else ''} B={wl.B} V={wl.V} rows={wl.rows} "
+        print(f"{wl.name}{' BF16' if bf16 else ''}{' PADDED rows=' + str(acts.numel() // wl.V) if padded else ''} B={wl.B} V={wl.V} rows={wl.rows} "
               f"k1w={k1w} k3w={k3w}: "
-              f"K1 {k[0]*1e3:7.1f} us ({n4/k[0]/1e6:6.0f} GB/s of 4N)  K2 {k[1]*1e3:7.1f} us  "
-              f"K3 {k[2]*1e3:7.1f} us ({2*n4/k[2]/1e6:6.0f} GB/s of 8N)  call {w*1e3:7.1f} us "
-              f"({3*n4/w/1e6:6.0f} GB/s of 12N, {wl.B/w*1e3:8.0f} utt/s)", flush=True)
+              f"K1 {k[0]*1e3:7.1f} us ({n4/k[0]/1e6:6.0f} GB/s of 1xN)  K2 {k[1]*1e3:7.1f} us  "
+              f"K3 {k[2]*1e3:7.1f} us ({2*n4/k[2]/1e6:6.0f} GB/s of 2xN)  call {w*1e3:7.1f} us "
+              f"({3*n4/w/1e6:6.0f} GB/s of 3xN, {wl.B/w*1e3:8.0f} utt/s)", flush=True)
     # cost-only call (K1 + alpha pass, no beta / coefficients / K3)
     ts = []
     for i in range(8):
@@ -76,8 +78,9 @@ if __name__ == "__main__":
     ap.add_argument("workloads", nargs="*", default=["c2"])
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--combos", default="24:24")
+    ap.add_argument("--bf16", action="store_true", help="bfloat16 logits and gradients")
     ap.add_argument("--padded", action="store_true", help="feed the padded [B,T,S+1,V] tensor instead of packed rows")
     a = ap.parse_args()
     combos = [tuple(int(x) for x in c.split(":")) for c in a.combos.split(",")]
     for name in a.workloads:
-        run(name, a.iters, combos, a.padded)
+        run(name, a.iters, combos, a.padded, a.bf16)
