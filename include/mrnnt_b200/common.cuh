@@ -48,11 +48,12 @@ struct __align__(16) Weight {  // transition weights of one packed row: p(blank)
     float ml;
     int el;
 };
-struct __align__(16) RawRow {  // what K1 leaves per live packed row (dead rows are never read)
+struct __align__(16) RawRow {  // per live packed row (dead rows are never written nor used)
     float xb;  // logit of the blank
     float xl;  // logit of the row's label (-inf without one)
-    float dh;  // dh + dl = -log2 sum_v exp(x[v]) as an unevaluated sum of two floats (~48 bits), so that
-    float dl;  //           log2 p(v) = x[v] * log2(e) + dh + dl
+    float dh;  // as K1 leaves it: (dh, dl) = (max_v x[v] * log2 e, sum_v 2^(x[v] log2 e - max)).  K2's phase A replaces
+    float dl;  // the pair IN PLACE by dh + dl = -log2 sum_v exp(x[v]) as an unevaluated sum of two floats (~48 bits),
+               // so that log2 p(v) = x[v] * log2(e) + dh + dl
 };
 constexpr int kZeroExp = -(1 << 24);  // non-zero values reach down to 2^-(2^23); 17 frames of drift stay below 2^29
 
@@ -311,6 +312,24 @@ __device__ __forceinline__ void log2_parts(float v, int &ip, float &fp) {
     const float f = frexpf(v, &ex);  // v = f * 2^ex, f in [0.5, 1)
     ip = ex - 1;
     fp = log2f(f + f);
+}
+
+// From a row's max (times log2 e, rounded once and used for every term) and its sum of 2^(x log2e - ML): the
+// base-2 denominator -(ML + log2 sum) = -log2 sum_v exp(x[v]) as an unevaluated sum of two floats (error-free
+// additions; the only error is log2f's ~6e-8 on a value in [0,1)).
+struct Denominator {
+    float hi, lo;
+};
+__device__ __forceinline__ Denominator lse_finish(float ML, float sum) {
+    int ip;
+    float fp, h, l1, h2, l2;
+    log2_parts(sum, ip, fp);
+    two_sum(ML, static_cast<float>(ip), h, l1);
+    two_sum(h, fp, h2, l2);
+    Denominator d;
+    d.hi = -h2;
+    d.lo = -(l1 + l2);
+    return d;
 }
 
 }  // namespace mrnnt

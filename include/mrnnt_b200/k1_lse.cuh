@@ -5,9 +5,9 @@
 // reads of the logits with 4-byte loads and two stream syncs) and the strided `log_p` gathers inside
 // the alpha/beta kernels (gpu_rnnt_kernel.h:80-84,144-149).  CPU twin: cpu_rnnt.h:98-115.
 //
-//   D = -log2 sum_v exp(x[v])  as two floats (dh, dl)           (log2 p(v) = x[v] log2 e + D; the reference's
-//                                                                 denominator is D ln 2, reduce.h:112-139)
-//   lp[row] = (x[blank], x[label(b,s)], dh, dl)                   one 16-byte record per live row
+//   ML = max_v x[v] * log2 e,  sum = sum_v 2^(x[v] log2 e - ML)   (the reference's denominator, reduce.h:112-139, is
+//                                                                 -(ML + log2 sum) ln 2; K2's phase A forms it)
+//   lp[row] = (x[blank], x[label(b,s)], ML, sum)                  one 16-byte record per live row
 //
 // Streaming design (HBM-bound; algorithmic bytes = 4*V per live row, nothing for dead rows):
 //   * persistent CTAs, one per SM; the flat row space is cut into tiles of G consecutive rows;
@@ -49,58 +49,68 @@ __device__ __forceinline__ float warp_sum_f(float v) {
     return v;
 }
 
-// four running sums of 2^(x*log2e + neg) over the NE floats of a vector
+// four running sums (two packed pairs) of 2^(x*log2e + neg) over the NE floats of a vector; the multiply-adds
+// and the additions are the packed two-float instructions of sm_100 (FFMA2 / FADD2), the exponentials MUFU.EX2
 template <int NE>
-__device__ __forceinline__ void exp_acc(const float (&f)[NE], float neg, float (&s)[4]) {
+__device__ __forceinline__ void exp_acc(const float (&f)[NE], float neg, float2 (&s)[2]) {
+    const float2 l2 = make_float2(kLog2e, kLog2e), n2 = make_float2(neg, neg);
 #pragma unroll
-    for (int i = 0; i < NE; ++i) s[i & 3] += ex2_approx(fmaf(f[i], kLog2e, neg));
+    for (int i = 0; i < NE; i += 2) {
+        const float2 t = __ffma2_rn(make_float2(f[i], f[i + 1]), l2, n2);
+        s[(i >> 1) & 1] = __fadd2_rn(s[(i >> 1) & 1], make_float2(ex2_approx(t.x), ex2_approx(t.y)));
+    }
+}
+// the same with the lanes whose vector lies beyond the row masked out (their registers hold a copy of the row's
+// last vector, see row_sums)
+template <int NE>
+__device__ __forceinline__ void exp_acc_masked(const float (&f)[NE], float neg, bool valid, float2 (&s)[2]) {
+    const float2 l2 = make_float2(kLog2e, kLog2e), n2 = make_float2(neg, neg);
+#pragma unroll
+    for (int i = 0; i < NE; i += 2) {
+        const float2 t = __ffma2_rn(make_float2(f[i], f[i + 1]), l2, n2);
+        const float2 e2 = make_float2(valid ? ex2_approx(t.x) : 0.0f, valid ? ex2_approx(t.y) : 0.0f);
+        s[(i >> 1) & 1] = __fadd2_rn(s[(i >> 1) & 1], e2);
+    }
 }
 
-// From the warp-wide max (times log2 e, rounded once and used for every term) and the warp-wide sum of
-// 2^(x log2e - ML): the base-2 denominator -(ML + log2 sum) = -log2 sum_v exp(x[v]) as an unevaluated sum of
-// two floats (error-free additions; the only error is log2f's ~6e-8 on a value in [0,1)).
-struct Denominator {
-    float hi, lo;
+// What K1 knows about a row's denominator: the warp-wide max (times log2 e, rounded once and used for every term)
+// and the sum of 2^(x log2e - ML).  Turning them into -log2 sum_v exp(x[v]) costs a logarithm and a few
+// error-free additions per row; that is left to the lattice kernel's helper CTAs (k2_lattice.cuh, phase A) -- K1
+// at V ~ 1000 is bound by the instruction stream of its consumer warps, not by HBM (tools/k1_probe.cu).
+struct RowSum {
+    float ML, sum;
 };
-__device__ __forceinline__ Denominator lse_finish(float ML, float sum) {
-    int ip;
-    float fp, h, l1, h2, l2;
-    log2_parts(sum, ip, fp);
-    two_sum(ML, static_cast<float>(ip), h, l1);
-    two_sum(h, fp, h2, l2);
-    Denominator d;
-    d.hi = -h2;
-    d.lo = -(l1 + l2);
-    return d;
-}
 
-// One row resident in shared memory (16-byte aligned, NV vectors of 16 bytes = NV * Elem<E>::kPerVec logits).
+// One row resident in shared memory (16-byte aligned, NV >= 1 vectors of 16 bytes = NV * Elem<E>::kPerVec logits).
 // C > 0: the lane's <= C vectors live in registers, unpacked (NV <= 32*C); C == 0: two passes over shared
-// memory, any NV.
+// memory, any NV.  Vector slots beyond the row: whole slots (c*32 >= NV, warp-uniform) are skipped; in the one
+// partly filled slot the surplus lanes load the row's last vector again -- harmless for the max, masked in the sum.
 template <typename E, int C>
-__device__ __forceinline__ Denominator row_denominator(const uint4 *__restrict__ xv, int NV, int lane) {
+__device__ __forceinline__ RowSum row_sums(const uint4 *__restrict__ xv, int NV, int lane) {
     constexpr int NE = Elem<E>::kPerVec;
-    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    float2 s[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
     float ML;
     if constexpr (C > 0) {
         float f[C][NE];
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            const int j = lane + c * kWarp;
-            if ((c + 1) * kWarp <= NV || j < NV) {  // (the first test is warp-uniform: no per-lane selects for full vectors)
-                Elem<E>::unpack(xv[j], f[c]);
-            } else {
-#pragma unroll
-                for (int i = 0; i < NE; ++i) f[c][i] = kNegInfF;
-            }
-        }
+        Elem<E>::unpack(xv[min(lane, NV - 1)], f[0]);
         float m = vec_max<NE>(f[0]);
 #pragma unroll
-        for (int c = 1; c < C; ++c) m = fmaxf(m, vec_max<NE>(f[c]));
+        for (int c = 1; c < C; ++c) {
+            if (c * kWarp < NV) {
+                Elem<E>::unpack(xv[min(lane + c * kWarp, NV - 1)], f[c]);
+                m = fmaxf(m, vec_max<NE>(f[c]));
+            }
+        }
         ML = warp_max_redux(m) * kLog2e;
         const float neg = -ML;
 #pragma unroll
-        for (int c = 0; c < C; ++c) exp_acc<NE>(f[c], neg, s);
+        for (int c = 0; c < C; ++c) {
+            if ((c + 1) * kWarp <= NV) {
+                exp_acc<NE>(f[c], neg, s);
+            } else if (c * kWarp < NV) {
+                exp_acc_masked<NE>(f[c], neg, lane + c * kWarp < NV, s);
+            }
+        }
     } else {
         float m = kNegInfF;
 #pragma unroll 4
@@ -118,19 +128,22 @@ __device__ __forceinline__ Denominator row_denominator(const uint4 *__restrict__
             exp_acc<NE>(f, neg, s);
         }
     }
-    return lse_finish(ML, warp_sum_f((s[0] + s[1]) + (s[2] + s[3])));
+    RowSum r;
+    r.ML = ML;
+    r.sum = warp_sum_f((s[0].x + s[0].y) + (s[1].x + s[1].y));
+    return r;
 }
 
-// What lane 0 writes for one live row: the two gathered logits and the denominator (one 16-byte store).  The
-// lattice kernel turns them into transition weights on its otherwise idle warps (k2_lattice.cuh); dead rows
+// What lane 0 writes for one live row: the two gathered logits and the row's (max, sum) (one 16-byte store).  The
+// lattice kernel's phase A turns them into the denominator and the transition weights (k2_lattice.cuh); dead rows
 // are never read again, so nothing is written for them.
-__device__ __forceinline__ void k1_store_row(RawRow *__restrict__ lp, int64_t row, const Denominator &den,
-                                             float x_blank, float x_label) {
+__device__ __forceinline__ void k1_store_row(RawRow *__restrict__ lp, int64_t row, const RowSum &rs, float x_blank,
+                                             float x_label) {
     RawRow r;
     r.xb = x_blank;
     r.xl = x_label;
-    r.dh = den.hi;
-    r.dl = den.lo;
+    r.dh = rs.ML;
+    r.dl = rs.sum;
     lp[row] = r;
 }
 
@@ -155,7 +168,9 @@ static __global__ void __launch_bounds__(kGenericWarps * kWarp)
         const float ML = warp_max_redux(m) * kLog2e;
         float s = 0.f;
         for (int v = lane; v < V; v += kWarp) s += ex2_approx(fmaf(Elem<E>::to_float(x[v]), kLog2e, -ML));
-        const Denominator den = lse_finish(ML, warp_sum_f(s));
+        RowSum den;
+        den.ML = ML;
+        den.sum = warp_sum_f(s);
         if (lane == 0) {
             const int lab = meta >= 0 ? __ldg(labels + meta) : -1;
             const bool has = lab >= 0 && lab < V;
@@ -309,7 +324,7 @@ static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
                 const E *xrow = tiles + stage * tile_elems + static_cast<size_t>(r) * V;
                 int lab = -1;
                 if (lane == 0 && meta >= 0) lab = __ldg(labels + meta);  // latency hides under the row math
-                const Denominator den = row_denominator<E, C>(reinterpret_cast<const uint4 *>(xrow), NV, lane);
+                const RowSum den = row_sums<E, C>(reinterpret_cast<const uint4 *>(xrow), NV, lane);
                 if (lane == 0) {
                     const bool has = lab >= 0 && lab < V;
                     k1_store_row(lp, row, den, Elem<E>::to_float(xrow[blank]),

@@ -25,8 +25,9 @@
 //    meet at a barrier: warp i+1 simply runs a few frames behind warp i.
 //  * `parts` CTAs per utterance (sized so that the whole grid is co-resident: the helpers sit on SMs that
 //    would otherwise idle during this kernel) and three phases separated by per-utterance flags:
-//    A. all parts turn the (x_blank, x_label, denominator) records K1 left per row into transition weights
-//       (mantissa, exponent), in float arithmetic, and fold the WHOLE band logic into them: a weight is
+//    A. all parts turn the (x_blank, x_label, max, sum) records K1 left per row into the row's denominator
+//       -log2 sum exp (a float pair, written back in place) and its transition weights (mantissa, exponent), in
+//       float arithmetic, and fold the WHOLE band logic into them: a weight is
 //       zeroed when the cell it leads into lies outside the lattice (alpha_s_min/max of the target frame,
 //       cpu_workspace_manager.h:67-71; the beta limits :73-86 are the same set shifted by one frame).  The
 //       chain warps therefore contain no band arithmetic at all.
@@ -66,7 +67,7 @@ struct K2Args {
     const int *labels;
     const int64_t *row_start;
     const int2 *band;
-    const RawRow *lp;
+    RawRow *lp;        // [rows] K1's records; phase A replaces their (max, sum) by the denominator pair in place
     Weight *wts;       // [rows] transition weights, written by phase A
     Cell *alpha;
     Cell *beta;
@@ -191,7 +192,7 @@ __device__ __forceinline__ void k2_weight_rows(const K2Args &a, int b, int part,
     const int Tb = a.T[b], Sb = a.S[b];
     const int W = Sb + 1, ld = k2_ld(a, Sb);
     const int64_t R = a.row_start[b];
-    const RawRow *lp = a.lp + R;
+    RawRow *lp = a.lp + R;
     Weight *wts = a.wts + R;
     const int2 *band = a.band + static_cast<size_t>(b) * a.T_max;
     const int n = Tb * W;
@@ -217,8 +218,16 @@ __device__ __forceinline__ void k2_weight_rows(const K2Args &a, int b, int part,
         for (int u = 0; u < U; ++u) {
             bool stay_ok, emit_ok;
             k2_row_flags(tt[u], ss[u], lh[u], lq[u], Tb, Sb, false, stay_ok, emit_ok);
+            // K1 left (max * log2 e, sum of 2^(x log2 e - max)); from here on the record holds -log2 sum exp
+            const Denominator d = lse_finish(raw[u].dh, raw[u].dl);
+            raw[u].dh = d.hi;
+            raw[u].dl = d.lo;
             const int i = base + u * kK2Threads;
-            if (i < i_end) wts[static_cast<int64_t>(tt[u]) * ld + ss[u]] = k2_make_weight(raw[u], stay_ok, emit_ok);
+            if (i < i_end) {
+                const int64_t idx = static_cast<int64_t>(tt[u]) * ld + ss[u];
+                *reinterpret_cast<float2 *>(&lp[idx].dh) = make_float2(d.hi, d.lo);
+                wts[idx] = k2_make_weight(raw[u], stay_ok, emit_ok);
+            }
         }
     }
 }
@@ -647,11 +656,22 @@ static __global__ void __launch_bounds__(kK2Threads) k2_lattice_wide_kernel(K2Ar
     const int Tb = a.T[b], Sb = a.S[b];
     const int W = k2_ld(a, Sb);  // rows per frame in memory
     const int64_t R = a.row_start[b];
-    const RawRow *lp = a.lp + R;
+    RawRow *lp = a.lp + R;
     const int2 *band = a.band + static_cast<size_t>(b) * a.T_max;
     Cell *alpha = a.alpha + R;
     Cell *beta = a.beta + R;
     const int tid = threadIdx.x;
+
+    // K1's (max, sum) -> the denominator pair, in place (what phase A of the main kernel does); rows K1 skipped
+    // hold garbage before and after, and are masked wherever they are read
+    for (int i = tid; i < Tb * (Sb + 1); i += kK2Threads) {
+        const int t = i / (Sb + 1);
+        RawRow &r = lp[static_cast<int64_t>(t) * W + (i - t * (Sb + 1))];
+        const Denominator d = lse_finish(r.dh, r.dl);
+        r.dh = d.hi;
+        r.dl = d.lo;
+    }
+    __syncthreads();
 
     auto put = [](float m, int e) {
         Cell c;

@@ -39,7 +39,8 @@ struct Workspace {
     int2 *band = nullptr;          // [B*T_max] (min_allowed_s, max_allowed_s) per frame
     int *rowmeta = nullptr;        // [rows]  >=0: index into labels[], kRowNoLabel, kRowDead
     int *rowutt = nullptr;         // [rows]  utterance of the row (the gradient kernel's per-utterance scale)
-    RawRow *lp = nullptr;          // [rows]  (x[blank], x[label_s], -log2 sum_v exp x[v]) per live row, from K1
+    RawRow *lp = nullptr;          // [rows]  (x[blank], x[label_s], max, sum) per live row from K1; K2 turns (max, sum)
+                                   //         into -log2 sum_v exp x[v] in place
     Weight *wts = nullptr;         // [rows]  transition weights (m * 2^e pairs, band folded in), K2 phase A
     Cell *alpha = nullptr;         // [rows]  full T x (S+1) grid per utterance (m * 2^e), zero outside the band
     Cell *beta = nullptr;          // [rows]

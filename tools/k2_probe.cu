@@ -8,6 +8,10 @@
 #include "../include/mrnnt_b200/k2_lattice.cuh"
 using namespace mrnnt;
 
+static const RawRow *g_lp_host = nullptr;  // K1-style records; the kernel rewrites them in place, so every launch gets a fresh copy
+static RawRow *g_lp_dev = nullptr;
+static size_t g_lp_bytes = 0;
+
 template <int K>
 static float run(const K2Args &a, int B, size_t sm, int reps) {
     cudaFuncSetAttribute(k2_lattice_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
@@ -17,6 +21,7 @@ static float run(const K2Args &a, int B, size_t sm, int reps) {
     float best = 1e9f;
     for (int r = 0; r < reps; ++r) {
         b.epoch = a.epoch + r;
+        cudaMemcpy(g_lp_dev, g_lp_host, g_lp_bytes, cudaMemcpyHostToDevice);
         cudaEventRecord(e0);
         k2_lattice_kernel<K><<<B * a.parts, kK2Threads, sm>>>(b);
         cudaEventRecord(e1);
@@ -31,7 +36,7 @@ int main(int argc, char **argv) {
     const int T = argc > 1 ? atoi(argv[1]) : 150, S = argc > 2 ? atoi(argv[2]) : 40, W = S + 1;
     const int B = argc > 3 ? atoi(argv[3]) : 32, parts = argc > 4 ? atoi(argv[4]) : 4;
     const size_t rows1 = (size_t)T * W, rows = rows1 * B, slack = 8 * W;
-    RawRow w0; w0.xb = 5.5f; w0.xl = 0.3f; w0.dh = -10.1f; w0.dl = 1e-9f;
+    RawRow w0; w0.xb = 5.5f; w0.xl = 0.3f; w0.dh = 9.0f; w0.dl = 2.1f;
     std::vector<RawRow> lp(rows + 2 * slack, w0);
     std::vector<int2> band((size_t)B * T + 64, make_int2(0, S));
         std::vector<int> labels((size_t)B * S, 3), hT(B, T), hS(B, S);
@@ -47,6 +52,7 @@ int main(int argc, char **argv) {
     cudaMemcpy(dl, labels.data(), 4 * B * S, cudaMemcpyHostToDevice); cudaMemcpy(drs, rs.data(), 8 * (B + 1), cudaMemcpyHostToDevice);
     cudaMemcpy(dband, band.data(), band.size() * 8, cudaMemcpyHostToDevice);
     cudaMemcpy(dlp, lp.data(), lp.size() * 16, cudaMemcpyHostToDevice);
+    g_lp_host = lp.data(); g_lp_dev = dlp; g_lp_bytes = lp.size() * 16;
     a.T = dT; a.S = dS; a.labels = dl; a.row_start = drs; a.band = dband + 32; a.lp = dlp + slack; a.wts = dw;
     a.alpha = dal; a.beta = dbe; a.coef = dco; a.ll_fwd = dll; a.ll_bwd = dll + B; a.costs = dc; a.flags = dfl;
     a.T_max = T; a.S_max = S; a.V = 1000; a.blank = 0;
