@@ -11,7 +11,9 @@ using namespace mrnnt;
 template <typename E, int NW, int C>
 static void run(const void *acts, const int *labels, const int *meta, RawRow *lp, int64_t rows, int V, const StreamTiling &tl) {
     auto kern = k1_lse_tma_kernel<E, NW, C>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.smem_bytes);
+    cudaError_t ea = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.smem_bytes);
+    cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, kern);
+    printf("regs=%d smem_dyn_max=%d static=%zu attr=%s\n", fa.numRegs, fa.maxDynamicSharedSizeBytes, fa.sharedSizeBytes, cudaGetErrorString(ea));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e9f;
     for (int rep = 0; rep < 5; ++rep) {
@@ -19,7 +21,9 @@ static void run(const void *acts, const int *labels, const int *meta, RawRow *lp
         cudaMemcpyToSymbol(g_k1_trace, zero, sizeof(zero));
         cudaEventRecord(e0);
         kern<<<148, (NW + 1) * 32, tl.smem_bytes>>>((const E *)acts, labels, meta, lp, rows, V, 0, tl.G, tl.stages);
-        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        cudaError_t el = cudaGetLastError();
+        cudaEventRecord(e1); cudaError_t es = cudaEventSynchronize(e1);
+        if (rep == 0) printf("launch: %s, sync: %s\n", cudaGetErrorString(el), cudaGetErrorString(es));
         float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
     }
     long long h[32][4]; cudaMemcpyFromSymbol(h, g_k1_trace, sizeof(h));
