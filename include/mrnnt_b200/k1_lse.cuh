@@ -202,7 +202,11 @@ struct StreamTiling {
 
 constexpr int kStreamMaxStages = 12;
 constexpr size_t kStreamSmemBudget = 200 * 1024;  // of the 227 KB a CTA may use
-constexpr int kStreamTileTarget = 32 * 1024;      // bytes per ring slot we aim for
+// Bytes per ring slot we aim for.  Measured on B200 (c2/c3, float and bfloat16): K1 gains from larger tiles (the
+// cost of a tile hand-over is per tile, not per byte: 8 KB tiles are 2x slower than 32 KB ones, 64 KB ones up to
+// 6 % faster on c3 and 17 % faster on bfloat16 rows), K3 is best at 32 KB.
+constexpr int kK1TileTarget = 64 * 1024;
+constexpr int kK3TileTarget = 32 * 1024;
 
 // Tiling of the streaming kernels for vocabulary size V with `warps` consumer warps.
 // extra_per_row: additional per-row shared bytes a kernel keeps next to the tile (K3: its coefficients).
@@ -212,11 +216,12 @@ constexpr int kStreamTileTarget = 32 * 1024;      // bytes per ring slot we aim 
 // waiting warp also consumed the PREVIOUS use of that ring stage (bulk copies complete out of order, so
 // "an earlier tile was issued first" proves nothing).  Hence G is a power of two and the ring depth is a
 // multiple of the stride NW/G: every warp then cycles through a fixed subset of the stages.
-inline bool stream_tiling(int V, size_t elem_bytes, size_t extra_per_row, int warps, StreamTiling *out) {
+inline bool stream_tiling(int V, size_t elem_bytes, size_t extra_per_row, int warps, int tile_target,
+                          StreamTiling *out) {
     const size_t row_bytes = static_cast<size_t>(V) * elem_bytes;
     if (V <= 0 || (row_bytes % 16) != 0 || (warps != 8 && warps != 16 && warps != 24)) return false;
     int G = 1;
-    while (G < 32 && static_cast<size_t>(2 * G) * row_bytes <= static_cast<size_t>(kStreamTileTarget)) G *= 2;
+    while (G < 32 && static_cast<size_t>(2 * G) * row_bytes <= static_cast<size_t>(tile_target)) G *= 2;
     const size_t slot = static_cast<size_t>(G) * row_bytes + 32 * (sizeof(int) + extra_per_row) + 16;
     int stages = static_cast<int>(kStreamSmemBudget / slot);
     if (stages > kStreamMaxStages) stages = kStreamMaxStages;
@@ -288,7 +293,7 @@ static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
             m_next = load_meta(k + 1);  // one tile ahead: its latency hides behind this tile's wait
             const int64_t row0 = (blockIdx.x + k * gridDim.x) * G;
             const uint32_t mask = __ballot_sync(0xffffffffu, m != kRowDead);
-            const long long tw0 = MRNNT_K1_CLOCK();
+            [[maybe_unused]] const long long tw0 = MRNNT_K1_CLOCK();
             mbar_wait(empty + stage, phase ^ 1u);
             MRNNT_K1_ADD(NW, 0, MRNNT_K1_CLOCK() - tw0);
             MRNNT_K1_ADD(NW, 2, 1);
@@ -314,9 +319,9 @@ static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
             const int stage = static_cast<int>(k % stages);
             const uint32_t phase = static_cast<uint32_t>((k / stages) & 1);
             const int64_t row = (blockIdx.x + k * gridDim.x) * G + r;
-            const long long tw0 = MRNNT_K1_CLOCK();
+            [[maybe_unused]] const long long tw0 = MRNNT_K1_CLOCK();
             mbar_wait(full + stage, phase);
-            const long long tw1 = MRNNT_K1_CLOCK();
+            [[maybe_unused]] const long long tw1 = MRNNT_K1_CLOCK();
             MRNNT_K1_ADD(warp, 0, tw1 - tw0);
             MRNNT_K1_ADD(warp, 2, 1);
             const int meta = meta_sh[stage * 32 + r];
