@@ -182,7 +182,7 @@ static __global__ void __launch_bounds__(kGenericWarps * kWarp)
 // ---------------------------------------------------------------------------------------------
 // TMA-staged variant.  Requirements (checked on the host): rows are whole 16-byte vectors (V % 4 == 0 for
 // float, V % 8 == 0 for bfloat16), acts 16-byte aligned, a tile fits a ring slot.
-// Shared memory: [stages][G*V] elements | full[stages] | empty[stages] | meta[stages][32]
+// Shared memory: [stages][G*V] elements | full[stages] | empty[stages] | meta[stages][32] | tile[stages]
 // ---------------------------------------------------------------------------------------------
 #ifdef MRNNT_K1_TRACE  // development aid (tools/k1_probe.cu): where the warps of CTA 0 spend their cycles
 __device__ long long g_k1_trace[32][4];  // per warp: cycles waiting, cycles working, rows/tiles, -
@@ -262,6 +262,7 @@ static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + static_cast<size_t>(stages) * tile_elems * sizeof(E));
     uint64_t *empty = full + stages;
     int *meta_sh = reinterpret_cast<int *>(empty + stages);
+    int *tile_sh = meta_sh + stages * 32;  // [stages] which of this CTA's tiles a slot holds (-1: no more tiles)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -281,29 +282,58 @@ static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
     if (warp == NW) {
         // ---------------- producer warp ----------------
         const uint64_t policy = l2_policy_evict_first();
-        auto load_meta = [&](int64_t k) {
-            const int64_t row = (blockIdx.x + k * gridDim.x) * G + lane;
-            return (k < nloc && lane < G && row < rows) ? __ldg(rowmeta + row) : kRowDead;
+        // rowmeta is fetched for 32/G tiles per load (lane l: tile k0 + l/G, row l%G) and two such batches ahead:
+        // with mostly dead tiles the producer does nothing but wait for these loads
+        const int TPB = 32 / G;  // tiles per batch (G is a power of two <= 32)
+        const uint32_t gmask = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
+        auto load_batch = [&](int64_t k0) {
+            const int64_t k = k0 + lane / G;
+            const int64_t row = (blockIdx.x + k * gridDim.x) * G + (lane % G);
+            return (k < nloc && row < rows) ? __ldg(rowmeta + row) : kRowDead;
         };
-        int m_next = load_meta(0);
+        int mb0 = load_batch(0), mb1 = load_batch(TPB);
         int stage = 0;
         uint32_t phase = 0;
-        for (int64_t k = 0; k < nloc; ++k) {
-            const int m = m_next;
-            m_next = load_meta(k + 1);  // one tile ahead: its latency hides behind this tile's wait
-            const int64_t row0 = (blockIdx.x + k * gridDim.x) * G;
-            const uint32_t mask = __ballot_sync(0xffffffffu, m != kRowDead);
-            [[maybe_unused]] const long long tw0 = MRNNT_K1_CLOCK();
-            mbar_wait(empty + stage, phase ^ 1u);
-            MRNNT_K1_ADD(NW, 0, MRNNT_K1_CLOCK() - tw0);
-            MRNNT_K1_ADD(NW, 2, 1);
-            meta_sh[stage * 32 + lane] = m;
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive_expect_tx(full + stage, static_cast<uint32_t>(__popc(mask)) * static_cast<uint32_t>(V) *
-                                                        static_cast<uint32_t>(sizeof(E)));
-                issue_live_runs<E>(mask, tiles + stage * tile_elems, acts + row0 * V, V, full + stage, policy);
+        for (int64_t k0 = 0; k0 < nloc; k0 += TPB) {
+            const int mb = mb0;
+            mb0 = mb1;
+            mb1 = load_batch(k0 + 2 * TPB);
+            const uint32_t ball = __ballot_sync(0xffffffffu, mb != kRowDead);
+            for (int j = 0; j < TPB && k0 + j < nloc; ++j) {
+                const int64_t k = k0 + j;
+                const uint32_t mask = (ball >> (j * G)) & gmask;
+                // A tile without a single live row takes no ring slot at all: the slots carry their tile's index,
+                // and the consumers walk the slots, not the tiles (alignment-restricted lattices and padded inputs
+                // are mostly dead rows, and a slot hand-over costs about as much as streaming 8 KB).
+                if (mask == 0u) continue;
+                const int m = __shfl_sync(0xffffffffu, mb, j * G + (lane % G));
+                const int64_t row0 = (blockIdx.x + k * gridDim.x) * G;
+                [[maybe_unused]] const long long tw0 = MRNNT_K1_CLOCK();
+                mbar_wait(empty + stage, phase ^ 1u);
+                MRNNT_K1_ADD(NW, 0, MRNNT_K1_CLOCK() - tw0);
+                MRNNT_K1_ADD(NW, 2, 1);
+                meta_sh[stage * 32 + lane] = lane < G ? m : kRowDead;
+                if (lane == 0) tile_sh[stage] = static_cast<int>(k);
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(full + stage, static_cast<uint32_t>(__popc(mask)) * static_cast<uint32_t>(V) *
+                                                            static_cast<uint32_t>(sizeof(E)));
+                    issue_live_runs<E>(mask, tiles + stage * tile_elems, acts + row0 * V, V, full + stage, policy);
+                }
+                if (++stage == stages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
             }
+        }
+        // one terminator per slot: every consumer warp meets one within its next `stages` slot uses
+        for (int i = 0; i < stages; ++i) {
+            mbar_wait(empty + stage, phase ^ 1u);
+            if (lane == 0) {
+                tile_sh[stage] = -1;
+                mbar_arrive_expect_tx(full + stage, 0u);
+            }
+            __syncwarp();
             if (++stage == stages) {
                 stage = 0;
                 phase ^= 1u;
@@ -311,17 +341,20 @@ static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
         }
     } else {
         // ---------------- consumer warps: one row at a time ----------------
+        // q walks the rows of the slot uses u = 0, 1, ... in order (G rows each); which tile a use holds is read
+        // from the slot
         const int NV = V / Elem<E>::kPerVec;
-        const int64_t nq = nloc * G;
-        for (int64_t q = warp; q < nq; q += NW) {
-            const int64_t k = q / G;
-            const int r = static_cast<int>(q - k * G);
-            const int stage = static_cast<int>(k % stages);
-            const uint32_t phase = static_cast<uint32_t>((k / stages) & 1);
-            const int64_t row = (blockIdx.x + k * gridDim.x) * G + r;
+        for (int64_t q = warp;; q += NW) {
+            const int64_t u = q / G;
+            const int r = static_cast<int>(q - u * G);
+            const int stage = static_cast<int>(u % stages);
+            const uint32_t phase = static_cast<uint32_t>((u / stages) & 1);
             [[maybe_unused]] const long long tw0 = MRNNT_K1_CLOCK();
             mbar_wait(full + stage, phase);
             [[maybe_unused]] const long long tw1 = MRNNT_K1_CLOCK();
+            const int k = tile_sh[stage];
+            if (k < 0) break;
+            const int64_t row = (blockIdx.x + static_cast<int64_t>(k) * gridDim.x) * G + r;
             MRNNT_K1_ADD(warp, 0, tw1 - tw0);
             MRNNT_K1_ADD(warp, 2, 1);
             const int meta = meta_sh[stage * 32 + r];
