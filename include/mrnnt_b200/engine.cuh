@@ -367,12 +367,12 @@ class Engine {
     // Pick the streaming (TMA-staged) configuration: the preferred consumer-warp count if a safe ring exists
     // for it, else 8 warps, else none (generic kernels).
     bool can_stream(const void *p0, const void *p1, size_t extra_per_row, int preferred_warps, int tile_target,
-                    const DeviceInfo &dev, StreamTiling *tl) const {
+                    bool whole_tiles, const DeviceInfo &dev, StreamTiling *tl) const {
         if (force_generic_) return false;
         if ((reinterpret_cast<uintptr_t>(p0) & 15) || (reinterpret_cast<uintptr_t>(p1) & 15)) return false;
         const int order[3] = {preferred_warps, 16, 8};
         for (int w : order) {
-            if (stream_tiling(V_, elem_bytes(), extra_per_row, w, tile_target, tl) &&
+            if (stream_tiling(V_, elem_bytes(), extra_per_row, w, tile_target, whole_tiles, tl) &&
                 tl->smem_bytes <= static_cast<size_t>(dev.max_smem_optin))
                 return true;
         }
@@ -414,7 +414,9 @@ class Engine {
         const int NV = V_ / NE;
         const bool wide_regs = NV > (32 / NE) * kWarp && NV <= (64 / NE) * kWarp;
         const int want = (k1_warps_ == 24 && wide_regs) ? 16 : k1_warps_;
-        if (can_stream(acts_, acts_, 0, want, kK1TileTarget, dev, &tl)) {
+        const size_t input_bytes = static_cast<size_t>(shape_.rows) * V_ * elem_bytes();
+        const int tile_target = input_bytes < kK1SmallInputBytes ? kK1TileTargetSmall : kK1TileTarget;
+        if (can_stream(acts_, acts_, sizeof(int), want, tile_target, false, dev, &tl)) {  // (8 bytes of slot metadata per row)
             return tl.warps == 8    ? launch_k1_nw<E, 8>(blank, stream, dev, tl)
                    : tl.warps == 16 ? launch_k1_nw<E, 16>(blank, stream, dev, tl)
                                     : launch_k1_nw<E, 24>(blank, stream, dev, tl);
@@ -493,7 +495,7 @@ class Engine {
     template <typename E>
     RNNTStatus launch_k3_typed(int blank, cudaStream_t stream, const DeviceInfo &dev, void *grads, const float *scale) {
         StreamTiling tl;
-        if (can_stream(acts_, grads, sizeof(float4), k3_warps_, kK3TileTarget, dev, &tl)) {
+        if (can_stream(acts_, grads, sizeof(float4), k3_warps_, kK3TileTarget, true, dev, &tl)) {
             if (scale != nullptr)
                 return tl.warps == 8    ? launch_k3_tma<E, 8, true>(blank, stream, dev, tl, grads, scale)
                        : tl.warps == 16 ? launch_k3_tma<E, 16, true>(blank, stream, dev, tl, grads, scale)

@@ -182,7 +182,7 @@ static __global__ void __launch_bounds__(kGenericWarps * kWarp)
 // ---------------------------------------------------------------------------------------------
 // TMA-staged variant.  Requirements (checked on the host): rows are whole 16-byte vectors (V % 4 == 0 for
 // float, V % 8 == 0 for bfloat16), acts 16-byte aligned, a tile fits a ring slot.
-// Shared memory: [stages][G*V] elements | full[stages] | empty[stages] | meta[stages][32] | tile[stages]
+// Shared memory: [stages][G*V] elements | full[stages] | empty[stages] | (meta, tile)[stages][32]
 // ---------------------------------------------------------------------------------------------
 #ifdef MRNNT_K1_TRACE  // development aid (tools/k1_probe.cu): where the warps of CTA 0 spend their cycles
 __device__ long long g_k1_trace[32][4];  // per warp: cycles waiting, cycles working, rows/tiles, -
@@ -206,6 +206,8 @@ constexpr size_t kStreamSmemBudget = 200 * 1024;  // of the 227 KB a CTA may use
 // cost of a tile hand-over is per tile, not per byte: 8 KB tiles are 2x slower than 32 KB ones, 64 KB ones up to
 // 6 % faster on c3 and 17 % faster on bfloat16 rows), K3 is best at 32 KB.
 constexpr int kK1TileTarget = 64 * 1024;
+constexpr int kK1TileTargetSmall = 32 * 1024;            // ... except on small inputs (c2: 100 us against 103)
+constexpr size_t kK1SmallInputBytes = size_t(2) << 30;  // "small": less than 2 GiB of logits
 constexpr int kK3TileTarget = 32 * 1024;
 
 // Tiling of the streaming kernels for vocabulary size V with `warps` consumer warps.
@@ -215,9 +217,12 @@ constexpr int kK3TileTarget = 32 * 1024;
 // NW > G a warp only touches every (NW/G)-th tile; a parity wait on an mbarrier is only meaningful if the
 // waiting warp also consumed the PREVIOUS use of that ring stage (bulk copies complete out of order, so
 // "an earlier tile was issued first" proves nothing).  Hence G is a power of two and the ring depth is a
-// multiple of the stride NW/G: every warp then cycles through a fixed subset of the stages.
+// multiple of the period NW/gcd(NW,G) of a warp's tile pattern: every warp then visits a fixed subset of the
+// stages, each of them at every one of its uses.
+// whole_tiles_per_warp_set: only accept warp counts that are a multiple of G when they exceed it (K3 measured
+// slower with 24 warps on 16-row tiles than with 16)
 inline bool stream_tiling(int V, size_t elem_bytes, size_t extra_per_row, int warps, int tile_target,
-                          StreamTiling *out) {
+                          bool whole_tiles_per_warp_set, StreamTiling *out) {
     const size_t row_bytes = static_cast<size_t>(V) * elem_bytes;
     if (V <= 0 || (row_bytes % 16) != 0 || (warps != 8 && warps != 16 && warps != 24)) return false;
     int G = 1;
@@ -225,8 +230,15 @@ inline bool stream_tiling(int V, size_t elem_bytes, size_t extra_per_row, int wa
     const size_t slot = static_cast<size_t>(G) * row_bytes + 32 * (sizeof(int) + extra_per_row) + 16;
     int stages = static_cast<int>(kStreamSmemBudget / slot);
     if (stages > kStreamMaxStages) stages = kStreamMaxStages;
-    if (warps > G && warps % G != 0) return false;  // (24 warps with 16-row tiles: no regular stride)
-    const int stride = warps > G ? warps / G : 1;
+    // warp w's uses repeat with period lcm(NW, G) rows = NW / gcd(NW, G) tiles (24 warps on 16-row tiles: 3)
+    int g = warps, h = G;
+    while (h != 0) {
+        const int t = g % h;
+        g = h;
+        h = t;
+    }
+    if (whole_tiles_per_warp_set && warps > G && warps % G != 0) return false;
+    const int stride = warps > G ? warps / g : 1;
     stages = stages / stride * stride;
     if (stages < 3) return false;
     out->G = G;
@@ -261,8 +273,8 @@ static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
     E *tiles = reinterpret_cast<E *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + static_cast<size_t>(stages) * tile_elems * sizeof(E));
     uint64_t *empty = full + stages;
-    int *meta_sh = reinterpret_cast<int *>(empty + stages);
-    int *tile_sh = meta_sh + stages * 32;  // [stages] which of this CTA's tiles a slot holds (-1: no more tiles)
+    // per slot and row: (rowmeta, which of this CTA's tiles the slot holds; -1: no more tiles) -- one 8-byte load
+    int2 *meta_sh = reinterpret_cast<int2 *>(empty + stages);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -312,8 +324,7 @@ static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
                 mbar_wait(empty + stage, phase ^ 1u);
                 MRNNT_K1_ADD(NW, 0, MRNNT_K1_CLOCK() - tw0);
                 MRNNT_K1_ADD(NW, 2, 1);
-                meta_sh[stage * 32 + lane] = lane < G ? m : kRowDead;
-                if (lane == 0) tile_sh[stage] = static_cast<int>(k);
+                meta_sh[stage * 32 + lane] = make_int2(lane < G ? m : kRowDead, static_cast<int>(k));
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive_expect_tx(full + stage, static_cast<uint32_t>(__popc(mask)) * static_cast<uint32_t>(V) *
@@ -329,11 +340,9 @@ static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
         // one terminator per slot: every consumer warp meets one within its next `stages` slot uses
         for (int i = 0; i < stages; ++i) {
             mbar_wait(empty + stage, phase ^ 1u);
-            if (lane == 0) {
-                tile_sh[stage] = -1;
-                mbar_arrive_expect_tx(full + stage, 0u);
-            }
+            meta_sh[stage * 32 + lane] = make_int2(kRowDead, -1);
             __syncwarp();
+            if (lane == 0) mbar_arrive_expect_tx(full + stage, 0u);
             if (++stage == stages) {
                 stage = 0;
                 phase ^= 1u;
@@ -352,12 +361,13 @@ static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
             [[maybe_unused]] const long long tw0 = MRNNT_K1_CLOCK();
             mbar_wait(full + stage, phase);
             [[maybe_unused]] const long long tw1 = MRNNT_K1_CLOCK();
-            const int k = tile_sh[stage];
+            const int2 mk = meta_sh[stage * 32 + r];
+            const int k = mk.y;
             if (k < 0) break;
             const int64_t row = (blockIdx.x + static_cast<int64_t>(k) * gridDim.x) * G + r;
             MRNNT_K1_ADD(warp, 0, tw1 - tw0);
             MRNNT_K1_ADD(warp, 2, 1);
-            const int meta = meta_sh[stage * 32 + r];
+            const int meta = mk.x;
             if (row < rows && meta != kRowDead) {
                 const E *xrow = tiles + stage * tile_elems + static_cast<size_t>(r) * V;
                 int lab = -1;

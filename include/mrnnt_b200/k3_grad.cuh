@@ -113,15 +113,17 @@ static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
             const int64_t row = (blockIdx.x + k * gridDim.x) * G + lane;
             return (SCALED && k < nloc && lane < G && row < rows) ? __ldg(scale + __ldg(rowutt + row)) : 1.0f;
         };
-        float4 c_next = load_coef(0);
-        float s_next = load_scale(0);
+        float4 c_next = load_coef(0), c_next2 = load_coef(1);
+        float s_next = load_scale(0), s_next2 = load_scale(1);
         int stage = 0;
         uint32_t phase = 0;
         for (int64_t k = 0; k < nloc; ++k) {
             const float4 c = c_next;
             const float sc = s_next;
-            c_next = load_coef(k + 1);  // one tile ahead: its latency hides behind this tile's wait
-            s_next = load_scale(k + 1);
+            c_next = c_next2;  // two tiles ahead: the latency hides behind two tiles' waits
+            s_next = s_next2;
+            c_next2 = load_coef(k + 2);
+            s_next2 = load_scale(k + 2);
             const int64_t row0 = (blockIdx.x + k * gridDim.x) * G;
             const uint32_t mask = __ballot_sync(0xffffffffu, !(c.x == kNegInfF));
             mbar_wait(empty + stage, phase ^ 1u);

@@ -52,7 +52,7 @@ int main(int argc, char **argv) {
     cudaMalloc(&meta, rows * 4); cudaMemcpy(meta, hm.data(), rows * 4, cudaMemcpyHostToDevice);
     cudaMalloc(&lp, rows * sizeof(RawRow));
     StreamTiling tl;
-    if (!stream_tiling(V, es, 0, NW, kK1TileTarget, &tl)) { printf("no tiling\n"); return 1; }
+    if (!stream_tiling(V, es, sizeof(int), NW, kK1TileTarget, false, &tl)) { printf("no tiling\n"); return 1; }
     const int NV = V / (16 / (int)es);
 #define DISPATCH(E, NWc) do { if (NV <= (32 / Elem<E>::kPerVec) * 32) run<E, NWc, 32 / Elem<E>::kPerVec>(acts, labels, meta, lp, rows, V, tl); \
                               else run<E, NWc, 0>(acts, labels, meta, lp, rows, V, tl); } while (0)

@@ -83,7 +83,7 @@ int main() {
     float *acts, *out; cudaMalloc(&acts, n * 4); cudaMalloc(&out, n * 4); cudaMemset(acts, 0, n * 4);
     const double gb = n * 4 / 1e9;
     for (int nw : {8, 16}) {
-        StreamTiling tl; stream_tiling(V, 4, 0, nw, kK3TileTarget, &tl);
+        StreamTiling tl; stream_tiling(V, 4, 0, nw, kK3TileTarget, true, &tl);
         auto run = [&](auto kern, const char *name) {
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.smem_bytes);
             float ms = timeit([&] { kern<<<148, (nw + 1) * 32, tl.smem_bytes>>>(acts, out, rows, V, tl.G, tl.stages); });
