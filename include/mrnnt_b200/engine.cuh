@@ -321,6 +321,7 @@ class Engine {
     // Force the generic (non-TMA) streaming kernels; used by the tests to cross-check both variants.
     void set_force_generic(bool v) { force_generic_ = v; }
     void set_pdl(bool on) { pdl_ = on; }
+    void set_k1_compact(int mode) { k1_compact_ = mode < 0 ? -1 : (mode != 0); }
     // SMs the gradient kernel leaves free for a concurrent collective (0: none).
     void set_reserved_sms(int n) { reserved_sms_ = n < 0 ? 0 : n; }
     // Upper limit for the CTAs per utterance of the lattice kernel's coefficient phase (0: automatic).
@@ -385,13 +386,27 @@ class Engine {
         return static_cast<int>(want < cap ? (want < 1 ? 1 : want) : cap);
     }
 
-    template <typename E, int NW, int C>
-    RNNTStatus launch_k1_tma(int blank, cudaStream_t stream, const DeviceInfo &dev, const StreamTiling &tl) {
-        auto kern = k1_lse_tma_kernel<E, NW, C>;
+    template <typename E, int NW, int C, bool COMPACT>
+    RNNTStatus launch_k1_variant(int blank, cudaStream_t stream, const DeviceInfo &dev, const StreamTiling &tl) {
+        auto kern = k1_lse_tma_kernel<E, NW, C, COMPACT>;
         if (!ensure_dynamic_smem(kern, tl.smem_bytes)) return RNNT_STATUS_EXECUTION_FAILED;
         kern<<<dev.sm_count, (NW + 1) * kWarp, tl.smem_bytes, stream>>>(static_cast<const E *>(acts_), labels_, ws_.rowmeta,
                                                                          ws_.lp, shape_.rows, V_, blank, tl.G, tl.stages);
         return launched();
+    }
+
+    // Many dead tiles expected -- an alignment band, a padded tensor, or tiles of so few rows that the dead corners of
+    // the lattice fill whole tiles (c4: tiles of 2 rows, 15 % of them dead, K1 2211 -> 2030 us): the variant of K1 that
+    // gives them no ring slot.  On c2 / c3 (tiles of 8 / 16 rows) it costs 1-4 us, so it is not the default there.
+    bool k1_compact(const StreamTiling &tl) const {
+        if (k1_compact_ >= 0) return k1_compact_ != 0;
+        return alignment_ != nullptr || shape_.U > 0 || tl.G <= 4;
+    }
+
+    template <typename E, int NW, int C>
+    RNNTStatus launch_k1_tma(int blank, cudaStream_t stream, const DeviceInfo &dev, const StreamTiling &tl) {
+        return k1_compact(tl) ? launch_k1_variant<E, NW, C, true>(blank, stream, dev, tl)
+                              : launch_k1_variant<E, NW, C, false>(blank, stream, dev, tl);
     }
 
     // C = 16-byte vectors a lane keeps in registers: a row in 32 floats per lane, in 64, or two passes over smem
@@ -539,6 +554,7 @@ class Engine {
     int align_blank_ = 0;
     bool force_generic_ = false;
     int k1_warps_ = 24;
+    int k1_compact_ = -1;  // -1: automatic (k1_compact()), 0 / 1: forced
     int k3_warps_ = 24;
     int k2_parts_ = 0;     // 0: automatic
     int reserved_sms_ = 0;

@@ -263,7 +263,11 @@ __device__ __forceinline__ void issue_live_runs(uint32_t mask, E *tile, const E 
     }
 }
 
-template <typename E, int NW, int C>
+// COMPACT: tiles without a live row take no ring slot (the slots carry their tile's index and the consumers walk
+// the slots, not the tiles; the producer ends the sequence with one terminator per slot).  Worth it when many
+// tiles are dead -- alignment-restricted lattices, padded inputs -- and costs ~2 % on dense inputs (the end of the
+// kernel waits for the terminators), hence a compile-time choice made by the engine.
+template <typename E, int NW, int C, bool COMPACT>
 static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
     k1_lse_tma_kernel(const E *__restrict__ acts, const int *__restrict__ labels,
                       const int *__restrict__ rowmeta, RawRow *__restrict__ lp, int64_t rows, int V, int blank,
@@ -314,10 +318,9 @@ static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
             for (int j = 0; j < TPB && k0 + j < nloc; ++j) {
                 const int64_t k = k0 + j;
                 const uint32_t mask = (ball >> (j * G)) & gmask;
-                // A tile without a single live row takes no ring slot at all: the slots carry their tile's index,
-                // and the consumers walk the slots, not the tiles (alignment-restricted lattices and padded inputs
-                // are mostly dead rows, and a slot hand-over costs about as much as streaming 8 KB).
-                if (mask == 0u) continue;
+                // COMPACT: a tile without a single live row takes no ring slot at all (a slot hand-over costs about
+                // as much as streaming 8 KB)
+                if (COMPACT && mask == 0u) continue;
                 const int m = __shfl_sync(0xffffffffu, mb, j * G + (lane % G));
                 const int64_t row0 = (blockIdx.x + k * gridDim.x) * G;
                 [[maybe_unused]] const long long tw0 = MRNNT_K1_CLOCK();
@@ -338,7 +341,7 @@ static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
             }
         }
         // one terminator per slot: every consumer warp meets one within its next `stages` slot uses
-        for (int i = 0; i < stages; ++i) {
+        for (int i = 0; COMPACT && i < stages; ++i) {
             mbar_wait(empty + stage, phase ^ 1u);
             meta_sh[stage * 32 + lane] = make_int2(kRowDead, -1);
             __syncwarp();
@@ -353,7 +356,8 @@ static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
         // q walks the rows of the slot uses u = 0, 1, ... in order (G rows each); which tile a use holds is read
         // from the slot
         const int NV = V / Elem<E>::kPerVec;
-        for (int64_t q = warp;; q += NW) {
+        const int64_t nq = nloc * G;
+        for (int64_t q = warp; COMPACT || q < nq; q += NW) {
             const int64_t u = q / G;
             const int r = static_cast<int>(q - u * G);
             const int stage = static_cast<int>(u % stages);
@@ -362,9 +366,9 @@ static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
             mbar_wait(full + stage, phase);
             [[maybe_unused]] const long long tw1 = MRNNT_K1_CLOCK();
             const int2 mk = meta_sh[stage * 32 + r];
-            const int k = mk.y;
-            if (k < 0) break;
-            const int64_t row = (blockIdx.x + static_cast<int64_t>(k) * gridDim.x) * G + r;
+            const int64_t k = COMPACT ? mk.y : u;
+            if (COMPACT && k < 0) break;
+            const int64_t row = (blockIdx.x + k * gridDim.x) * G + r;
             MRNNT_K1_ADD(warp, 0, tw1 - tw0);
             MRNNT_K1_ADD(warp, 2, 1);
             const int meta = mk.x;

@@ -215,6 +215,9 @@ RNNTStatus mrnnt_set_option(mrnnt_handle_t h, int option, int value) {
         case MRNNT_OPT_K3_WARPS:
             h->manager.engine().set_stream_warps(0, value);
             return RNNT_STATUS_SUCCESS;
+        case MRNNT_OPT_K1_COMPACT:
+            h->manager.engine().set_k1_compact(value);
+            return RNNT_STATUS_SUCCESS;
         case MRNNT_OPT_PDL:
             h->manager.engine().set_pdl(value != 0);
             return RNNT_STATUS_SUCCESS;

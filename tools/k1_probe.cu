@@ -10,7 +10,7 @@ using namespace mrnnt;
 
 template <typename E, int NW, int C>
 static void run(const void *acts, const int *labels, const int *meta, RawRow *lp, int64_t rows, int V, const StreamTiling &tl) {
-    auto kern = k1_lse_tma_kernel<E, NW, C>;
+    auto kern = k1_lse_tma_kernel<E, NW, C, false>;
     cudaError_t ea = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.smem_bytes);
     cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, kern);
     printf("regs=%d smem_dyn_max=%d static=%zu attr=%s\n", fa.numRegs, fa.maxDynamicSharedSizeBytes, fa.sharedSizeBytes, cudaGetErrorString(ea));

@@ -18,7 +18,7 @@ import monotonic_rnnt_b200 as mr  # noqa: E402
 from monotonic_rnnt_b200 import _lib  # noqa: E402
 
 
-def run(name: str, iters: int, combos, padded: bool = False, bf16: bool = False) -> None:
+def run(name: str, iters: int, combos, padded: bool = False, bf16: bool = False, compact: int = -1) -> None:
     wl = mr.synth.workload(name)
     dev = torch.device("cuda", 0)
     lib = _lib.load()
@@ -41,6 +41,7 @@ def run(name: str, iters: int, combos, padded: bool = False, bf16: bool = False)
     if wl.alignment is not None:
         h.restrict_to_alignment(torch.from_numpy(wl.alignment).to(dev), wl.max_shift, wl.blank)
     h.set_option(_lib.OPT_TIMING, 1)
+    h.set_option(_lib.OPT_K1_COMPACT, compact)
     costs = torch.empty(wl.B, dtype=torch.float32).pin_memory()
     n4 = wl.elements * (2 if bf16 else 4)
     for k1w, k3w in combos:
@@ -79,8 +80,9 @@ if __name__ == "__main__":
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--combos", default="24:24")
     ap.add_argument("--bf16", action="store_true", help="bfloat16 logits and gradients")
+    ap.add_argument("--compact", type=int, default=-1, help="K1 dead-tile compaction: 1 / 0 forced, -1 automatic")
     ap.add_argument("--padded", action="store_true", help="feed the padded [B,T,S+1,V] tensor instead of packed rows")
     a = ap.parse_args()
     combos = [tuple(int(x) for x in c.split(":")) for c in a.combos.split(",")]
     for name in a.workloads:
-        run(name, a.iters, combos, a.padded, a.bf16)
+        run(name, a.iters, combos, a.padded, a.bf16, a.compact)
