@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstring>
 #include <mutex>
 #include <vector>
 
@@ -85,6 +86,42 @@ inline bool ensure_dynamic_smem(Kern kern, size_t bytes) {
         slot->bytes[dev] = bytes;
     }
     return true;
+}
+
+// Host-mapped pinned staging buffers for the B costs of a synchronous call: the lattice kernel writes them straight
+// into host memory (128 bytes over PCIe for c2), so the call ends with the stream synchronisation alone -- no
+// device-to-host copy is queued behind the gradient kernel.  Allocation of pinned memory is slow, so the buffers are
+// pooled per module and reused; a batch that does not fit (or a failed allocation) falls back to cudaMemcpyAsync.
+constexpr size_t kCostStageFloats = 16384;
+struct CostStage {
+    float *host = nullptr;  // == device address (unified addressing, cudaHostAllocPortable | cudaHostAllocMapped)
+};
+static std::vector<CostStage> g_cost_stages;
+static std::mutex g_cost_stage_mutex;
+
+inline CostStage acquire_cost_stage(size_t floats) {
+    CostStage st;
+    if (floats > kCostStageFloats) return st;
+    {
+        std::lock_guard<std::mutex> lock(g_cost_stage_mutex);
+        if (!g_cost_stages.empty()) {
+            st = g_cost_stages.back();
+            g_cost_stages.pop_back();
+            return st;
+        }
+    }
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, kCostStageFloats * sizeof(float), cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return st;
+    }
+    st.host = static_cast<float *>(p);
+    return st;
+}
+inline void release_cost_stage(const CostStage &st) {
+    if (st.host == nullptr) return;
+    std::lock_guard<std::mutex> lock(g_cost_stage_mutex);
+    g_cost_stages.push_back(st);
 }
 
 // Kernel launch, optionally as a programmatic dependent of the previous kernel in the stream (common.cuh).
@@ -240,12 +277,18 @@ class Engine {
         RNNTStatus st = ensure_shape();
         if (st != RNNT_STATUS_SUCCESS) return st;
         if (base_ == nullptr || blank < 0 || blank >= V_) return RNNT_STATUS_INVALID_VALUE;
+        const CostStage stage = acquire_cost_stage(static_cast<size_t>(B_));
+        costs_mapped_ = stage.host;
         st = enqueue(blank, stream, grads_dev);
-        if (st != RNNT_STATUS_SUCCESS) return st;
-        if (cudaMemcpyAsync(costs_host, ws_.costs, sizeof(float) * B_, cudaMemcpyDeviceToHost, stream) != cudaSuccess)
-            return RNNT_STATUS_MEMOPS_FAILED;
-        if (cudaStreamSynchronize(stream) != cudaSuccess) return RNNT_STATUS_EXECUTION_FAILED;
-        return RNNT_STATUS_SUCCESS;
+        costs_mapped_ = nullptr;
+        if (st == RNNT_STATUS_SUCCESS && stage.host == nullptr &&
+            cudaMemcpyAsync(costs_host, ws_.costs, sizeof(float) * B_, cudaMemcpyDeviceToHost, stream) != cudaSuccess)
+            st = RNNT_STATUS_MEMOPS_FAILED;
+        if (st == RNNT_STATUS_SUCCESS && cudaStreamSynchronize(stream) != cudaSuccess) st = RNNT_STATUS_EXECUTION_FAILED;
+        if (st == RNNT_STATUS_SUCCESS && stage.host != nullptr) std::memcpy(costs_host, stage.host, sizeof(float) * B_);
+        if (st != RNNT_STATUS_SUCCESS && stage.host != nullptr) (void)cudaStreamSynchronize(stream);  // nothing may still write into it
+        release_cost_stage(stage);
+        return st;
     }
 
     // Launch everything on `stream` without synchronising; costs stay in workspace().costs.
@@ -460,6 +503,7 @@ class Engine {
         a.T = T_dev_; a.S = S_dev_; a.labels = labels_; a.row_start = ws_.row_start; a.band = ws_.band;
         a.lp = ws_.lp; a.wts = ws_.wts; a.alpha = ws_.alpha; a.beta = ws_.beta; a.coef = ws_.coef;
         a.ll_fwd = ws_.ll_fwd; a.ll_bwd = ws_.ll_bwd; a.costs = ws_.costs;
+        a.costs_mapped = need_beta ? nullptr : costs_mapped_;  // (with gradients: K3 mirrors the costs, see cost_mirror)
         a.T_max = shape_.T_max; a.S_max = shape_.S_max; a.V = V_; a.blank = blank;
         a.ld = shape_.U; a.T_dim = shape_.T_dim; a.label_stride = shape_.label_stride;
         a.need_beta = need_beta ? 1 : 0;
@@ -502,7 +546,7 @@ class Engine {
         // predecessor to wait for, and an ordinary launch orders it behind whatever precedes it in the stream)
         if (launch_kernel(kern, grid, (NW + 1) * kWarp, tl.smem_bytes, stream, pdl_ && k3_follows_k2_,
                           static_cast<const E *>(acts_), ws_.coef, static_cast<E *>(grads), shape_.rows, V_, blank, tl.G,
-                          tl.stages, ws_.rowutt, scale) != cudaSuccess)
+                          tl.stages, ws_.rowutt, scale, cost_mirror()) != cudaSuccess)
             return RNNT_STATUS_EXECUTION_FAILED;
         return launched();
     }
@@ -520,7 +564,8 @@ class Engine {
                                     : launch_k3_tma<E, 24, false>(blank, stream, dev, tl, grads, scale);
         }
         k3_grad_generic_kernel<E><<<generic_grid(dev), kGenericWarps * kWarp, 0, stream>>>(
-            static_cast<const E *>(acts_), ws_.coef, static_cast<E *>(grads), shape_.rows, V_, blank, ws_.rowutt, scale);
+            static_cast<const E *>(acts_), ws_.coef, static_cast<E *>(grads), shape_.rows, V_, blank, ws_.rowutt, scale,
+            cost_mirror());
         return launched();
     }
 
@@ -530,6 +575,16 @@ class Engine {
     }
 
     size_t elem_bytes() const { return bf16_ ? 2 : 4; }
+
+    // who copies the costs into a synchronous call's host-mapped staging buffer: the gradient kernel when there is
+    // one (the write then overlaps it), else the lattice kernel
+    CostMirror cost_mirror() const {
+        CostMirror m;
+        m.costs = ws_.costs;
+        m.mapped = costs_mapped_;
+        m.B = B_;
+        return m;
+    }
 
     const void *acts_;   // float32 (the reference's type) or bfloat16 (set_bf16)
     bool bf16_ = false;
@@ -561,6 +616,7 @@ class Engine {
     bool pdl_ = true;             // programmatic dependent launch of K2 behind K1 and of K3 behind K2
     bool k3_follows_k2_ = false;  // K3 is being enqueued directly behind K2 (enqueue(), not a separate backward)
     unsigned epoch_ = 0u;  // launch counter published through Workspace::k2_flags
+    float *costs_mapped_ = nullptr;  // set for the duration of a synchronous compute(): host-mapped copy of the costs
     int coef_blank_ = -1;  // blank label of the forward pass whose coefficients sit in the workspace (-1: none)
     bool timing_ = false;
     cudaEvent_t ev_[4] = {};

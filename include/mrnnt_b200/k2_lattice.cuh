@@ -75,6 +75,7 @@ struct K2Args {
     double *ll_fwd;
     double *ll_bwd;
     float *costs;
+    float *costs_mapped;  // optional second copy of the costs in host-mapped pinned memory (nullptr: none)
     unsigned *flags;   // [2B] per utterance: phase-A arrival counter, "recursion done" epoch (zeroed at set-up)
     unsigned epoch;    // value published by this launch (never 0)
     int T_max;
@@ -429,6 +430,7 @@ __device__ __forceinline__ void k2_chain_warp(const K2Args &a, int b, K2Dir &rin
                 const double ll = cell_log(m[j], e[j]);
                 a.ll_fwd[b] = ll;
                 a.costs[b] = static_cast<float>(-ll);
+                if (a.costs_mapped != nullptr) a.costs_mapped[b] = static_cast<float>(-ll);
             }
         }
     } else if (wi == 0 && lane == 0) {
@@ -721,6 +723,7 @@ static __global__ void __launch_bounds__(kK2Threads) k2_lattice_wide_kernel(K2Ar
         const double ll = cell_log(prev[Sb].m, prev[Sb].e);
         a.ll_fwd[b] = ll;
         a.costs[b] = static_cast<float>(-ll);
+        if (a.costs_mapped != nullptr) a.costs_mapped[b] = static_cast<float>(-ll);
     }
     if (!a.need_beta) return;
     __syncthreads();

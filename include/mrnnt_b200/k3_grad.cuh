@@ -26,6 +26,19 @@ namespace mrnnt {
 
 __device__ __forceinline__ float grad_elem(float x, float c) { return ex2_approx(fmaf(x, kLog2e, c)); }
 
+// Optional hand-over of the B costs to the host (a synchronous call's staging buffer in host-mapped pinned memory,
+// engine.cuh): done here, by the first CTA of the LAST kernel of the call, so that the PCIe write overlaps the whole
+// gradient pass instead of sitting between the lattice kernel and this one.
+struct CostMirror {
+    const float *costs = nullptr;  // device, final since the lattice kernel
+    float *mapped = nullptr;       // host-mapped copy, or nullptr
+    int B = 0;
+};
+__device__ __forceinline__ void mirror_costs(const CostMirror &m) {
+    if (m.mapped != nullptr && blockIdx.x == 0)
+        for (int i = threadIdx.x; i < m.B; i += blockDim.x) m.mapped[i] = m.costs[i];
+}
+
 // subtract the blank / label term from component k of a vector of NE gradients (k is warp-divergent, so the
 // component is picked with selects instead of a dynamically indexed register array)
 template <int NE>
@@ -45,7 +58,8 @@ template <typename E>
 static __global__ void __launch_bounds__(kGenericWarps * kWarp)
     k3_grad_generic_kernel(const E *__restrict__ acts, const float4 *__restrict__ coef, E *__restrict__ grads,
                            int64_t rows, int V, int blank, const int *__restrict__ rowutt,
-                           const float *__restrict__ scale) {
+                           const float *__restrict__ scale, CostMirror mirror) {
+    mirror_costs(mirror);
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * kGenericWarps + (threadIdx.x >> 5);
     const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kGenericWarps;
@@ -77,7 +91,7 @@ template <typename E, int NW, bool SCALED>
 static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
     k3_grad_tma_kernel(const E *__restrict__ acts, const float4 *__restrict__ coef, E *__restrict__ grads,
                        int64_t rows, int V, int blank, int G, int stages, const int *__restrict__ rowutt,
-                       const float *__restrict__ scale) {
+                       const float *__restrict__ scale, CostMirror mirror) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NE = Elem<E>::kPerVec;
     const size_t tile_elems = static_cast<size_t>(G) * V;
@@ -98,6 +112,7 @@ static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
     }
     __syncthreads();
     pdl_wait();  // the coefficients come from the lattice kernel; everything above overlapped its tail
+    mirror_costs(mirror);
 
     const int64_t ntiles = (rows + G - 1) / G;
     const int64_t nloc = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;

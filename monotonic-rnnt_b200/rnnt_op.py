@@ -16,6 +16,7 @@ Differences, all on the host side of the boundary:
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 from typing import Optional, Tuple
 
@@ -23,6 +24,9 @@ import numpy as np
 import torch
 
 from . import _lib
+
+
+_NULL_CONTEXT = contextlib.nullcontext()
 
 
 def _check_inputs(acts, labels, input_lengths, label_lengths) -> None:
@@ -133,6 +137,13 @@ class LossHandle:
         _lib.check(self._lib.mrnnt_restrict_to_alignment(self._h, alignment.data_ptr(), int(max_shift), int(blank_idx)),
                    "mrnnt_restrict_to_alignment")
 
+    def _device(self):
+        """Make acts' device current for the call; free when it already is (the usual case)."""
+        idx = self.acts.device.index
+        if idx is None or torch.cuda.current_device() == idx:
+            return _NULL_CONTEXT
+        return torch.cuda.device(idx)
+
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.acts.device).cuda_stream
 
@@ -147,7 +158,7 @@ class LossHandle:
             assert grads.is_cuda and grads.dtype == self.acts.dtype and grads.is_contiguous()
             assert grads.numel() == self.acts.numel()
             gptr = grads.data_ptr()
-        with torch.cuda.device(self.acts.device):
+        with self._device():
             st = self._lib.mrnnt_cost_and_grad(self._h, int(blank_label), self._stream(), costs_host.data_ptr(), gptr)
         _lib.check(st, "mrnnt_cost_and_grad")
         return costs_host
@@ -158,7 +169,7 @@ class LossHandle:
     def enqueue(self, blank_label: int = 0, grads: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Launch without synchronising the host; returns a device VIEW of the costs (valid in stream order)."""
         gptr = grads.data_ptr() if grads is not None else None
-        with torch.cuda.device(self.acts.device):
+        with self._device():
             st = self._lib.mrnnt_enqueue(self._h, int(blank_label), self._stream(), gptr)
         _lib.check(st, "mrnnt_enqueue")
         return self.device_costs()
@@ -166,7 +177,7 @@ class LossHandle:
     def enqueue_forward(self, blank_label: int = 0, want_grads: bool = True) -> torch.Tensor:
         """First half of a call (K1 + K2); returns a device VIEW of the costs.  With want_grads the workspace
         keeps what enqueue_backward() needs; acts and the workspace must stay untouched until then."""
-        with torch.cuda.device(self.acts.device):
+        with self._device():
             st = self._lib.mrnnt_enqueue_forward(self._h, int(blank_label), self._stream(), 1 if want_grads else 0)
         _lib.check(st, "mrnnt_enqueue_forward")
         return self.device_costs()
@@ -179,7 +190,7 @@ class LossHandle:
         if scale is not None:
             assert scale.is_cuda and scale.dtype == torch.float32 and scale.is_contiguous() and scale.numel() == self.B
             sptr = scale.data_ptr()
-        with torch.cuda.device(self.acts.device):
+        with self._device():
             st = self._lib.mrnnt_enqueue_backward(self._h, self._stream(), grads.data_ptr(), sptr)
         _lib.check(st, "mrnnt_enqueue_backward")
         return grads
@@ -203,7 +214,7 @@ class LossHandle:
         }
         dt, shape = shapes[what]
         out = np.empty(shape, dtype=dt)
-        with torch.cuda.device(self.acts.device):
+        with self._device():
             _lib.check(self._lib.mrnnt_debug_copy(self._h, what, out.ctypes.data, out.nbytes), "mrnnt_debug_copy")
         return out
 
