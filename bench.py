@@ -232,9 +232,18 @@ def run_b200(args) -> None:
 
     cost_sum_host = torch.zeros((), dtype=torch.float32).pin_memory()
 
+    # the C-ABI entry itself, bound once (handle, blank, stream, costs on the host, gradients on the device): the
+    # Python mirror adds argument checks and attribute look-ups that are not part of the path being measured
+    import ctypes
+    abi_call = lib.mrnnt_cost_and_grad
+    abi_args = (handle._h, ctypes.c_int(wl.blank), ctypes.c_void_p(stream.cuda_stream),
+                ctypes.c_void_p(costs_host.data_ptr()), ctypes.c_void_p(grads.data_ptr()))
+
     def one_step():
         if world == 1:
-            handle.cost_and_grad(wl.blank, grads, costs_host)  # the C-ABI call: costs on the host on return
+            st = abi_call(*abi_args)  # costs on the host on return (one stream synchronisation inside)
+            if st != 0:
+                _lib.check(st, "mrnnt_cost_and_grad")
             return
         # N > 1: the same three kernels without a host round trip in between.  The costs are final after K2, so the
         # path's only collective (all-reduce of the summed cost, 4 bytes over NVLink) runs on NCCL's stream WHILE
