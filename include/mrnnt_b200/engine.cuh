@@ -489,10 +489,24 @@ class Engine {
     }
 
     template <int K>
-    RNNTStatus launch_k2_warp(const K2Args &args, cudaStream_t stream) {
+    RNNTStatus launch_k2_warp(K2Args args, cudaStream_t stream, const DeviceInfo &dev) {
         auto kern = k2_lattice_kernel<K>;
         const size_t smem = k2_smem_bytes(shape_.width(), args.row_warps);
         if (!ensure_dynamic_smem(kern, smem)) return RNNT_STATUS_EXECUTION_FAILED;
+        if (args.parts > 1) {
+            // The CTAs of an utterance wait for each other: the whole grid has to be co-resident.  How many CTAs fit
+            // on an SM depends on the ring size of this launch; asked once per (kernel, shared-memory size).
+            if (k2_occ_smem_ != smem || k2_occ_kernel_ != reinterpret_cast<const void *>(kern)) {
+                int occ = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kK2Threads, smem) != cudaSuccess || occ < 1)
+                    return RNNT_STATUS_EXECUTION_FAILED;
+                k2_occ_ = occ;
+                k2_occ_smem_ = smem;
+                k2_occ_kernel_ = reinterpret_cast<const void *>(kern);
+            }
+            const int fit = k2_occ_ * dev.sm_count / B_;
+            if (args.parts > fit) args.parts = fit < 1 ? 1 : fit;
+        }
         if (launch_kernel(kern, B_ * args.parts, kK2Threads, smem, stream, pdl_ && !timing_, args) != cudaSuccess)
             return RNNT_STATUS_EXECUTION_FAILED;
         return launched();
@@ -510,8 +524,7 @@ class Engine {
         a.chunk_frames = k2_chunk_frames(shape_.width());
         // Coefficient phase: spread every utterance over `parts` CTAs while the whole grid still fits on the
         // machine at one CTA per SM (the extra CTAs wait for their utterance's recursion on idle SMs).
-        int parts = need_beta ? dev.sm_count / B_ : 1;
-        parts = parts < 1 ? 1 : (parts > kK2MaxParts ? kK2MaxParts : parts);
+        int parts = need_beta ? kK2MaxParts : 1;  // (launch_k2_warp lowers it to what is co-resident)
         if (k2_parts_ > 0 && k2_parts_ < parts) parts = k2_parts_;
         a.parts = parts;
         a.flags = ws_.k2_flags;
@@ -522,7 +535,9 @@ class Engine {
         if (K > 0) {
             a.row_warps = k2_row_warps(states, K);
             a.chunk_bufs = k2_chunk_bufs(a.row_warps);
-            return K == 1 ? launch_k2_warp<1>(a, stream) : K == 2 ? launch_k2_warp<2>(a, stream) : launch_k2_warp<4>(a, stream);
+            return K == 1   ? launch_k2_warp<1>(a, stream, dev)
+                   : K == 2 ? launch_k2_warp<2>(a, stream, dev)
+                            : launch_k2_warp<4>(a, stream, dev);
         }
         a.parts = 1;
         a.row_warps = 0;
@@ -612,6 +627,9 @@ class Engine {
     int k1_compact_ = -1;  // -1: automatic (k1_compact()), 0 / 1: forced
     int k3_warps_ = 24;
     int k2_parts_ = 0;     // 0: automatic
+    int k2_occ_ = 0;       // CTAs of the lattice kernel per SM for (k2_occ_kernel_, k2_occ_smem_)
+    size_t k2_occ_smem_ = 0;
+    const void *k2_occ_kernel_ = nullptr;
     int reserved_sms_ = 0;
     bool pdl_ = true;             // programmatic dependent launch of K2 behind K1 and of K3 behind K2
     bool k3_follows_k2_ = false;  // K3 is being enqueued directly behind K2 (enqueue(), not a separate backward)
