@@ -246,17 +246,32 @@ def run_b200(args) -> None:
                 _lib.check(st, "mrnnt_cost_and_grad")
             return
         # N > 1: the same three kernels without a host round trip in between.  The costs are final after K2, so the
-        # path's only collective (all-reduce of the summed cost, 4 bytes over NVLink) runs on NCCL's stream WHILE
-        # K3 streams the gradients (measured: no SM needs to be set aside for it); ONE synchronisation at the end, at
-        # which the per-utterance costs and the global sum are on the host.
-        dev_costs = handle.enqueue_forward(wl.blank, want_grads=True)
-        total = dev_costs.sum()
-        work = dist.all_reduce(total, async_op=True)
-        handle.enqueue_backward(grads)
-        work.wait()
-        costs_host.copy_(dev_costs, non_blocking=True)
-        cost_sum_host.copy_(total, non_blocking=True)
+        # path's only collective (all-reduce of the summed cost, 4 bytes over NVLink) and the copies of the costs to
+        # the host run on a side stream / NCCL's stream WHILE K3 streams the gradients on the compute stream
+        # (measured: no SM needs to be set aside for them); ONE host synchronisation at the end of the step, at
+        # which the gradients are complete and the per-utterance costs and the global sum are on the host.
+        st = fwd_call(*fwd_args)                       # K1, K2
+        if st != 0:
+            _lib.check(st, "mrnnt_enqueue_forward")
+        k2_done.record(stream)
+        st = bwd_call(*bwd_args)                       # K3 (compute stream)
+        if st != 0:
+            _lib.check(st, "mrnnt_enqueue_backward")
+        with torch.cuda.stream(side):
+            side.wait_event(k2_done)
+            costs_host.copy_(dev_costs, non_blocking=True)
+            total = dev_costs.sum()
+            dist.all_reduce(total)                     # NCCL's stream, ordered after `side` up to here
+            cost_sum_host.copy_(total, non_blocking=True)
+        side.synchronize()
         stream.synchronize()
+
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
+    k2_done = torch.cuda.Event() if world > 1 else None
+    dev_costs = handle.device_costs()
+    fwd_call, bwd_call = lib.mrnnt_enqueue_forward, lib.mrnnt_enqueue_backward
+    fwd_args = (handle._h, ctypes.c_int(wl.blank), ctypes.c_void_p(stream.cuda_stream), ctypes.c_int(1))
+    bwd_args = (handle._h, ctypes.c_void_p(stream.cuda_stream), ctypes.c_void_p(grads.data_ptr()), None)
 
     if world > 1:
         handle.set_option(_lib.OPT_RESERVED_SMS, args.reserve_sms)
