@@ -187,6 +187,17 @@ def run_reference(args) -> None:
 # ----------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------
+def _bind_to_gpu_numa_node(index: int) -> None:
+    """Pin this process to the CPUs next to its GPU (NVML's ideal affinity), so that the pinned host buffers of the
+    e2e leg are allocated on the GPU's own NUMA node and its H2D copies do not cross the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+    except Exception:
+        pass  # no NVML / no permission: run unbound
+
+
 def run_b200(args) -> None:
     import torch
     import torch.distributed as dist
@@ -205,6 +216,7 @@ def run_b200(args) -> None:
                          "(use --impl reference for the host baseline)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    _bind_to_gpu_numa_node(local_rank)  # before any pinned allocation: first touch decides where the pages live
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -314,6 +326,33 @@ def run_b200(args) -> None:
         ev1.record(stream)
         barrier()
         async_ms = ev0.elapsed_time(ev1) / args.steps
+
+    # ---- the call as the reference's torch binding pays for it (pytorch_binding/monotonic_rnnt.cu:99-111): a new manager,
+    #      cudaMalloc of the workspace, cost_and_grad, cudaFree -- every call ----
+    alloc_ms = None
+    if world == 1:
+        hp = ctypes.c_void_p()
+        Th = np.ascontiguousarray(wl.T, dtype=np.int32); Sh = np.ascontiguousarray(wl.S, dtype=np.int32)
+
+        def alloc_step():
+            _lib.check(lib.mrnnt_create(ctypes.byref(hp), acts.data_ptr(), labels.data_ptr(), wl.B, T.data_ptr(), S.data_ptr(),
+                                        wl.V, Th.ctypes.data, Sh.ctypes.data), "mrnnt_create")
+            _lib.check(lib.mrnnt_create_workspace(hp), "mrnnt_create_workspace")
+            st = lib.mrnnt_cost_and_grad(hp, wl.blank, stream.cuda_stream, costs_host.data_ptr(), grads.data_ptr())
+            lib.mrnnt_free_workspace(hp)
+            lib.mrnnt_destroy(hp)
+            _lib.check(st, "mrnnt_cost_and_grad")
+
+        if wl.alignment is None:
+            for _ in range(3):
+                alloc_step()
+            n_alloc = max(3, min(args.steps, 20))
+            barrier()
+            t_a = time.perf_counter()
+            for _ in range(n_alloc):
+                alloc_step()
+            torch.cuda.synchronize()
+            alloc_ms = 1000.0 * (time.perf_counter() - t_a) / n_alloc
 
     # ---- instrumented pass: per-kernel durations (CUDA events around K1, K2, K3 on the launch stream) -
     handle.set_option(_lib.OPT_TIMING, 1)
@@ -438,6 +477,10 @@ def run_b200(args) -> None:
         "async_enqueue": None if async_ms is None else {
             "value": wl.B / (async_ms / 1000.0), "unit": UNIT, "ms_per_step": async_ms,
             "what": "the same steps through mrnnt_enqueue (no host synchronisation per step, one at the end)"},
+        "per_call_workspace": None if alloc_ms is None else {
+            "value": wl.B / (alloc_ms / 1000.0), "unit": UNIT, "ms_per_step": alloc_ms,
+            "what": "new handle + cudaMalloc of the workspace + set-up kernels + cost_and_grad + cudaFree per call (host clock), "
+                    "the way the reference's torch binding drives its manager"},
         "gpu_launches": 3 * args.steps,
         "clocks": clock_info, "wall_ms_timed_region": wall_ms,
         "cpu_baseline": cpu_baseline, "reference_cuda_same_gpu": ref_cuda, "parity": parity,
