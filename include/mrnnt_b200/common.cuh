@@ -120,12 +120,6 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-
 // 1-D bulk copy global -> shared through the TMA engine; completion is reported as `bytes`
 // transaction units on `bar`.  dst, src and bytes must be multiples of 16.
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
@@ -142,21 +136,6 @@ __device__ __forceinline__ void bulk_g2s_hint(void *dst_smem, const void *src_gm
             "r"(smem_u32(dst_smem)),
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
-}
-
-// ---------------------------------------------------------------------------------------------
-// per-thread cp.async (LDGSTS) used as a private prefetch FIFO by the lattice kernel
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async_16(void *dst_smem, const void *src_gmem) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_8(void *dst_smem, const void *src_gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -218,10 +197,6 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 // ---------------------------------------------------------------------------------------------
 // streaming global stores / loads
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void st_stream_f4(float4 *p, const float4 &v) {
-    asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                 : "memory");
-}
 __device__ __forceinline__ void st_stream_u4(uint4 *p, const uint4 &v) {
     asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                  : "memory");
@@ -234,18 +209,6 @@ __device__ __forceinline__ float ex2_approx(float x) {  // 2^x, MUFU.EX2; ex2(-i
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
-}
-
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
 }
 
 // 2^-k for 0 <= k < 127; exactly 0 for k >= 127 (the scaled term is then either an exact zero or ~2^-100 below

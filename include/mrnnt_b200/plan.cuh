@@ -53,14 +53,6 @@ struct Workspace {
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// K2 prefetches lp[] and band[] up to 8 frames beyond either end of an utterance without bounds checks
-// (k2_lattice.cuh); the two arrays therefore carry this much never-consumed slack on both sides.
-constexpr int kPrefetchFrames = 8;
-inline size_t lp_slack_bytes(const Shape &sh) {
-    return align_up(static_cast<size_t>(kPrefetchFrames) * static_cast<size_t>(sh.width()) * sizeof(RawRow), 256);
-}
-constexpr size_t kBandSlackBytes = 256;  // >= kPrefetchFrames * sizeof(int2)
-
 // Bytes needed for `shape`.  A function of (B, T[], S[]) only, like the reference
 // (gpu_workspace_manager.h:242-247); the value differs (60 B/row + O(B*T_max) instead of 12 B/row).
 inline size_t workspace_bytes(const Shape &sh) {
@@ -68,9 +60,9 @@ inline size_t workspace_bytes(const Shape &sh) {
     const size_t B = static_cast<size_t>(sh.B);
     size_t n = 256;  // slack to align an arbitrarily aligned base pointer
     n += align_up((B + 1) * sizeof(int64_t), 256);
-    n += align_up(B * static_cast<size_t>(sh.T_max) * sizeof(int2), 256) + 2 * kBandSlackBytes;
+    n += align_up(B * static_cast<size_t>(sh.T_max) * sizeof(int2), 256);
     n += 2 * align_up(rows * sizeof(int), 256);
-    n += align_up(rows * sizeof(RawRow), 256) + 2 * lp_slack_bytes(sh);
+    n += align_up(rows * sizeof(RawRow), 256);
     n += align_up(rows * sizeof(Weight), 256);
     n += 2 * align_up(rows * sizeof(Cell), 256);
     n += align_up(rows * sizeof(float4), 256);
@@ -91,14 +83,10 @@ inline Workspace carve_workspace(void *base, const Shape &sh) {
     };
     Workspace w;
     w.row_start = reinterpret_cast<int64_t *>(take((B + 1) * sizeof(int64_t)));
-    take(kBandSlackBytes);
     w.band = reinterpret_cast<int2 *>(take(B * static_cast<size_t>(sh.T_max) * sizeof(int2)));
-    take(kBandSlackBytes);
     w.rowmeta = reinterpret_cast<int *>(take(rows * sizeof(int)));
     w.rowutt = reinterpret_cast<int *>(take(rows * sizeof(int)));
-    take(lp_slack_bytes(sh));
     w.lp = reinterpret_cast<RawRow *>(take(rows * sizeof(RawRow)));
-    take(lp_slack_bytes(sh));
     w.wts = reinterpret_cast<Weight *>(take(rows * sizeof(Weight)));
     w.alpha = reinterpret_cast<Cell *>(take(rows * sizeof(Cell)));
     w.beta = reinterpret_cast<Cell *>(take(rows * sizeof(Cell)));
