@@ -56,11 +56,11 @@ int main(int argc, char **argv) {
     a.T = dT; a.S = dS; a.labels = dl; a.row_start = drs; a.band = dband + 32; a.lp = dlp + slack; a.wts = dw;
     a.alpha = dal; a.beta = dbe; a.coef = dco; a.ll_fwd = dll; a.ll_bwd = dll + B; a.costs = dc; a.costs_mapped = nullptr; a.flags = dfl;
     a.T_max = T; a.S_max = S; a.V = 1000; a.blank = 0;
-    a.chunk_frames = k2_chunk_frames(S);
+    a.chunk_frames = k2_chunk_frames(W);
     const int K = argc > 5 ? atoi(argv[5]) : k2_states_per_lane(W);  // optional: force the states per lane
     a.row_warps = k2_row_warps(W, K);
     a.chunk_bufs = k2_chunk_bufs(a.row_warps);
-    const size_t sm = k2_smem_bytes(S, a.row_warps);
+    const size_t sm = k2_smem_bytes(W, a.row_warps);
     unsigned epoch = 1;
     for (int nb = 0; nb < 2; ++nb) {
         a.need_beta = nb; a.parts = nb ? parts : 1; a.epoch = epoch; epoch += 100;
