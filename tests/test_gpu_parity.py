@@ -419,3 +419,39 @@ def test_bf16_logits(gu, shape):
     scale = np.repeat(w.cpu().numpy().astype(np.float64), rows)[:, None]
     ga = a.grad.to(torch.float32).cpu().numpy().astype(np.float64)
     assert np.all(np.abs(ga - want * scale) <= np.abs(want * scale) * 2.0 ** -7 + GRAD_ATOL * 2)
+
+
+def test_owned_workspace_is_recycled_across_handles(gu):
+    """create_workspace / free_workspace per call, as the reference's torch binding does it: the blocks are recycled
+    (larger, smaller, more handles than cache slots, two alive at once) and every call still gives the oracle's result."""
+    import ctypes
+    import monotonic_rnnt_b200 as mr
+    from monotonic_rnnt_b200 import _lib
+    import gpu_util
+    lib = _lib.load()
+    names = ["rand_v32", "readme", "rand_wide", "multibatch", "rand_v17", "rand_edges", "rand_v32", "rand_wide"]
+    keep = []
+    for round_ in range(2):
+        for name in names:
+            case, ref = golden_io.load(name)
+            acts = gpu_util.to_dev(case.acts, torch.float32)
+            labels = gpu_util.to_dev(case.labels, torch.int32)
+            T = gpu_util.to_dev(case.T, torch.int32); S = gpu_util.to_dev(case.S, torch.int32)
+            h = ctypes.c_void_p()
+            _lib.check(lib.mrnnt_create(ctypes.byref(h), acts.data_ptr(), labels.data_ptr(), case.B, T.data_ptr(),
+                                        S.data_ptr(), case.V, None, None), "create")
+            _lib.check(lib.mrnnt_create_workspace(h), "create_workspace")
+            grads = torch.full_like(acts, float("nan"))
+            costs = torch.empty(case.B, dtype=torch.float32)
+            _lib.check(lib.mrnnt_cost_and_grad(h, case.blank, torch.cuda.current_stream().cuda_stream, costs.data_ptr(),
+                                               grads.data_ptr()), "cost_and_grad")
+            np.testing.assert_allclose(costs.numpy(), ref["costs_f64"], rtol=COST_RTOL)
+            assert np.abs(grads.cpu().numpy() - ref["grads_f64"]).max() <= GRAD_ATOL
+            keep.append((h, acts, labels, T, S))
+            if len(keep) > 2:                      # two handles stay alive: their blocks must not be handed out
+                old = keep.pop(0)
+                lib.mrnnt_free_workspace(old[0])
+                lib.mrnnt_destroy(old[0])
+    for old in keep:
+        lib.mrnnt_free_workspace(old[0])
+        lib.mrnnt_destroy(old[0])
