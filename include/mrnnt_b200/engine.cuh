@@ -124,6 +124,16 @@ inline void release_cost_stage(const CostStage &st) {
     g_cost_stages.push_back(st);
 }
 
+// T[] and S[] in one hop: a tiny kernel writes both into a host-mapped staging buffer (one launch + one
+// synchronisation of the legacy stream, ~8 us) instead of two blocking cudaMemcpy calls (~16 us).
+static __global__ void gather_lengths_kernel(const int *__restrict__ T, const int *__restrict__ S, int B,
+                                             int *__restrict__ out) {
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+        out[b] = T[b];
+        out[B + b] = S[b];
+    }
+}
+
 // Device blocks handed back by free_workspace() are kept for the next create_workspace() of this module instead of
 // going through cudaFree / cudaMalloc: the reference's torch binding creates and frees the workspace on every loss
 // call (pytorch_binding/monotonic_rnnt.cu:99-111), and the driver's allocator costs milliseconds for blocks of this
@@ -257,8 +267,21 @@ class Engine {
         }
         T_h_.resize(B_);
         S_h_.resize(B_);
-        if (cudaMemcpy(T_h_.data(), T_dev_, sizeof(int) * B_, cudaMemcpyDeviceToHost) != cudaSuccess ||
-            cudaMemcpy(S_h_.data(), S_dev_, sizeof(int) * B_, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        bool fetched = false;
+        const CostStage stage = acquire_cost_stage(2 * static_cast<size_t>(B_));
+        if (stage.host != nullptr) {
+            // on the legacy default stream, like the reference's blocking copies (gpu_workspace_manager.h:87-95)
+            int *mapped = reinterpret_cast<int *>(stage.host);
+            gather_lengths_kernel<<<(B_ + 255) / 256, 256>>>(T_dev_, S_dev_, B_, mapped);
+            if (cudaGetLastError() == cudaSuccess && cudaStreamSynchronize(nullptr) == cudaSuccess) {
+                std::memcpy(T_h_.data(), mapped, sizeof(int) * B_);
+                std::memcpy(S_h_.data(), mapped + B_, sizeof(int) * B_);
+                fetched = true;
+            }
+            release_cost_stage(stage);
+        }
+        if (!fetched && (cudaMemcpy(T_h_.data(), T_dev_, sizeof(int) * B_, cudaMemcpyDeviceToHost) != cudaSuccess ||
+                         cudaMemcpy(S_h_.data(), S_dev_, sizeof(int) * B_, cudaMemcpyDeviceToHost) != cudaSuccess)) {
             have_shape_ = true;
             return shape_status_ = RNNT_STATUS_MEMOPS_FAILED;
         }
