@@ -373,7 +373,7 @@ class Engine {
 
     // Launch everything on `stream` without synchronising; costs stay in workspace().costs.
     RNNTStatus enqueue(int blank, cudaStream_t stream, void *grads_dev) {
-        RNNTStatus st = enqueue_forward(blank, stream, grads_dev != nullptr);
+        RNNTStatus st = enqueue_forward(blank, stream, grads_dev != nullptr, grads_dev);
         if (st != RNNT_STATUS_SUCCESS || grads_dev == nullptr) return st;
         k3_follows_k2_ = !timing_;  // (the timing events between the kernels would break the dependent launch)
         st = enqueue_backward(stream, grads_dev, nullptr);
@@ -385,10 +385,14 @@ class Engine {
     // coefficients in the workspace, and enqueue_backward() may follow at any later time (same or another
     // stream-ordered point) as long as acts and the workspace are untouched: a training framework calls this
     // from its forward pass and enqueue_backward() from its backward pass.
-    RNNTStatus enqueue_forward(int blank, cudaStream_t stream, bool want_grads) {
+    // zero_dst (enqueue() only): the gradient buffer the backward half is about to fill; the lattice kernel writes
+    // its zero rows while the recursions leave the memory system idle.
+    RNNTStatus enqueue_forward(int blank, cudaStream_t stream, bool want_grads, void *zero_dst = nullptr) {
         const DeviceInfo &dev = device_info();
         if (!dev.ok) return RNNT_STATUS_EXECUTION_FAILED;
         coef_blank_ = -1;
+        zero_dst_ = want_grads ? zero_dst : nullptr;
+        dead_rows_zeroed_ = nullptr;
         RNNTStatus st = setup(stream);
         if (st != RNNT_STATUS_SUCCESS) return st;
         mark(0, stream);
@@ -410,6 +414,8 @@ class Engine {
         const DeviceInfo &dev = device_info();
         if (!dev.ok) return RNNT_STATUS_EXECUTION_FAILED;
         if (grads_dev == nullptr || coef_blank_ < 0) return RNNT_STATUS_INVALID_VALUE;
+        k3_write_dead_ = dead_rows_zeroed_ != grads_dev;
+        dead_rows_zeroed_ = nullptr;  // (good for the one backward pass that follows directly)
         mark(2, stream);
         const RNNTStatus st = launch_k3(coef_blank_, stream, dev, grads_dev, scale_dev);
         mark(3, stream);
@@ -447,6 +453,7 @@ class Engine {
     void set_k1_compact(int mode) { k1_compact_ = mode < 0 ? -1 : (mode != 0); }
     // SMs the gradient kernel leaves free for a concurrent collective (0: none).
     void set_reserved_sms(int n) { reserved_sms_ = n < 0 ? 0 : n; }
+    void set_k2_zero_fill(int warps) { k2_zero_warps_ = warps; }
     // Upper limit for the CTAs per utterance of the lattice kernel's coefficient phase (0: automatic).
     void set_k2_parts(int parts) { k2_parts_ = parts < 0 ? 0 : parts; }
     // Consumer warps per CTA of the streaming kernels (8 or 16); tuning knob for the bench.
@@ -587,7 +594,11 @@ class Engine {
             const int fit = k2_occ_ * dev.sm_count / B_;
             if (args.parts > fit) args.parts = fit < 1 ? 1 : fit;
         }
-        if (launch_kernel(kern, B_ * args.parts, kK2Threads, smem, stream, pdl_ && !timing_, args) != cudaSuccess)
+        args.phase_ctas = B_ * args.parts;
+
+        // with the zero fill: one CTA on every SM, the ones behind the utterances' CTAs only fill
+        const int grid = args.zero_warps > 0 && args.phase_ctas < dev.sm_count ? dev.sm_count : args.phase_ctas;
+        if (launch_kernel(kern, grid, kK2Threads, smem, stream, pdl_ && !timing_, args) != cudaSuccess)
             return RNNT_STATUS_EXECUTION_FAILED;
         return launched();
     }
@@ -612,9 +623,27 @@ class Engine {
         a.epoch = epoch_;
         const int states = shape_.S_max + 1;
         const int K = k2_states_per_lane(states);
+        a.zero_dst = nullptr;
+        a.rowmeta = ws_.rowmeta;
+        a.row_bytes = static_cast<unsigned>(static_cast<size_t>(V_) * elem_bytes());
+        a.zero_warps = 0;
+        a.rows = shape_.rows;
+        a.B = B_;
+        a.phase_ctas = 0;
         if (K > 0) {
             a.row_warps = k2_row_warps(states, K);
             a.chunk_bufs = k2_chunk_bufs(a.row_warps);
+            // the zero fill needs bulk-copy granularity (16 bytes) and whole warps next to the chain warps and
+            // their chunk issuers
+            const int spare = kK2Warps - 1 - 2 * (a.row_warps + 1);
+            int zw = k2_zero_warps_ < 0 ? (zero_fill_pays() ? 2 : 0) : k2_zero_warps_;
+            if (zw > spare) zw = spare;
+            if (need_beta && zero_dst_ != nullptr && zw > 0 && a.row_bytes % 16 == 0 &&
+                reinterpret_cast<uintptr_t>(zero_dst_) % 16 == 0 && static_cast<size_t>(V_) * elem_bytes() < (1ull << 31)) {
+                a.zero_dst = static_cast<unsigned char *>(zero_dst_);
+                a.zero_warps = zw;
+                dead_rows_zeroed_ = zero_dst_;
+            }
             return K == 1   ? launch_k2_warp<1>(a, stream, dev)
                    : K == 2 ? launch_k2_warp<2>(a, stream, dev)
                             : launch_k2_warp<4>(a, stream, dev);
@@ -629,6 +658,25 @@ class Engine {
         return launched();
     }
 
+    // Zero fill inside the lattice kernel (automatic choice).  What it wins is the duration of the recursions, during
+    // which the memory system would idle (~0.17 us per frame); moving the zero rows out of the gradient kernel is
+    // otherwise neutral at best (there they are written in the shadow of the live rows' arithmetic).  So: where many
+    // rows are dead (alignment band, padded tensor: the gradient kernel then also skips whole tiles), and where the
+    // recursions are a visible share of the call.  Measured (tools/kernel_times.py --zero 0,2): c2 -3 %, c3 -4 %,
+    // c5 -12 %, c4 +1.5 % (off there).
+    bool zero_fill_pays() const {
+        if (alignment_ != nullptr || shape_.U > 0) return true;
+        const double chain_us = 0.17 * shape_.T_max;
+        const double stream_us = 3.0 * static_cast<double>(shape_.rows) * V_ * static_cast<double>(elem_bytes()) / 6.5e6;
+        return chain_us >= 0.025 * stream_us;
+    }
+
+    // (dead tiles are skipped under the same conditions as in K1, and only when nobody has to zero them here)
+    int k3_flags(const StreamTiling &tl) const {
+        if (k3_write_dead_) return kK3WriteDead;
+        return k1_compact(tl) ? kK3Compact : 0;
+    }
+
     template <typename E, int NW, bool SCALED>
     RNNTStatus launch_k3_tma(int blank, cudaStream_t stream, const DeviceInfo &dev, const StreamTiling &tl, void *grads,
                              const float *scale) {
@@ -641,7 +689,7 @@ class Engine {
         // predecessor to wait for, and an ordinary launch orders it behind whatever precedes it in the stream)
         if (launch_kernel(kern, grid, (NW + 1) * kWarp, tl.smem_bytes, stream, pdl_ && k3_follows_k2_,
                           static_cast<const E *>(acts_), ws_.coef, static_cast<E *>(grads), shape_.rows, V_, blank, tl.G,
-                          tl.stages, ws_.rowutt, scale, cost_mirror()) != cudaSuccess)
+                          tl.stages, ws_.rowutt, scale, cost_mirror(), k3_flags(tl)) != cudaSuccess)
             return RNNT_STATUS_EXECUTION_FAILED;
         return launched();
     }
@@ -714,6 +762,10 @@ class Engine {
     const void *k2_occ_kernel_ = nullptr;
     int reserved_sms_ = 0;
     bool pdl_ = true;             // programmatic dependent launch of K2 behind K1 and of K3 behind K2
+    void *zero_dst_ = nullptr;          // enqueue(): gradient buffer handed to the lattice kernel's zero fill
+    void *dead_rows_zeroed_ = nullptr;  // the buffer whose dead rows the last lattice kernel zeroed (nullptr: none)
+    bool k3_write_dead_ = true;         // the gradient kernel writes the zero rows itself
+    int k2_zero_warps_ = -1;            // warps per lattice CTA for the zero fill: -1 automatic, 0 off
     bool k3_follows_k2_ = false;  // K3 is being enqueued directly behind K2 (enqueue(), not a separate backward)
     unsigned epoch_ = 0u;  // launch counter published through Workspace::k2_flags
     float *costs_mapped_ = nullptr;  // set for the duration of a synchronous compute(): host-mapped copy of the costs

@@ -86,12 +86,17 @@ static __global__ void __launch_bounds__(kGenericWarps * kWarp)
 // ---------------------------------------------------------------------------------------------
 // TMA-staged variant.  Requirements: rows are whole 16-byte vectors, acts and grads 16-byte aligned.
 // Shared memory: [stages][G*V] elements | full[stages] | empty[stages] | scale[stages][32] floats | coef[stages][32] float4
+// | tile[stages] ints
 // ---------------------------------------------------------------------------------------------
+// flags
+constexpr int kK3WriteDead = 1;  // write the zero rows (off: the lattice kernel has zeroed the rows the plan calls dead)
+constexpr int kK3Compact = 2;    // tiles without a live row take no ring slot (needs kK3WriteDead off)
+
 template <typename E, int NW, bool SCALED>
 static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
     k3_grad_tma_kernel(const E *__restrict__ acts, const float4 *__restrict__ coef, E *__restrict__ grads,
                        int64_t rows, int V, int blank, int G, int stages, const int *__restrict__ rowutt,
-                       const float *__restrict__ scale, CostMirror mirror) {
+                       const float *__restrict__ scale, CostMirror mirror, int flags) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NE = Elem<E>::kPerVec;
     const size_t tile_elems = static_cast<size_t>(G) * V;
@@ -101,6 +106,7 @@ static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
     float *scale_sh = reinterpret_cast<float *>(empty + stages);
     float4 *coef_sh = reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(empty + stages) +
                                                  static_cast<size_t>(stages) * 32 * sizeof(float));
+    int *tile_sh = reinterpret_cast<int *>(coef_sh + static_cast<size_t>(stages) * 32);  // [stages] tile held by the slot
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -116,34 +122,22 @@ static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
 
     const int64_t ntiles = (rows + G - 1) / G;
     const int64_t nloc = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const bool write_dead = (flags & kK3WriteDead) != 0;
+    // compact (only without write_dead): tiles without a live row take no ring slot; the slots carry their tile's
+    // index, the consumers walk the slots and stop at a terminator (as in the LSE kernel's COMPACT variant)
+    const bool compact = (flags & kK3Compact) != 0;
 
     if (warp == NW) {
         // ---------------- producer warp ----------------
         const uint64_t policy = l2_policy_evict_first();
-        auto load_coef = [&](int64_t k) {
-            const int64_t row = (blockIdx.x + k * gridDim.x) * G + lane;
-            return (k < nloc && lane < G && row < rows) ? __ldg(coef + row) : make_float4(kNegInfF, 0.f, 0.f, 0.f);
-        };
-        auto load_scale = [&](int64_t k) {
-            const int64_t row = (blockIdx.x + k * gridDim.x) * G + lane;
-            return (SCALED && k < nloc && lane < G && row < rows) ? __ldg(scale + __ldg(rowutt + row)) : 1.0f;
-        };
-        float4 c_next = load_coef(0), c_next2 = load_coef(1);
-        float s_next = load_scale(0), s_next2 = load_scale(1);
         int stage = 0;
         uint32_t phase = 0;
-        for (int64_t k = 0; k < nloc; ++k) {
-            const float4 c = c_next;
-            const float sc = s_next;
-            c_next = c_next2;  // two tiles ahead: the latency hides behind two tiles' waits
-            s_next = s_next2;
-            c_next2 = load_coef(k + 2);
-            s_next2 = load_scale(k + 2);
+        auto fill_slot = [&](int64_t k, const float4 &c, float sc, uint32_t mask) {
             const int64_t row0 = (blockIdx.x + k * gridDim.x) * G;
-            const uint32_t mask = __ballot_sync(0xffffffffu, !(c.x == kNegInfF));
             mbar_wait(empty + stage, phase ^ 1u);
             coef_sh[stage * 32 + lane] = c;
             if (SCALED) scale_sh[stage * 32 + lane] = sc;
+            if (lane == 0) tile_sh[stage] = static_cast<int>(k);
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive_expect_tx(full + stage, static_cast<uint32_t>(__popc(mask)) * static_cast<uint32_t>(V) *
@@ -154,24 +148,105 @@ static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
                 stage = 0;
                 phase ^= 1u;
             }
+        };
+        if (!compact) {
+            auto load_coef = [&](int64_t k) {
+                const int64_t row = (blockIdx.x + k * gridDim.x) * G + lane;
+                return (k < nloc && lane < G && row < rows) ? __ldg(coef + row) : make_float4(kNegInfF, 0.f, 0.f, 0.f);
+            };
+            auto load_scale = [&](int64_t k) {
+                const int64_t row = (blockIdx.x + k * gridDim.x) * G + lane;
+                return (SCALED && k < nloc && lane < G && row < rows) ? __ldg(scale + __ldg(rowutt + row)) : 1.0f;
+            };
+            float4 c_next = load_coef(0), c_next2 = load_coef(1);
+            float s_next = load_scale(0), s_next2 = load_scale(1);
+            for (int64_t k = 0; k < nloc; ++k) {
+                const float4 c = c_next;
+                const float sc = s_next;
+                c_next = c_next2;  // two tiles ahead: the latency hides behind two tiles' waits
+                s_next = s_next2;
+                c_next2 = load_coef(k + 2);
+                s_next2 = load_scale(k + 2);
+                fill_slot(k, c, sc, __ballot_sync(0xffffffffu, !(c.x == kNegInfF)));
+            }
+        } else {
+            // coefficients for 32/G tiles per load (lane l: tile k0 + l/G, row l%G), two such batches ahead: with
+            // mostly dead tiles the producer does nothing but wait for these loads
+            const int TPB = 32 / G;  // (G is a power of two <= 32)
+            const uint32_t gmask = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
+            auto batch_row = [&](int64_t k0) {
+                const int64_t kk = k0 + lane / G;
+                const int64_t row = (blockIdx.x + kk * gridDim.x) * G + (lane % G);
+                return (kk < nloc && row < rows) ? row : static_cast<int64_t>(-1);
+            };
+            auto load_coef = [&](int64_t k0) {
+                const int64_t row = batch_row(k0);
+                return row >= 0 ? __ldg(coef + row) : make_float4(kNegInfF, 0.f, 0.f, 0.f);
+            };
+            auto load_scale = [&](int64_t k0) {
+                const int64_t row = batch_row(k0);
+                return (SCALED && row >= 0) ? __ldg(scale + __ldg(rowutt + row)) : 1.0f;
+            };
+            float4 cb0 = load_coef(0), cb1 = load_coef(TPB);
+            float sb0 = load_scale(0), sb1 = load_scale(TPB);
+            for (int64_t k0 = 0; k0 < nloc; k0 += TPB) {
+                const float4 cb = cb0;
+                const float sb = sb0;
+                cb0 = cb1;
+                sb0 = sb1;
+                cb1 = load_coef(k0 + 2 * TPB);
+                sb1 = load_scale(k0 + 2 * TPB);
+                const uint32_t ball = __ballot_sync(0xffffffffu, !(cb.x == kNegInfF));
+                for (int j = 0; j < TPB && k0 + j < nloc; ++j) {
+                    const uint32_t mask = (ball >> (j * G)) & gmask;
+                    if (mask == 0u) continue;
+                    const int src = j * G + (lane % G);
+                    float4 c;
+                    c.x = __shfl_sync(0xffffffffu, cb.x, src);
+                    c.y = __shfl_sync(0xffffffffu, cb.y, src);
+                    c.z = __shfl_sync(0xffffffffu, cb.z, src);
+                    c.w = __shfl_sync(0xffffffffu, cb.w, src);
+                    const float sc = SCALED ? __shfl_sync(0xffffffffu, sb, src) : 1.0f;
+                    if (lane >= G) c.x = kNegInfF;
+                    fill_slot(k0 + j, c, sc, mask);
+                }
+            }
+            // one terminator per slot: every consumer warp meets one within its next `stages` slot uses
+            for (int i = 0; i < stages; ++i) {
+                mbar_wait(empty + stage, phase ^ 1u);
+                if (lane == 0) {
+                    tile_sh[stage] = -1;
+                    mbar_arrive_expect_tx(full + stage, 0u);
+                }
+                if (++stage == stages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
         }
     } else {
         // ---------------- consumer warps ----------------
+        // q walks the rows of the slot uses u = 0, 1, ... in order (G rows each)
         const int NV = V / NE;
         const int64_t nq = nloc * G;
-        for (int64_t q = warp; q < nq; q += NW) {
-            const int64_t k = q / G;
-            const int r = static_cast<int>(q - k * G);
-            const int stage = static_cast<int>(k % stages);
-            const uint32_t phase = static_cast<uint32_t>((k / stages) & 1);
-            const int64_t row = (blockIdx.x + k * gridDim.x) * G + r;
+        for (int64_t q = warp; compact || q < nq; q += NW) {
+            const int64_t u = q / G;
+            const int r = static_cast<int>(q - u * G);
+            const int stage = static_cast<int>(u % stages);
+            const uint32_t phase = static_cast<uint32_t>((u / stages) & 1);
             mbar_wait(full + stage, phase);
+            const int64_t k = compact ? tile_sh[stage] : u;
+            if (k < 0) break;
+            const int64_t row = (blockIdx.x + k * gridDim.x) * G + r;
             if (row < rows) {
                 const float4 c = coef_sh[stage * 32 + r];
                 uint4 *gv = reinterpret_cast<uint4 *>(grads + row * V);
                 if (c.x == kNegInfF) {
+                    // a zero row; without write_dead the lattice kernel has already zeroed the rows the plan calls dead
+                    // (k2_zero_dead_rows) and marked them in the label slot
                     const uint4 z = make_uint4(0u, 0u, 0u, 0u);  // +0.0 in either element type
-                    for (int j = lane; j < NV; j += kWarp) st_stream_u4(gv + j, z);
+                    if (write_dead || __float_as_int(c.w) != kRowDead)
+                        for (int j = lane; j < NV; j += kWarp) st_stream_u4(gv + j, z);
                 } else {
                     const uint4 *xv = reinterpret_cast<const uint4 *>(tiles + stage * tile_elems +
                                                                       static_cast<size_t>(r) * V);

@@ -98,7 +98,10 @@ enum {
     MRNNT_OPT_K2_PARTS = 5,      /* upper limit of CTAs per utterance in K2's coefficient phase (0: auto) */
     MRNNT_OPT_RESERVED_SMS = 6,  /* SMs the gradient kernel leaves free for a concurrent collective (0)    */
     MRNNT_OPT_PDL = 7,           /* programmatic dependent launch of K2 behind K1 and K3 behind K2 (1)     */
-    MRNNT_OPT_K1_COMPACT = 8     /* K1 variant that gives dead tiles no ring slot: 1 / 0 forced, -1 automatic */
+    MRNNT_OPT_K1_COMPACT = 8,    /* K1 variant that gives dead tiles no ring slot: 1 / 0 forced, -1 automatic */
+    MRNNT_OPT_K2_ZERO_FILL = 9,  /* warps per lattice CTA that zero the gradient's dead rows while the recursions
+                                    run: 0 off (the gradient kernel writes them), 1..4, -1 automatic        */
+    MRNNT_OPT_K2_ZERO_FIRST_PART = 10 /* parts of an utterance below this one take no share of the zero fill (0) */
 };
 RNNTStatus mrnnt_set_option(mrnnt_handle_t h, int option, int value);
 /* Durations in ms of K1, K2, K3 of the last call (MRNNT_OPT_TIMING on, stream synchronised). */

@@ -227,6 +227,9 @@ RNNTStatus mrnnt_set_option(mrnnt_handle_t h, int option, int value) {
         case MRNNT_OPT_K2_PARTS:
             h->manager.engine().set_k2_parts(value);
             return RNNT_STATUS_SUCCESS;
+        case MRNNT_OPT_K2_ZERO_FILL:
+            h->manager.engine().set_k2_zero_fill(value);
+            return RNNT_STATUS_SUCCESS;
         default:
             return RNNT_STATUS_INVALID_VALUE;
     }

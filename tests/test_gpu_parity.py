@@ -151,6 +151,32 @@ def test_random_shapes(gu, shape, restricted):
     assert np.abs(g.grads - o64.grads).max() <= GRAD_ATOL
 
 
+@pytest.mark.parametrize("V", [16, 1000], ids=["generic_v16", "stream_v1000"])
+def test_masked_logits_leave_zero_rows_inside_the_lattice(gu, V):
+    """Logits of -inf (a masked vocabulary entry) make whole rows INSIDE the lattice come out as exact zeros: the first
+    label may only be emitted in frame 0, so beta(t, 0) = 0 for t >= 1.  Those rows are not the plan's dead rows (which
+    the lattice kernel zeroes); the gradient kernel has to write them."""
+    case = fixtures.random_case("masked", 77, B=3, V=V, T_range=(12, 20), S_range=(2, 5), dist="uniform")
+    acts = case.acts.copy()
+    row = 0
+    for b in range(len(case.T)):
+        Tb, Sb = int(case.T[b]), int(case.S[b])
+        lab0 = int(case.labels[b, 0])
+        if lab0 != case.blank:
+            for t in range(1, Tb):
+                acts[row + t * (Sb + 1), lab0] = -np.inf
+        row += Tb * (Sb + 1)
+    case = fixtures.Case("masked", acts, case.labels, case.T, case.S, case.V, case.blank)
+    o64 = _oracle(case, "f64_from_f32")
+    assert np.isfinite(o64.costs).all()
+    zero_rows = np.where((o64.grads == 0).all(axis=1))[0]
+    r = gu.run_case(case)
+    _check_costs(r.costs, o64.costs)
+    assert not np.isnan(r.grads).any(), "a row of grads was not written"
+    assert np.abs(r.grads - o64.grads).max() <= GRAD_ATOL
+    assert (r.grads[zero_rows] == 0).all()
+
+
 def test_device_lengths_fetch_and_repeated_restrict(gu):
     """One manager reused across restrict_to_alignment + cost calls (tests/test_cpu.cpp:412-430), lengths
     fetched from the device (no host copies given)."""
