@@ -264,7 +264,7 @@ def run_b200(args) -> None:
         # which the gradients are complete and the per-utterance costs and the global sum are on the host.
         st = fwd_call(*fwd_args)                       # K1, K2
         if st != 0:
-            _lib.check(st, "mrnnt_enqueue_forward")
+            _lib.check(st, "mrnnt_enqueue_forward_into")
         k2_done.record(stream)
         st = bwd_call(*bwd_args)                       # K3 (compute stream)
         if st != 0:
@@ -281,8 +281,9 @@ def run_b200(args) -> None:
     side = torch.cuda.Stream(device=dev) if world > 1 else None
     k2_done = torch.cuda.Event() if world > 1 else None
     dev_costs = handle.device_costs()
-    fwd_call, bwd_call = lib.mrnnt_enqueue_forward, lib.mrnnt_enqueue_backward
-    fwd_args = (handle._h, ctypes.c_int(wl.blank), ctypes.c_void_p(stream.cuda_stream), ctypes.c_int(1))
+    # (the forward half is told which buffer the backward half will fill: the lattice kernel zeroes its dead rows)
+    fwd_call, bwd_call = lib.mrnnt_enqueue_forward_into, lib.mrnnt_enqueue_backward
+    fwd_args = (handle._h, ctypes.c_int(wl.blank), ctypes.c_void_p(stream.cuda_stream), ctypes.c_void_p(grads.data_ptr()))
     bwd_args = (handle._h, ctypes.c_void_p(stream.cuda_stream), ctypes.c_void_p(grads.data_ptr()), None)
 
     if world > 1:
@@ -367,6 +368,10 @@ def run_b200(args) -> None:
         clocks.pause()
     handle.set_option(_lib.OPT_TIMING, 0)
     k_ms = acc / args.steps
+    # who writes the gradient's zero rows (rows whose alpha(t-1, s) lies outside the lattice): the lattice kernel,
+    # while its recursions run, or the gradient kernel.  The roofline below charges each kernel with what it moves.
+    zero_fill_warps = handle.get_option(_lib.OPT_K2_ZERO_FILL)
+    dead_rows = int((handle.debug(_lib.DBG_ROWMETA) == -2).sum())
     costs_gpu = costs_host.clone().numpy()
 
     # ---- e2e: host buffers, copies inside the timed region --------------------------------------------
@@ -456,7 +461,10 @@ def run_b200(args) -> None:
         return
 
     peak, peak_src = _peaks()
-    k3_bytes = 2 * 4 * n  # K3 algorithmic bytes per launch: read logits once + write gradients once
+    # K3 algorithmic bytes per launch: read the logits once + write the gradients once, less the zero rows the
+    # lattice kernel has already written when its zero fill is on (those are charged to K2 below)
+    zero_bytes_in_k2 = 4 * dead_rows * wl.V if zero_fill_warps > 0 else 0
+    k3_bytes = 2 * 4 * n - zero_bytes_in_k2
     k3_gbs = k3_bytes / (k_ms[2] * 1e-3) / 1e9
     call_gbs = wl.algorithmic_bytes / (ms_per_step * 1e-3) / 1e9
     line = {
@@ -465,7 +473,9 @@ def run_b200(args) -> None:
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": _config(wl),
         "roofline": {"kernel": "k3_grad_tma_kernel", "bound": "hbm", "achieved": k3_gbs, "peak": peak, "unit": "GB/s",
                      "frac": k3_gbs / peak, "traffic": _traffic("k3_grad_tma_kernel"), "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": k3_bytes, "ms_per_launch": float(k_ms[2])},
+                     "algorithmic_bytes_per_launch": k3_bytes, "ms_per_launch": float(k_ms[2]),
+                     "zero_rows_written_by_k2_bytes": zero_bytes_in_k2, "k2_zero_fill_warps": zero_fill_warps,
+                     "dead_rows": dead_rows},
         "kernels_ms": {"k1_lse_gather": float(k_ms[0]), "k2_lattice": float(k_ms[1]), "k3_grad": float(k_ms[2]),
                        "sum": float(k_ms.sum()), "k1_GBps_of_4N": 4 * n / (k_ms[0] * 1e-3) / 1e9},
         "call_roofline": {"algorithmic_bytes": wl.algorithmic_bytes, "achieved_GBps": call_gbs,

@@ -453,6 +453,7 @@ class Engine {
     void set_k1_compact(int mode) { k1_compact_ = mode < 0 ? -1 : (mode != 0); }
     // SMs the gradient kernel leaves free for a concurrent collective (0: none).
     void set_reserved_sms(int n) { reserved_sms_ = n < 0 ? 0 : n; }
+    int last_k2_zero_warps() const { return last_k2_zero_warps_; }
     void set_k2_zero_fill(int warps) { k2_zero_warps_ = warps; }
     // Upper limit for the CTAs per utterance of the lattice kernel's coefficient phase (0: automatic).
     void set_k2_parts(int parts) { k2_parts_ = parts < 0 ? 0 : parts; }
@@ -627,6 +628,7 @@ class Engine {
         a.rowmeta = ws_.rowmeta;
         a.row_bytes = static_cast<unsigned>(static_cast<size_t>(V_) * elem_bytes());
         a.zero_warps = 0;
+        last_k2_zero_warps_ = 0;
         a.rows = shape_.rows;
         a.B = B_;
         a.phase_ctas = 0;
@@ -642,6 +644,7 @@ class Engine {
                 reinterpret_cast<uintptr_t>(zero_dst_) % 16 == 0 && static_cast<size_t>(V_) * elem_bytes() < (1ull << 31)) {
                 a.zero_dst = static_cast<unsigned char *>(zero_dst_);
                 a.zero_warps = zw;
+                last_k2_zero_warps_ = zw;
                 dead_rows_zeroed_ = zero_dst_;
             }
             return K == 1   ? launch_k2_warp<1>(a, stream, dev)
@@ -765,6 +768,7 @@ class Engine {
     void *zero_dst_ = nullptr;          // enqueue(): gradient buffer handed to the lattice kernel's zero fill
     void *dead_rows_zeroed_ = nullptr;  // the buffer whose dead rows the last lattice kernel zeroed (nullptr: none)
     bool k3_write_dead_ = true;         // the gradient kernel writes the zero rows itself
+    int last_k2_zero_warps_ = 0;        // what the last lattice launch ran with
     int k2_zero_warps_ = -1;            // warps per lattice CTA for the zero fill: -1 automatic, 0 off
     bool k3_follows_k2_ = false;  // K3 is being enqueued directly behind K2 (enqueue(), not a separate backward)
     unsigned epoch_ = 0u;  // launch counter published through Workspace::k2_flags

@@ -99,7 +99,7 @@ struct K2Args {
     unsigned row_bytes;       // V * sizeof(element), a multiple of 16
     int zero_warps;           // 0: off
     int64_t rows;             // rows of the whole batch (= row_start[B])
-    int B;                    // utterances; flags[2B], flags[2B+1]: the zero fill's counters
+    int B;                    // utterances; flags[k2_zero_ctr_word(B)...]: the zero fill's two counters
     int phase_ctas;           // B * parts; CTAs behind them (zero fill only) do nothing else
 };
 
@@ -588,7 +588,7 @@ __device__ __forceinline__ void k2_zero_dead_rows(const K2Args &a, int fw, int n
     __syncwarp();
     const int64_t rows = a.rows;
     const int *meta = a.rowmeta;
-    unsigned *ctr = a.flags + 2 * a.B;
+    unsigned *ctr = a.flags + k2_zero_ctr_word(a.B);
     const int64_t nunits = (rows + kWarp - 1) / kWarp;
     auto grab = [&]() { return lane == 0 ? atomicAdd(ctr, 1u) : 0u; };  // (the value is only looked at two units later)
     auto unit_of = [&](unsigned raw) { return static_cast<int64_t>(__shfl_sync(0xffffffffu, raw, 0)) + 2 * nfw; };
@@ -682,7 +682,9 @@ static __global__ void __launch_bounds__(kK2Threads) k2_lattice_kernel(K2Args a)
     unsigned *done = arrived + 1;         // epoch of the last finished recursion
     if (warp < zw) {
         // ---- zero fill: this warp's share of the batch's dead rows, nothing else (and nothing K1 wrote) ----
+        if (warp == 0) MRNNT_K2_STAMP(53);
         k2_zero_dead_rows(a, blockIdx.x * zw + warp, gridDim.x * zw, k2_smem + k2_zero_offset(dir_bytes));
+        if (warp == 0) MRNNT_K2_STAMP(54);
         return;
     }
     const int nphase = kK2Threads - zw * kWarp;

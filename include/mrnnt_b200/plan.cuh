@@ -48,14 +48,18 @@ struct Workspace {
     double *ll_fwd = nullptr;      // [B]     alpha(T-1, S)
     double *ll_bwd = nullptr;      // [B]     beta(0, 0)  (diagnostic, as in the reference)
     float *costs = nullptr;        // [B]     -ll_fwd
-    unsigned *k2_flags = nullptr;  // [2B+2]  per utterance: phase-A arrivals, epoch of the last recursion; then the
-                                   //         zero fill's two counters (k2_lattice.cuh)
+    unsigned *k2_flags = nullptr;  // [k2_flag_words(B)] per utterance: phase-A arrivals, epoch of the last recursion;
+                                   //         then, in a cache line of their own, the zero fill's two counters
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Bytes needed for `shape`.  A function of (B, T[], S[]) only, like the reference
 // (gpu_workspace_manager.h:242-247); the value differs (60 B/row + O(B*T_max) instead of 12 B/row).
+// words of Workspace::k2_flags: 2 per utterance, then (256 bytes clear of the flags that waiting CTAs poll) the two
+// counters of the lattice kernel's zero fill
+__host__ __device__ inline size_t k2_zero_ctr_word(int B) { return (2 * static_cast<size_t>(B) + 63) / 64 * 64 + 64; }
+__host__ __device__ inline size_t k2_flag_words(int B) { return k2_zero_ctr_word(B) + 2; }
 inline size_t workspace_bytes(const Shape &sh) {
     const size_t rows = static_cast<size_t>(sh.rows);
     const size_t B = static_cast<size_t>(sh.B);
@@ -69,7 +73,7 @@ inline size_t workspace_bytes(const Shape &sh) {
     n += align_up(rows * sizeof(float4), 256);
     n += 2 * align_up(B * sizeof(double), 256);
     n += align_up(B * sizeof(float), 256);
-    n += align_up((2 * B + 2) * sizeof(unsigned), 256);
+    n += align_up(k2_flag_words(sh.B) * sizeof(unsigned), 256);
     return n;
 }
 
@@ -95,7 +99,7 @@ inline Workspace carve_workspace(void *base, const Shape &sh) {
     w.ll_fwd = reinterpret_cast<double *>(take(B * sizeof(double)));
     w.ll_bwd = reinterpret_cast<double *>(take(B * sizeof(double)));
     w.costs = reinterpret_cast<float *>(take(B * sizeof(float)));
-    w.k2_flags = reinterpret_cast<unsigned *>(take((2 * B + 2) * sizeof(unsigned)));
+    w.k2_flags = reinterpret_cast<unsigned *>(take(k2_flag_words(sh.B) * sizeof(unsigned)));
     return w;
 }
 
@@ -115,7 +119,7 @@ static __global__ void __launch_bounds__(kPlanThreads) plan_row_start_kernel(con
     const int tid = threadIdx.x;
     const int per = (B + kPlanThreads - 1) / kPlanThreads;
     const int b0 = tid * per;
-    for (int b = tid; b < 2 * B + 2; b += kPlanThreads) k2_flags[b] = 0u;
+    for (int b = tid; b < static_cast<int>(k2_flag_words(B)); b += kPlanThreads) k2_flags[b] = 0u;
     if (padded_block_rows > 0) {  // padded layout: every utterance owns a block of T_dim * U rows
         for (int b = tid; b <= B; b += kPlanThreads) row_start[b] = b * padded_block_rows;
         return;

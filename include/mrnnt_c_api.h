@@ -82,6 +82,10 @@ const float *mrnnt_device_costs(mrnnt_handle_t h);
  * the logits-sized arrays).  acts and the workspace must stay untouched between the two halves. */
 RNNTStatus mrnnt_enqueue_forward(mrnnt_handle_t h, int blank_label, void *stream, int want_grads);
 RNNTStatus mrnnt_enqueue_backward(mrnnt_handle_t h, void *stream, float *gradients, const float *scale_dev_or_null);
+/* Forward half for a caller that already owns the gradient buffer the backward half will fill (want_grads implied):
+ * the lattice kernel writes that buffer's zero rows while its recursions run, and mrnnt_enqueue_backward, given the
+ * same pointer, only writes the others.  The buffer must not be written in between. */
+RNNTStatus mrnnt_enqueue_forward_into(mrnnt_handle_t h, int blank_label, void *stream, float *gradients);
 
 /* One-shot convenience: size check + set_workspace + optional restrict_to_alignment + cost_and_grad. */
 RNNTStatus rnnt_loss_grad_gpu(const float *acts, const int *labels, const int *T_dev, const int *S_dev,
@@ -99,11 +103,13 @@ enum {
     MRNNT_OPT_RESERVED_SMS = 6,  /* SMs the gradient kernel leaves free for a concurrent collective (0)    */
     MRNNT_OPT_PDL = 7,           /* programmatic dependent launch of K2 behind K1 and K3 behind K2 (1)     */
     MRNNT_OPT_K1_COMPACT = 8,    /* K1 variant that gives dead tiles no ring slot: 1 / 0 forced, -1 automatic */
-    MRNNT_OPT_K2_ZERO_FILL = 9,  /* warps per lattice CTA that zero the gradient's dead rows while the recursions
+    MRNNT_OPT_K2_ZERO_FILL = 9   /* warps per lattice CTA that zero the gradient's dead rows while the recursions
                                     run: 0 off (the gradient kernel writes them), 1..4, -1 automatic        */
-    MRNNT_OPT_K2_ZERO_FIRST_PART = 10 /* parts of an utterance below this one take no share of the zero fill (0) */
 };
 RNNTStatus mrnnt_set_option(mrnnt_handle_t h, int option, int value);
+/* What the last call actually did: MRNNT_OPT_K2_ZERO_FILL -> zero-fill warps per lattice CTA it ran with (0: the
+   gradient kernel wrote the zero rows).  Other options: RNNT_STATUS_INVALID_VALUE. */
+RNNTStatus mrnnt_get_option(mrnnt_handle_t h, int option, int *value);
 /* Durations in ms of K1, K2, K3 of the last call (MRNNT_OPT_TIMING on, stream synchronised). */
 RNNTStatus mrnnt_last_timings(mrnnt_handle_t h, float ms_k1_k2_k3[3]);
 

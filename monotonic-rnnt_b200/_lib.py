@@ -28,9 +28,9 @@ DBG_DENOM, DBG_ALPHA, DBG_BETA, DBG_LP, DBG_BAND, DBG_ROWMETA, DBG_LL, DBG_ROWST
 EXPORTED_SYMBOLS = (
     "compute_rnnt_loss", "mrnnt_get_workspace_size", "mrnnt_create", "mrnnt_destroy", "mrnnt_workspace_size",
     "mrnnt_set_workspace", "mrnnt_create_workspace", "mrnnt_free_workspace", "mrnnt_restrict_to_alignment",
-    "mrnnt_cost_and_grad", "mrnnt_enqueue", "mrnnt_device_costs", "rnnt_loss_grad_gpu", "mrnnt_set_option",
+    "mrnnt_cost_and_grad", "mrnnt_enqueue", "mrnnt_device_costs", "rnnt_loss_grad_gpu", "mrnnt_set_option", "mrnnt_get_option",
     "mrnnt_debug_copy", "mrnnt_synth_uniform", "mrnnt_build_info", "mrnnt_last_timings",
-    "mrnnt_enqueue_forward", "mrnnt_enqueue_backward", "mrnnt_create_padded",
+    "mrnnt_enqueue_forward", "mrnnt_enqueue_backward", "mrnnt_enqueue_forward_into", "mrnnt_create_padded",
     "mrnnt_get_workspace_size_padded", "mrnnt_set_dtype",
 )
 
@@ -64,10 +64,12 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mrnnt_enqueue.argtypes = [vp, ci, vp, vp]
     lib.mrnnt_enqueue_forward.argtypes = [vp, ci, vp, ci]
     lib.mrnnt_enqueue_backward.argtypes = [vp, vp, vp, vp]
+    lib.mrnnt_enqueue_forward_into.argtypes = [vp, ci, vp, vp]
     lib.mrnnt_device_costs.argtypes = [vp]
     lib.mrnnt_device_costs.restype = vp
     lib.rnnt_loss_grad_gpu.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, vp, ci, vp, sz, vp, vp, vp]
     lib.mrnnt_set_option.argtypes = [vp, ci, ci]
+    lib.mrnnt_get_option.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_int)]
     lib.mrnnt_debug_copy.argtypes = [vp, ci, vp, sz]
     lib.mrnnt_last_timings.argtypes = [vp, vp]
     lib.mrnnt_synth_uniform.argtypes = [vp, ctypes.c_int64, ctypes.c_uint64, ctypes.c_int64, vp]
@@ -75,8 +77,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mrnnt_build_info.restype = ctypes.c_char_p
     for name in ("mrnnt_get_workspace_size", "mrnnt_create", "mrnnt_workspace_size", "mrnnt_set_workspace",
                  "mrnnt_create_workspace", "mrnnt_restrict_to_alignment", "mrnnt_cost_and_grad", "mrnnt_enqueue",
-                 "rnnt_loss_grad_gpu", "mrnnt_set_option", "mrnnt_debug_copy", "mrnnt_synth_uniform",
-                 "mrnnt_last_timings", "mrnnt_enqueue_forward", "mrnnt_enqueue_backward", "mrnnt_create_padded",
+                 "rnnt_loss_grad_gpu", "mrnnt_set_option", "mrnnt_get_option", "mrnnt_debug_copy", "mrnnt_synth_uniform",
+                 "mrnnt_last_timings", "mrnnt_enqueue_forward", "mrnnt_enqueue_backward", "mrnnt_enqueue_forward_into", "mrnnt_create_padded",
                  "mrnnt_get_workspace_size_padded", "mrnnt_set_dtype"):
         getattr(lib, name).restype = ci
 

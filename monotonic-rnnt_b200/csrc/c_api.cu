@@ -170,6 +170,15 @@ RNNTStatus mrnnt_enqueue_forward(mrnnt_handle_t h, int blank_label, void *stream
     return e.enqueue_forward(blank_label, static_cast<cudaStream_t>(stream), want_grads != 0);
 }
 
+RNNTStatus mrnnt_enqueue_forward_into(mrnnt_handle_t h, int blank_label, void *stream, float *gradients) {
+    if (h == nullptr || gradients == nullptr) return RNNT_STATUS_INVALID_VALUE;
+    mrnnt::Engine &e = h->manager.engine();
+    const RNNTStatus st = e.ensure_shape();
+    if (st != RNNT_STATUS_SUCCESS) return st;
+    if (!e.has_workspace() || blank_label < 0 || blank_label >= e.shape().V) return RNNT_STATUS_INVALID_VALUE;
+    return e.enqueue_forward(blank_label, static_cast<cudaStream_t>(stream), true, gradients);
+}
+
 RNNTStatus mrnnt_enqueue_backward(mrnnt_handle_t h, void *stream, float *gradients, const float *scale_dev_or_null) {
     if (h == nullptr || gradients == nullptr) return RNNT_STATUS_INVALID_VALUE;
     mrnnt::Engine &e = h->manager.engine();
@@ -229,6 +238,17 @@ RNNTStatus mrnnt_set_option(mrnnt_handle_t h, int option, int value) {
             return RNNT_STATUS_SUCCESS;
         case MRNNT_OPT_K2_ZERO_FILL:
             h->manager.engine().set_k2_zero_fill(value);
+            return RNNT_STATUS_SUCCESS;
+        default:
+            return RNNT_STATUS_INVALID_VALUE;
+    }
+}
+
+RNNTStatus mrnnt_get_option(mrnnt_handle_t h, int option, int *value) {
+    if (h == nullptr || value == nullptr) return RNNT_STATUS_INVALID_VALUE;
+    switch (option) {
+        case MRNNT_OPT_K2_ZERO_FILL:
+            *value = h->manager.engine().last_k2_zero_warps();
             return RNNT_STATUS_SUCCESS;
         default:
             return RNNT_STATUS_INVALID_VALUE;

@@ -124,6 +124,12 @@ class LossHandle:
     def set_option(self, option: int, value: int) -> None:
         _lib.check(self._lib.mrnnt_set_option(self._h, option, value), "mrnnt_set_option")
 
+    def get_option(self, option: int) -> int:
+        import ctypes
+        v = ctypes.c_int(0)
+        _lib.check(self._lib.mrnnt_get_option(self._h, option, ctypes.byref(v)), "mrnnt_get_option")
+        return int(v.value)
+
     def last_timings(self):
         """(ms_K1, ms_K2, ms_K3) of the last call; needs set_option(OPT_TIMING, 1) and a synchronised stream."""
         out = (ctypes.c_float * 3)()
@@ -174,11 +180,19 @@ class LossHandle:
         _lib.check(st, "mrnnt_enqueue")
         return self.device_costs()
 
-    def enqueue_forward(self, blank_label: int = 0, want_grads: bool = True) -> torch.Tensor:
+    def enqueue_forward(self, blank_label: int = 0, want_grads: bool = True,
+                        grads: Optional[torch.Tensor] = None) -> torch.Tensor:
         """First half of a call (K1 + K2); returns a device VIEW of the costs.  With want_grads the workspace
-        keeps what enqueue_backward() needs; acts and the workspace must stay untouched until then."""
+        keeps what enqueue_backward() needs; acts and the workspace must stay untouched until then.  `grads`
+        (optional): the buffer enqueue_backward() will be given -- its zero rows are then written here, while the
+        lattice recursions run; it must not be written in between."""
         with self._device():
-            st = self._lib.mrnnt_enqueue_forward(self._h, int(blank_label), self._stream(), 1 if want_grads else 0)
+            if grads is not None:
+                assert grads.is_cuda and grads.dtype == self.acts.dtype and grads.is_contiguous()
+                assert grads.numel() == self.acts.numel()
+                st = self._lib.mrnnt_enqueue_forward_into(self._h, int(blank_label), self._stream(), grads.data_ptr())
+            else:
+                st = self._lib.mrnnt_enqueue_forward(self._h, int(blank_label), self._stream(), 1 if want_grads else 0)
         _lib.check(st, "mrnnt_enqueue_forward")
         return self.device_costs()
 

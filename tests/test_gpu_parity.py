@@ -304,6 +304,46 @@ def _pad_case(case, extra_T, extra_U, extra_S):
     return acts4, labels
 
 
+@pytest.mark.parametrize("name", ["rand_v32", "rand_v17_shift1"])
+def test_forward_into_gradient_buffer(gu, name):
+    """mrnnt_enqueue_forward_into: the lattice kernel zeroes the dead rows of the buffer the backward half will fill.
+    Same result as the one-shot call; a backward half given ANOTHER buffer must still write every row of it."""
+    import monotonic_rnnt_b200 as mr
+    from monotonic_rnnt_b200 import _lib
+    case, ref = golden_io.load(name)
+    dev = torch.device("cuda", 0)
+    V = 1000  # (the streaming kernels; the golden cases' own V is below their minimum)
+    rng = np.random.default_rng(5)
+    acts_np = rng.random((case.acts.shape[0], V), dtype=np.float32)
+    wide = fixtures.Case(name + "_v1000", acts_np, case.labels, case.T, case.S, V, case.blank)
+    if case.alignment is not None:
+        wide = wide.with_alignment(case.alignment, case.max_shift)
+    o64 = _oracle(wide, "f64_from_f32")
+    acts = torch.from_numpy(acts_np).to(dev)
+    h = mr.LossHandle(acts, torch.from_numpy(wide.labels).to(dev), torch.from_numpy(wide.T).to(dev),
+                      torch.from_numpy(wide.S).to(dev))
+    if wide.alignment is not None:
+        h.restrict_to_alignment(torch.from_numpy(wide.alignment).to(dev), wide.max_shift, wide.blank)
+    h.set_option(_lib.OPT_K2_ZERO_FILL, 2)
+    g1 = torch.full_like(acts, float("nan"))
+    costs = h.enqueue_forward(wide.blank, grads=g1).clone()
+    assert h.get_option(_lib.OPT_K2_ZERO_FILL) == 2
+    h.enqueue_backward(g1)
+    torch.cuda.synchronize()
+    _check_costs(costs.cpu().numpy(), o64.costs)
+    assert not torch.isnan(g1).any()
+    assert np.abs(g1.cpu().numpy() - o64.grads).max() <= GRAD_ATOL
+    # forward into g1, backward into g2: g2 complete, nothing assumed about it
+    g1.fill_(float("nan"))
+    g2 = torch.full_like(acts, float("nan"))
+    h.enqueue_forward(wide.blank, grads=g1)
+    h.enqueue_backward(g2)
+    torch.cuda.synchronize()
+    assert not torch.isnan(g2).any()
+    assert np.abs(g2.cpu().numpy() - o64.grads).max() <= GRAD_ATOL
+    h.close()
+
+
 @pytest.mark.parametrize("name,extra", [("rand_v32", (0, 0, 0)), ("rand_v32", (3, 2, 4)), ("rand_v17_shift1", (1, 5, 0)),
                                         ("rand_edges", (2, 1, 1)), ("rand_wide_shift3", (0, 3, 2)), ("readme", (0, 0, 0))])
 def test_padded_layout_matches_packed(gu, name, extra):

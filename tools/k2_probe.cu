@@ -1,5 +1,6 @@
 // Development aid: where the time of the REAL lattice kernel (k2_lattice.cuh) goes, on synthetic weights.
-//   k2_probe [T] [S] [B] [parts]   -> event time of the kernel, clock64 stamps of the alpha pass of utterance 0
+//   k2_probe [T] [S] [B] [parts] [K] [zero_warps] [V]  -> event time of the kernel, clock64 stamps of the alpha pass of
+//   utterance 0 (and of its CTA's first zero-fill warp)
 #define MRNNT_K2_TRACE
 #include <cstdio>
 #include <cstdlib>
@@ -23,7 +24,8 @@ static float run(const K2Args &a, int B, size_t sm, int reps) {
         b.epoch = a.epoch + r;
         cudaMemcpy(g_lp_dev, g_lp_host, g_lp_bytes, cudaMemcpyHostToDevice);
         cudaEventRecord(e0);
-        k2_lattice_kernel<K><<<B * a.parts, kK2Threads, sm>>>(b);
+        b.phase_ctas = B * a.parts;
+        k2_lattice_kernel<K><<<(a.zero_warps > 0 && a.need_beta && B * a.parts < 148) ? 148 : B * a.parts, kK2Threads, sm>>>(b);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1);
@@ -47,7 +49,7 @@ int main(int argc, char **argv) {
     cudaMalloc(&dT, 4 * B); cudaMalloc(&dS, 4 * B); cudaMalloc(&dl, 4 * B * S); cudaMalloc(&drs, 8 * (B + 1));
     cudaMalloc(&dband, band.size() * 8); cudaMalloc(&dlp, lp.size() * 16);
     cudaMalloc(&dal, rows * 8); cudaMalloc(&dbe, rows * 8); cudaMalloc(&dll, 16 * B); cudaMalloc(&dco, rows * 16);
-    cudaMalloc(&dc, 4 * B); cudaMalloc(&dfl, 8 * B); cudaMemset(dfl, 0, 8 * B); cudaMalloc(&dw, rows * 16);
+    cudaMalloc(&dc, 4 * B); cudaMalloc(&dfl, 4 * k2_flag_words(B)); cudaMemset(dfl, 0, 4 * k2_flag_words(B)); cudaMalloc(&dw, rows * 16);
     cudaMemcpy(dT, hT.data(), 4 * B, cudaMemcpyHostToDevice); cudaMemcpy(dS, hS.data(), 4 * B, cudaMemcpyHostToDevice);
     cudaMemcpy(dl, labels.data(), 4 * B * S, cudaMemcpyHostToDevice); cudaMemcpy(drs, rs.data(), 8 * (B + 1), cudaMemcpyHostToDevice);
     cudaMemcpy(dband, band.data(), band.size() * 8, cudaMemcpyHostToDevice);
@@ -61,9 +63,26 @@ int main(int argc, char **argv) {
     a.row_warps = k2_row_warps(W, K);
     a.chunk_bufs = k2_chunk_bufs(a.row_warps);
     const size_t sm = k2_smem_bytes(W, a.row_warps);
+    // zero fill: the plan's row flags of an unrestricted lattice, and a gradient buffer to fill
+    const int zero_warps = argc > 6 ? atoi(argv[6]) : 0, V = argc > 7 ? atoi(argv[7]) : 1000;
+    std::vector<int> meta(rows);
+    size_t ndead = 0;
+    for (int b = 0; b < B; ++b)
+        for (int t = 0; t < T; ++t)
+            for (int s2 = 0; s2 <= S; ++s2) {
+                const bool live = t == 0 ? s2 == 0 : (s2 <= t && (S - s2) <= (T - t));
+                meta[(size_t)b * rows1 + (size_t)t * W + s2] = live ? kRowNoLabel : kRowDead;
+                ndead += !live;
+            }
+    int *dmeta; unsigned char *dgr = nullptr;
+    cudaMalloc(&dmeta, rows * 4); cudaMemcpy(dmeta, meta.data(), rows * 4, cudaMemcpyHostToDevice);
+    if (zero_warps > 0) cudaMalloc(&dgr, rows * (size_t)V * 4);
+    a.rowmeta = dmeta; a.zero_dst = dgr; a.row_bytes = (unsigned)V * 4u; a.rows = (int64_t)rows; a.B = B;
+    printf("dead rows: %zu of %zu = %.1f MB to zero\n", ndead, rows, ndead * (double)V * 4e-6);
     unsigned epoch = 1;
     for (int nb = 0; nb < 2; ++nb) {
         a.need_beta = nb; a.parts = nb ? parts : 1; a.epoch = epoch; epoch += 100;
+        a.zero_warps = nb ? zero_warps : 0;
         float ms;
         if (K == 1) ms = run<1>(a, B, sm, 10);
         else if (K == 2) ms = run<2>(a, B, sm, 10);
@@ -81,6 +100,7 @@ int main(int argc, char **argv) {
             printf("(%lld, %lld) ", h[3 + 2 * c] - h[2 + 2 * c], (c + 1 < nch && c < 19 ? h[4 + 2 * c] : h[50]) - h[3 + 2 * c]);
         printf("\n  phase A (own share) %lld cyc, wait for the other parts %lld cyc, both passes done at %lld cyc, coefficient phase %lld cyc\n",
                h[60] - h[0], h[61] - h[60], h[51] - h[0], h[52] - h[51]);
+        if (a.zero_warps > 0) printf("  zero fill of CTA 0's first warp: from %lld to %lld cyc\n", h[53] - h[0], h[54] - h[0]);
     }
     return 0;
 }

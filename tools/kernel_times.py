@@ -19,7 +19,7 @@ from monotonic_rnnt_b200 import _lib  # noqa: E402
 
 
 def run(name: str, iters: int, combos, padded: bool = False, bf16: bool = False, compact: int = -1,
-        zeros=(-1,), zero_first: int = 0) -> None:
+        zeros=(-1,)) -> None:
     wl = mr.synth.workload(name)
     dev = torch.device("cuda", 0)
     lib = _lib.load()
@@ -85,8 +85,7 @@ if __name__ == "__main__":
     ap.add_argument("--compact", type=int, default=-1, help="K1 dead-tile compaction: 1 / 0 forced, -1 automatic")
     ap.add_argument("--padded", action="store_true", help="feed the padded [B,T,S+1,V] tensor instead of packed rows")
     ap.add_argument("--zero", default="-1", help="comma list of MRNNT_OPT_K2_ZERO_FILL values to compare")
-    ap.add_argument("--zero-first", type=int, default=0)
     a = ap.parse_args()
     combos = [tuple(int(x) for x in c.split(":")) for c in a.combos.split(",")]
     for name in a.workloads:
-        run(name, a.iters, combos, a.padded, a.bf16, a.compact, [int(z) for z in a.zero.split(',')], a.zero_first)
+        run(name, a.iters, combos, a.padded, a.bf16, a.compact, [int(z) for z in a.zero.split(',')])
