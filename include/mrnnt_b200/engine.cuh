@@ -373,11 +373,24 @@ class Engine {
 
     // Launch everything on `stream` without synchronising; costs stay in workspace().costs.
     RNNTStatus enqueue(int blank, cudaStream_t stream, void *grads_dev) {
+        // Under an alignment band the zero rows are most of the call's traffic: the LSE kernel's and the gradient
+        // kernel's zero-fill warps share one fill (SHARED protocol, zero_fill.cuh).  Two counters take turns; the
+        // lattice kernel of this call clears the one the next call will use.
+        shared_fill_ctr_ = shared_fill_clear_ = nullptr;
+        zero_dst_ = grads_dev;
+        if (grads_dev != nullptr && k3_zero_warp_wanted() && zero_fill_possible() && base_ != nullptr) {
+            unsigned *pair = ws_.k2_flags + k2_zero_ctr_word(B_) + 2;
+            ++shared_seq_;
+            shared_fill_ctr_ = pair + (shared_seq_ & 1u);
+            shared_fill_clear_ = pair + ((shared_seq_ + 1u) & 1u);
+        }
         RNNTStatus st = enqueue_forward(blank, stream, grads_dev != nullptr, grads_dev);
-        if (st != RNNT_STATUS_SUCCESS || grads_dev == nullptr) return st;
-        k3_follows_k2_ = !timing_;  // (the timing events between the kernels would break the dependent launch)
-        st = enqueue_backward(stream, grads_dev, nullptr);
-        k3_follows_k2_ = false;
+        if (st == RNNT_STATUS_SUCCESS && grads_dev != nullptr) {
+            k3_follows_k2_ = !timing_;  // (the timing events between the kernels would break the dependent launch)
+            st = enqueue_backward(stream, grads_dev, nullptr);
+            k3_follows_k2_ = false;
+        }
+        shared_fill_ctr_ = shared_fill_clear_ = nullptr;
         return st;
     }
 
@@ -414,9 +427,14 @@ class Engine {
         const DeviceInfo &dev = device_info();
         if (!dev.ok) return RNNT_STATUS_EXECUTION_FAILED;
         if (grads_dev == nullptr || coef_blank_ < 0) return RNNT_STATUS_INVALID_VALUE;
-        k3_write_dead_ = dead_rows_zeroed_ != grads_dev;
+        // who writes the plan's dead rows: the lattice kernel has (into this very buffer), or the gradient kernel's own
+        // zero-fill warp will, or its consumer warps do
+        zero_dst_ = grads_dev;
+        k3_zero_warp_ = dead_rows_zeroed_ != grads_dev && k3_zero_warp_wanted() && zero_fill_possible();
+        k3_write_dead_ = dead_rows_zeroed_ != grads_dev && !k3_zero_warp_;
         dead_rows_zeroed_ = nullptr;  // (good for the one backward pass that follows directly)
         mark(2, stream);
+        if (k3_zero_warp_) last_k2_zero_warps_ = 32;
         const RNNTStatus st = launch_k3(coef_blank_, stream, dev, grads_dev, scale_dev);
         mark(3, stream);
         return st;
@@ -475,7 +493,7 @@ class Engine {
             plan_row_start_kernel<<<1, kPlanThreads, 0, stream>>>(
                 T_dev_, S_dev_, B_, ws_.row_start, ws_.k2_flags, static_cast<int64_t>(shape_.T_dim) * shape_.U);
             if (launched() != RNNT_STATUS_SUCCESS) return RNNT_STATUS_EXECUTION_FAILED;
-            plan_dirty_ = false;
+            plan_dirty_ = false;  // (both counters of the shared zero fill are clear now: either may come first)
         }
         if (band_dirty_) {
             size_t smem = alignment_ != nullptr ? (static_cast<size_t>(shape_.T_max) + 1) * sizeof(int) : 0;
@@ -520,9 +538,17 @@ class Engine {
     template <typename E, int NW, int C, bool COMPACT>
     RNNTStatus launch_k1_variant(int blank, cudaStream_t stream, const DeviceInfo &dev, const StreamTiling &tl) {
         auto kern = k1_lse_tma_kernel<E, NW, C, COMPACT>;
-        if (!ensure_dynamic_smem(kern, tl.smem_bytes)) return RNNT_STATUS_EXECUTION_FAILED;
-        kern<<<dev.sm_count, (NW + 1) * kWarp, tl.smem_bytes, stream>>>(static_cast<const E *>(acts_), labels_, ws_.rowmeta,
-                                                                         ws_.lp, shape_.rows, V_, blank, tl.G, tl.stages);
+        // (the kernel's zero-fill warp: one more warp, 8 KB more shared memory; the gradient kernel continues the fill)
+        ZeroFill zero{};
+        const bool zero_warp = COMPACT && shared_fill_ctr_ != nullptr;
+        if (zero_warp) {
+            zero = zero_fill_args(zero_dst_, shared_fill_ctr_);
+        }
+        const size_t smem = k1_smem_bytes(tl.smem_bytes, zero_warp);
+        if (smem > static_cast<size_t>(dev.max_smem_optin) || !ensure_dynamic_smem(kern, smem)) return RNNT_STATUS_EXECUTION_FAILED;
+        kern<<<dev.sm_count, (NW + (zero_warp ? 2 : 1)) * kWarp, smem, stream>>>(
+            static_cast<const E *>(acts_), labels_, ws_.rowmeta, ws_.lp, shape_.rows, V_, blank, tl.G, tl.stages, zero,
+            tl.smem_bytes);
         return launched();
     }
 
@@ -628,6 +654,7 @@ class Engine {
         a.rowmeta = ws_.rowmeta;
         a.row_bytes = static_cast<unsigned>(static_cast<size_t>(V_) * elem_bytes());
         a.zero_warps = 0;
+        a.zero_clear = shared_fill_clear_;
         last_k2_zero_warps_ = 0;
         a.rows = shape_.rows;
         a.B = B_;
@@ -638,10 +665,9 @@ class Engine {
             // the zero fill needs bulk-copy granularity (16 bytes) and whole warps next to the chain warps and
             // their chunk issuers
             const int spare = kK2Warps - 1 - 2 * (a.row_warps + 1);
-            int zw = k2_zero_warps_ < 0 ? (zero_fill_pays() ? 2 : 0) : k2_zero_warps_;
+            int zw = k2_zero_warps_ < 0 ? (zero_fill_pays() ? 2 : 0) : (k2_zero_warps_ & 15);
             if (zw > spare) zw = spare;
-            if (need_beta && zero_dst_ != nullptr && zw > 0 && a.row_bytes % 16 == 0 &&
-                reinterpret_cast<uintptr_t>(zero_dst_) % 16 == 0 && static_cast<size_t>(V_) * elem_bytes() < (1ull << 31)) {
+            if (need_beta && zero_dst_ != nullptr && zw > 0 && !k3_zero_warp_wanted() && zero_fill_possible()) {
                 a.zero_dst = static_cast<unsigned char *>(zero_dst_);
                 a.zero_warps = zw;
                 last_k2_zero_warps_ = zw;
@@ -659,6 +685,36 @@ class Engine {
         if (!ensure_dynamic_smem(k2_lattice_wide_kernel, smem)) return RNNT_STATUS_EXECUTION_FAILED;
         k2_lattice_wide_kernel<<<B_, kK2Threads, smem, stream>>>(a);
         return launched();
+    }
+
+    ZeroFill zero_fill_args(void *dst, unsigned *ctr) const {
+        ZeroFill z;
+        z.dst = static_cast<unsigned char *>(dst);
+        z.rowmeta = ws_.rowmeta;
+        z.rows = shape_.rows;
+        z.row_bytes = static_cast<unsigned>(static_cast<size_t>(V_) * elem_bytes());
+        z.ctr = ctr;
+        return z;
+    }
+
+    // bulk-copy granularity: whole 16-byte vectors per row, aligned base
+    bool zero_fill_possible() const {
+        const size_t row_bytes = static_cast<size_t>(V_) * elem_bytes();
+        return row_bytes % 16 == 0 && reinterpret_cast<uintptr_t>(zero_dst_) % 16 == 0 && row_bytes < (1ull << 31);
+    }
+
+    // The zero fill as one more warp of the gradient kernel instead (k3_grad.cuh) -- and, in a one-shot call, of the
+    // LSE kernel before it, the two sharing one hand-out counter (enqueue()): where writing the zeros takes longer
+    // than everything else -- an alignment band leaves a few percent of the rows alive (c5: 4.45 GB of zeros against
+    // 0.7 GB of live traffic) -- it should overlap the live rows' work, not sit between the kernels.  Measured on c5
+    // (tools/kernel_times.py --zero 0,2,32): 1.03 ms with the gradient kernel's consumers writing the zeros, 0.92 ms
+    // with the lattice kernel's fill, 0.89 ms with the gradient kernel's zero-fill warp alone, 0.87 ms shared with the
+    // LSE kernel's (5.15 GB of traffic in all: 5.9 TB/s over the whole call).  On c2 it loses against the lattice
+    // kernel's fill (0.396 against 0.381 ms).
+    bool k3_zero_warp_wanted() const {
+        if (k2_zero_warps_ >= 0) return k2_zero_warps_ >= 32;
+        // a band of 2 * max_shift + 1 states (at most) around the alignment, out of S + 1: "nearly all dead" = under half alive
+        return alignment_ != nullptr && 2 * (static_cast<int64_t>(max_shift_) + 1) < (shape_.S_max + 1) / 2;
     }
 
     // Zero fill inside the lattice kernel (automatic choice).  What it wins is the duration of the recursions, during
@@ -684,15 +740,24 @@ class Engine {
     RNNTStatus launch_k3_tma(int blank, cudaStream_t stream, const DeviceInfo &dev, const StreamTiling &tl, void *grads,
                              const float *scale) {
         auto kern = k3_grad_tma_kernel<E, NW, SCALED>;
-        if (!ensure_dynamic_smem(kern, tl.smem_bytes)) return RNNT_STATUS_EXECUTION_FAILED;
+        // the kernel's own zero-fill warp (one more warp, 8 KB more shared memory)
+        ZeroFill zero{};
+        const bool zero_warp = k3_zero_warp_ && !k3_write_dead_;
+        int flags = k3_flags(tl);
+        if (zero_warp) {
+            zero = zero_fill_args(grads, shared_fill_ctr_ != nullptr ? shared_fill_ctr_ : ws_.k2_flags + k2_zero_ctr_word(B_));
+            if (shared_fill_ctr_ != nullptr) flags |= kK3ZeroShared;
+        }
+        const size_t smem = k3_smem_bytes(tl.smem_bytes, zero_warp);
+        if (smem > static_cast<size_t>(dev.max_smem_optin) || !ensure_dynamic_smem(kern, smem)) return RNNT_STATUS_EXECUTION_FAILED;
         // K3 is persistent with one CTA per SM; `reserved_sms_` of them can be left to a collective that runs
         // concurrently on another stream (the all-reduce of the summed cost, which is final after K2)
         const int grid = dev.sm_count - reserved_sms_ > 0 ? dev.sm_count - reserved_sms_ : 1;
         // (a dependent launch only right behind the lattice kernel: a backward pass called on its own has no such
         // predecessor to wait for, and an ordinary launch orders it behind whatever precedes it in the stream)
-        if (launch_kernel(kern, grid, (NW + 1) * kWarp, tl.smem_bytes, stream, pdl_ && k3_follows_k2_,
+        if (launch_kernel(kern, grid, (NW + (zero_warp ? 2 : 1)) * kWarp, smem, stream, pdl_ && k3_follows_k2_,
                           static_cast<const E *>(acts_), ws_.coef, static_cast<E *>(grads), shape_.rows, V_, blank, tl.G,
-                          tl.stages, ws_.rowutt, scale, cost_mirror(), k3_flags(tl)) != cudaSuccess)
+                          tl.stages, ws_.rowutt, scale, cost_mirror(), flags, zero, tl.smem_bytes) != cudaSuccess)
             return RNNT_STATUS_EXECUTION_FAILED;
         return launched();
     }
@@ -767,7 +832,11 @@ class Engine {
     bool pdl_ = true;             // programmatic dependent launch of K2 behind K1 and of K3 behind K2
     void *zero_dst_ = nullptr;          // enqueue(): gradient buffer handed to the lattice kernel's zero fill
     void *dead_rows_zeroed_ = nullptr;  // the buffer whose dead rows the last lattice kernel zeroed (nullptr: none)
-    bool k3_write_dead_ = true;         // the gradient kernel writes the zero rows itself
+    bool k3_write_dead_ = true;         // the gradient kernel's consumer warps write the zero rows
+    bool k3_zero_warp_ = false;         // ... or its own zero-fill warp does
+    unsigned *shared_fill_ctr_ = nullptr;    // enqueue(): the counter K1's and K3's zero-fill warps share in this call
+    unsigned *shared_fill_clear_ = nullptr;  // ... and the one this call's K2 clears for the next call
+    unsigned shared_seq_ = 0u;
     int last_k2_zero_warps_ = 0;        // what the last lattice launch ran with
     int k2_zero_warps_ = -1;            // warps per lattice CTA for the zero fill: -1 automatic, 0 off
     bool k3_follows_k2_ = false;  // K3 is being enqueued directly behind K2 (enqueue(), not a separate backward)

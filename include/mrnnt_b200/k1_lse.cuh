@@ -22,6 +22,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "zero_fill.cuh"
 
 namespace mrnnt {
 
@@ -267,11 +268,18 @@ __device__ __forceinline__ void issue_live_runs(uint32_t mask, E *tile, const E 
 // the slots, not the tiles; the producer ends the sequence with one terminator per slot).  Worth it when many
 // tiles are dead -- alignment-restricted lattices, padded inputs -- and costs ~2 % on dense inputs (the end of the
 // kernel waits for the terminators), hence a compile-time choice made by the engine.
+// The COMPACT variant can carry one more warp that zeroes dead rows of the GRADIENT while this kernel runs (`zero`,
+// zero_fill.cuh, SHARED protocol: the gradient kernel's own zero-fill warp continues where this one stops): under an
+// alignment band this kernel leaves the memory system nearly idle, and the zeros are most of the call's traffic.
+inline size_t k1_smem_bytes(size_t ring_bytes, bool zero_warp) {
+    return zero_warp ? (ring_bytes + 127) / 128 * 128 + kZeroFillBytes + 16 : ring_bytes;
+}
+
 template <typename E, int NW, int C, bool COMPACT>
-static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
+static __global__ void __launch_bounds__((NW + (COMPACT ? 2 : 1)) * kWarp, 1)
     k1_lse_tma_kernel(const E *__restrict__ acts, const int *__restrict__ labels,
                       const int *__restrict__ rowmeta, RawRow *__restrict__ lp, int64_t rows, int V, int blank,
-                      int G, int stages) {
+                      int G, int stages, ZeroFill zero, size_t ring_bytes) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const size_t tile_elems = static_cast<size_t>(G) * V;
     E *tiles = reinterpret_cast<E *>(smem_raw);
@@ -281,16 +289,26 @@ static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
     int2 *meta_sh = reinterpret_cast<int2 *>(empty + stages);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *zbuf = smem_raw + (ring_bytes + 127) / 128 * 128;          // (only there with a zero-fill warp)
+    int *consumers_done = reinterpret_cast<int *>(zbuf + kZeroFillBytes);
+    const bool zero_warp = COMPACT && zero.dst != nullptr;
     if (threadIdx.x == 0) {
         for (int i = 0; i < stages; ++i) {
             mbar_init(full + i, 1);
             mbar_init(empty + i, static_cast<uint32_t>(G));
         }
         mbar_init_fence();
+        if (zero_warp) *consumers_done = 0;
     }
     __syncthreads();
     pdl_launch_dependents();  // the lattice kernel may be scheduled as our CTAs retire (it waits for all of us)
     pdl_wait();               // (first kernel of a call: its predecessor is the previous call or a set-up kernel)
+    if (COMPACT && warp == NW + 1) {
+        // ---------------- zero-fill warp: for as long as this CTA's consumer warps have work ----------------
+        zero_dead_rows_impl<false>(zero, 0, 0, zbuf,
+                                   [&] { return *reinterpret_cast<volatile int *>(consumers_done) >= NW; });
+        return;
+    }
 
     const int64_t ntiles = (rows + G - 1) / G;
     const int64_t nloc = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -387,6 +405,7 @@ static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
             if (lane == 0) mbar_arrive(empty + stage);
             MRNNT_K1_ADD(warp, 1, MRNNT_K1_CLOCK() - tw1);
         }
+        if (zero_warp && lane == 0) atomicAdd(consumers_done, 1);
     }
 }
 

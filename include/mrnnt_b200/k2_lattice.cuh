@@ -42,6 +42,7 @@
 
 #include "common.cuh"
 #include "plan.cuh"
+#include "zero_fill.cuh"
 
 namespace mrnnt {
 
@@ -100,6 +101,7 @@ struct K2Args {
     int zero_warps;           // 0: off
     int64_t rows;             // rows of the whole batch (= row_start[B])
     int B;                    // utterances; flags[k2_zero_ctr_word(B)...]: the zero fill's two counters
+    unsigned *zero_clear;     // SHARED zero fill: the counter of the NEXT call, cleared here (nullptr: none)
     int phase_ctas;           // B * parts; CTAs behind them (zero fill only) do nothing else
 };
 
@@ -133,8 +135,7 @@ __host__ __device__ inline size_t k2_dir_bytes(size_t chunk_bytes, int bufs, int
     return bufs * chunk_bytes + 2 * kK2MaxChunkBufs * sizeof(uint64_t) + 64 +
            static_cast<size_t>(row_warps > 1 ? row_warps - 1 : 0) * kK2FifoDepth * sizeof(Cell);
 }
-constexpr int kK2ZeroBytes = 8192;  // zeroed shared memory every bulk store of the zero fill reads from (tools/
-                                    // zero_probe.cu: 8 KB stores from one warp per SM already reach the write bandwidth)
+constexpr int kK2ZeroBytes = kZeroFillBytes;
 __host__ __device__ inline size_t k2_zero_offset(size_t dir_bytes) { return (2 * dir_bytes + 127) / 128 * 128; }
 inline size_t k2_smem_bytes(int width, int row_warps) {
     return k2_zero_offset(k2_dir_bytes(static_cast<size_t>(k2_chunk_frames(width)) * width * sizeof(Weight),
@@ -569,72 +570,15 @@ __device__ __forceinline__ void k2_coef_rows(const K2Args &a, int b, int part, i
 }
 
 // ---- cross-CTA hand-over of one utterance ----------------------------------------------------------------
-// ---- dead-row zero fill ---------------------------------------------------------------------------------
-__device__ __forceinline__ void bulk_s2g(void *gdst, const void *ssrc, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
-                 "r"(static_cast<uint32_t>(__cvta_generic_to_shared(ssrc))), "r"(bytes)
-                 : "memory");
-}
-// Called by whole warps (warp `fw` of the `nfw` zero-fill warps of the grid).  The rows of the whole batch are handed
-// out in units of 32 through a counter: the dead rows sit at the two ends of every utterance (or everywhere, under an
-// alignment band), and a fixed split leaves some warps with twice the bytes of others.  A warp's first two units are
-// fixed; the grab for the unit three ahead and the row flags of the unit two ahead are in flight while a unit is
-// processed.  A lane that sees the first row of a run of dead rows stores the whole run, 8 KB at a time.
-// `ctr`: {units handed out beyond the fixed ones, warps finished}, both zero between launches.
+// ---- dead-row zero fill (zero_fill.cuh) ----------------------------------------------------------------------
 __device__ __forceinline__ void k2_zero_dead_rows(const K2Args &a, int fw, int nfw, unsigned char *zbuf) {
-    const int lane = threadIdx.x & 31;
-    for (int i = lane * 16; i < kK2ZeroBytes; i += kWarp * 16) *reinterpret_cast<uint4 *>(zbuf + i) = make_uint4(0u, 0u, 0u, 0u);
-    fence_proxy_async_smem();
-    __syncwarp();
-    const int64_t rows = a.rows;
-    const int *meta = a.rowmeta;
-    unsigned *ctr = a.flags + k2_zero_ctr_word(a.B);
-    const int64_t nunits = (rows + kWarp - 1) / kWarp;
-    auto grab = [&]() { return lane == 0 ? atomicAdd(ctr, 1u) : 0u; };  // (the value is only looked at two units later)
-    auto unit_of = [&](unsigned raw) { return static_cast<int64_t>(__shfl_sync(0xffffffffu, raw, 0)) + 2 * nfw; };
-    auto load = [&](int64_t u) {
-        const int64_t r = u * kWarp + lane;
-        return (u < nunits && r < rows) ? __ldg(meta + r) : 0;
-    };
-    int64_t u0 = fw, u1 = fw + nfw;
-    unsigned raw_a = grab(), raw_b = grab();
-    int m0 = load(u0), m1 = load(u1);
-    while (u0 < nunits) {
-        const unsigned raw_c = grab();
-        const int64_t u2 = unit_of(raw_a);
-        const int m2 = load(u2);
-        const bool dead = m0 == kRowDead;
-        const uint32_t mask = __ballot_sync(0xffffffffu, dead);
-        if (dead && (lane == 0 || ((mask >> (lane - 1)) & 1u) == 0u)) {
-            const uint32_t inv = ~(mask >> lane);  // (the shift fills with zeros: inv != 0 unless lane == 0 and all dead)
-            const int len = inv ? __ffs(inv) - 1 : kWarp;
-            unsigned char *p = a.zero_dst + static_cast<size_t>(u0 * kWarp + lane) * a.row_bytes;
-            size_t left = static_cast<size_t>(len) * a.row_bytes;
-            while (left > 0) {
-                const uint32_t nbytes = left < static_cast<size_t>(kK2ZeroBytes) ? static_cast<uint32_t>(left) : kK2ZeroBytes;
-                bulk_s2g(p, zbuf, nbytes);
-                p += nbytes;
-                left -= nbytes;
-            }
-        }
-        u0 = u1;
-        m0 = m1;
-        u1 = u2;
-        m1 = m2;
-        raw_a = raw_b;
-        raw_b = raw_c;
-    }
-    // the stores must have left shared memory before the CTA gives it up; the kernel's end makes them visible
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    // the last warp to finish leaves the counters as it found them (every grab of this launch has been made by then:
-    // a warp looks at its last two grabs before it reports)
-    const unsigned seen = __shfl_sync(0xffffffffu, raw_a, 0) + __shfl_sync(0xffffffffu, raw_b, 0);
-    if (lane == 0 && atomicAdd(ctr + 1, seen * 0u + 1u) == static_cast<unsigned>(nfw) - 1u) {
-        ctr[0] = 0u;
-        ctr[1] = 0u;
-        __threadfence();
-    }
+    ZeroFill z;
+    z.dst = a.zero_dst;
+    z.rowmeta = a.rowmeta;
+    z.rows = a.rows;
+    z.row_bytes = a.row_bytes;
+    z.ctr = a.flags + k2_zero_ctr_word(a.B);
+    zero_dead_rows(z, fw, nfw, zbuf);
 }
 
 __device__ __forceinline__ unsigned k2_ld_acquire(const unsigned *p) {
@@ -690,6 +634,7 @@ static __global__ void __launch_bounds__(kK2Threads) k2_lattice_kernel(K2Args a)
     const int nphase = kK2Threads - zw * kWarp;
     MRNNT_K2_STAMP(0);
     pdl_wait();  // K1's records
+    if (blockIdx.x == 0 && tid == 0 && a.zero_clear != nullptr) *a.zero_clear = 0u;
 
     // ---- phase A: transition weights, all parts ----
     k2_weight_rows(a, b, part, parts, tid, nphase);
@@ -774,6 +719,7 @@ static __global__ void __launch_bounds__(kK2Threads) k2_lattice_wide_kernel(K2Ar
     Cell *alpha = a.alpha + R;
     Cell *beta = a.beta + R;
     const int tid = threadIdx.x;
+    if (b == 0 && tid == 0 && a.zero_clear != nullptr) *a.zero_clear = 0u;
 
     // K1's (max, sum) -> the denominator pair, in place (what phase A of the main kernel does); rows K1 skipped
     // hold garbage before and after, and are masked wherever they are read

@@ -20,6 +20,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "zero_fill.cuh"
 #include "k1_lse.cuh"
 
 namespace mrnnt {
@@ -34,9 +35,10 @@ struct CostMirror {
     float *mapped = nullptr;       // host-mapped copy, or nullptr
     int B = 0;
 };
-__device__ __forceinline__ void mirror_costs(const CostMirror &m) {
+// (called by threads 0 .. nthreads-1 of every CTA)
+__device__ __forceinline__ void mirror_costs(const CostMirror &m, int nthreads) {
     if (m.mapped != nullptr && blockIdx.x == 0)
-        for (int i = threadIdx.x; i < m.B; i += blockDim.x) m.mapped[i] = m.costs[i];
+        for (int i = threadIdx.x; i < m.B; i += nthreads) m.mapped[i] = m.costs[i];
 }
 
 // subtract the blank / label term from component k of a vector of NE gradients (k is warp-divergent, so the
@@ -59,7 +61,7 @@ static __global__ void __launch_bounds__(kGenericWarps * kWarp)
     k3_grad_generic_kernel(const E *__restrict__ acts, const float4 *__restrict__ coef, E *__restrict__ grads,
                            int64_t rows, int V, int blank, const int *__restrict__ rowutt,
                            const float *__restrict__ scale, CostMirror mirror) {
-    mirror_costs(mirror);
+    mirror_costs(mirror, blockDim.x);
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * kGenericWarps + (threadIdx.x >> 5);
     const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kGenericWarps;
@@ -89,14 +91,21 @@ static __global__ void __launch_bounds__(kGenericWarps * kWarp)
 // | tile[stages] ints
 // ---------------------------------------------------------------------------------------------
 // flags
-constexpr int kK3WriteDead = 1;  // write the zero rows (off: the lattice kernel has zeroed the rows the plan calls dead)
+constexpr int kK3WriteDead = 1;  // write the zero rows (off: somebody else zeroes the rows the plan calls dead)
 constexpr int kK3Compact = 2;    // tiles without a live row take no ring slot (needs kK3WriteDead off)
+constexpr int kK3ZeroShared = 4; // the zero-fill warp continues a fill the LSE kernel's zero-fill warp has begun
+// With a ZeroFill (dst != nullptr) the kernel is launched with one more warp, which zeroes the plan's dead rows next to
+// the consumer warps (zero_fill.cuh) out of kZeroFillBytes of shared memory behind the ring: where nearly all rows
+// are dead, writing the zeros takes longer than everything else, and it need not wait for anything.
+inline size_t k3_smem_bytes(size_t ring_bytes, bool zero_warp) {
+    return zero_warp ? (ring_bytes + 127) / 128 * 128 + kZeroFillBytes : ring_bytes;
+}
 
 template <typename E, int NW, bool SCALED>
-static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
+static __global__ void __launch_bounds__((NW + 2) * kWarp, 1)
     k3_grad_tma_kernel(const E *__restrict__ acts, const float4 *__restrict__ coef, E *__restrict__ grads,
                        int64_t rows, int V, int blank, int G, int stages, const int *__restrict__ rowutt,
-                       const float *__restrict__ scale, CostMirror mirror, int flags) {
+                       const float *__restrict__ scale, CostMirror mirror, int flags, ZeroFill zero, size_t ring_bytes) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NE = Elem<E>::kPerVec;
     const size_t tile_elems = static_cast<size_t>(G) * V;
@@ -117,8 +126,15 @@ static __global__ void __launch_bounds__((NW + 1) * kWarp, 1)
         mbar_init_fence();
     }
     __syncthreads();
+    if (warp == NW + 1) {
+        // ---------------- zero-fill warp (only launched with a ZeroFill): needs nothing the lattice kernel wrote ----
+        unsigned char *zbuf = smem_raw + (ring_bytes + 127) / 128 * 128;
+        if (flags & kK3ZeroShared) zero_dead_rows_impl<false>(zero, 0, 0, zbuf, [] { return false; });
+        else zero_dead_rows(zero, blockIdx.x, gridDim.x, zbuf);
+        return;
+    }
     pdl_wait();  // the coefficients come from the lattice kernel; everything above overlapped its tail
-    mirror_costs(mirror);
+    mirror_costs(mirror, (NW + 1) * kWarp);
 
     const int64_t ntiles = (rows + G - 1) / G;
     const int64_t nloc = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;

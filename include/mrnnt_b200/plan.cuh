@@ -56,10 +56,11 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 
 // Bytes needed for `shape`.  A function of (B, T[], S[]) only, like the reference
 // (gpu_workspace_manager.h:242-247); the value differs (60 B/row + O(B*T_max) instead of 12 B/row).
-// words of Workspace::k2_flags: 2 per utterance, then (256 bytes clear of the flags that waiting CTAs poll) the two
-// counters of the lattice kernel's zero fill
+// words of Workspace::k2_flags: 2 per utterance, then (256 bytes clear of the flags that waiting CTAs poll) the
+// counters of the zero fill (zero_fill.cuh): two of the OWNED protocol, then the two alternating ones of the SHARED
+// protocol
 __host__ __device__ inline size_t k2_zero_ctr_word(int B) { return (2 * static_cast<size_t>(B) + 63) / 64 * 64 + 64; }
-__host__ __device__ inline size_t k2_flag_words(int B) { return k2_zero_ctr_word(B) + 2; }
+__host__ __device__ inline size_t k2_flag_words(int B) { return k2_zero_ctr_word(B) + 4; }
 inline size_t workspace_bytes(const Shape &sh) {
     const size_t rows = static_cast<size_t>(sh.rows);
     const size_t B = static_cast<size_t>(sh.B);

@@ -1,0 +1,126 @@
+// Zero fill: writing the gradient rows that are zero by construction (the plan's dead rows, rowmeta == kRowDead) with
+// bulk shared->global copies, by warps that do nothing else -- inside the lattice kernel while its recursions leave the
+// memory system idle (k2_lattice.cuh), or inside the gradient kernel next to its consumer warps where nearly all rows
+// are dead (k3_grad.cuh).
+#pragma once
+
+#include "common.cuh"
+#include "plan.cuh"
+
+namespace mrnnt {
+
+constexpr int kZeroFillBytes = 8192;  // zeroed shared memory every bulk store reads from (tools/zero_probe.cu: 8 KB
+                                      // stores from one warp per SM already reach the write bandwidth of the GPU)
+struct ZeroFill {
+    unsigned char *dst;   // the gradient buffer
+    const int *rowmeta;   // [rows]
+    int64_t rows;         // rows of the whole batch
+    unsigned row_bytes;   // V * sizeof(element), a multiple of 16
+    unsigned *ctr;        // the hand-out counter (OWNED: {units handed out, warps finished}, zero between launches)
+};
+
+__device__ __forceinline__ void bulk_s2g(void *gdst, const void *ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                 "r"(static_cast<uint32_t>(__cvta_generic_to_shared(ssrc))), "r"(bytes)
+                 : "memory");
+}
+// Called by whole warps.  The rows of the whole batch are handed out in units of 32, in order, through a counter: the
+// dead rows sit at the two ends of every utterance (or everywhere, under an alignment band), and a fixed split leaves
+// some warps with twice the bytes of others.  The grab for the unit three ahead and the row flags of the unit two
+// ahead are in flight while a unit is processed.  A lane that sees the first row of a run of dead rows stores the
+// whole run, 8 KB at a time.  Two protocols:
+//  * OWNED (one kernel does the whole fill): warp `fw` of the `nfw` zero-fill warps of the grid takes the units fw and
+//    fw + nfw without asking, the counter hands out the ones from 2 * nfw on, and the last warp to finish sets
+//    `ctr` = {units handed out, warps finished} back to zero for the next launch.
+//  * SHARED (!OWNED; the kernels of one call take turns at one counter, each for as long as it runs): every unit comes
+//    from the counter, which nobody resets here (the engine alternates between two, and the lattice kernel of a call
+//    clears the other one); `stop()` is looked at once per unit, and a warp that sees it true takes no more units
+//    (the up to three it already holds it still finishes: whoever continues starts behind them).
+template <bool OWNED, typename Stop>
+__device__ __forceinline__ void zero_dead_rows_impl(const ZeroFill &a, int fw, int nfw, unsigned char *zbuf, Stop stop) {
+    const int lane = threadIdx.x & 31;
+    for (int i = lane * 16; i < kZeroFillBytes; i += kWarp * 16) *reinterpret_cast<uint4 *>(zbuf + i) = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    const int64_t rows = a.rows;
+    const int *meta = a.rowmeta;
+    unsigned *ctr = a.ctr;
+    const int64_t nunits = (rows + kWarp - 1) / kWarp;
+    constexpr unsigned kNoUnit = 0xffffffffu;
+    bool stopped = false;
+    auto grab = [&]() {  // (the value is only looked at two units later)
+        if (!OWNED && stopped) return kNoUnit;
+        return lane == 0 ? atomicAdd(ctr, 1u) : 0u;
+    };
+    auto unit_of = [&](unsigned raw) {
+        const unsigned v = __shfl_sync(0xffffffffu, raw, 0);
+        return (!OWNED && v == kNoUnit) ? nunits : static_cast<int64_t>(v) + (OWNED ? 2 * nfw : 0);
+    };
+    auto load = [&](int64_t u) {
+        const int64_t r = u * kWarp + lane;
+        return (u < nunits && r < rows) ? __ldg(meta + r) : 0;
+    };
+    unsigned raw_a = grab(), raw_b = grab();
+    int64_t u0, u1;
+    if (OWNED) {
+        u0 = fw;
+        u1 = fw + nfw;
+    } else {
+        u0 = unit_of(raw_a);
+        u1 = unit_of(raw_b);
+        raw_a = grab();
+        raw_b = grab();
+    }
+    int m0 = load(u0), m1 = load(u1);
+    while (u0 < nunits) {
+        if (!OWNED) stopped = stopped || stop();
+        const unsigned raw_c = grab();
+        const int64_t u2 = unit_of(raw_a);
+        const int m2 = load(u2);
+        const bool dead = m0 == kRowDead;
+        const uint32_t mask = __ballot_sync(0xffffffffu, dead);
+        if (dead && (lane == 0 || ((mask >> (lane - 1)) & 1u) == 0u)) {
+            const uint32_t inv = ~(mask >> lane);  // (the shift fills with zeros: inv != 0 unless lane == 0 and all dead)
+            const int len = inv ? __ffs(inv) - 1 : kWarp;
+            unsigned char *p = a.dst + static_cast<size_t>(u0 * kWarp + lane) * a.row_bytes;
+            size_t left = static_cast<size_t>(len) * a.row_bytes;
+            while (left > 0) {
+                const uint32_t nbytes = left < static_cast<size_t>(kZeroFillBytes) ? static_cast<uint32_t>(left) : kZeroFillBytes;
+                bulk_s2g(p, zbuf, nbytes);
+                p += nbytes;
+                left -= nbytes;
+            }
+        }
+        if (!OWNED) {
+            // a kernel that stops must not leave megabytes of queued stores behind (measured: the bulk-copy pipe of an
+            // SM takes them by the thousand, 170 us to drain): at most two units' stores in flight per lane
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        }
+        u0 = u1;
+        m0 = m1;
+        u1 = u2;
+        m1 = m2;
+        raw_a = raw_b;
+        raw_b = raw_c;
+    }
+    // the stores must have left shared memory before the CTA gives it up; the kernel's end makes them visible
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (OWNED) {
+        // the last warp to finish leaves the counters as it found them (every grab of this launch has been made by
+        // then: a warp looks at its last two grabs before it reports)
+        const unsigned seen = __shfl_sync(0xffffffffu, raw_a, 0) + __shfl_sync(0xffffffffu, raw_b, 0);
+        if (lane == 0 && atomicAdd(ctr + 1, seen * 0u + 1u) == static_cast<unsigned>(nfw) - 1u) {
+            ctr[0] = 0u;
+            ctr[1] = 0u;
+            __threadfence();
+        }
+    }
+}
+
+__device__ __forceinline__ void zero_dead_rows(const ZeroFill &a, int fw, int nfw, unsigned char *zbuf) {
+    zero_dead_rows_impl<true>(a, fw, nfw, zbuf, [] { return false; });
+}
+
+}  // namespace mrnnt

@@ -103,12 +103,13 @@ enum {
     MRNNT_OPT_RESERVED_SMS = 6,  /* SMs the gradient kernel leaves free for a concurrent collective (0)    */
     MRNNT_OPT_PDL = 7,           /* programmatic dependent launch of K2 behind K1 and K3 behind K2 (1)     */
     MRNNT_OPT_K1_COMPACT = 8,    /* K1 variant that gives dead tiles no ring slot: 1 / 0 forced, -1 automatic */
-    MRNNT_OPT_K2_ZERO_FILL = 9   /* warps per lattice CTA that zero the gradient's dead rows while the recursions
-                                    run: 0 off (the gradient kernel writes them), 1..4, -1 automatic        */
+    MRNNT_OPT_K2_ZERO_FILL = 9   /* who zeroes the gradient's dead rows: 0 the gradient kernel's consumer warps; 1..4
+                                    that many warps per lattice CTA, while the recursions run; 32 one more warp of
+                                    the gradient kernel, next to its consumers; -1 automatic                    */
 };
 RNNTStatus mrnnt_set_option(mrnnt_handle_t h, int option, int value);
-/* What the last call actually did: MRNNT_OPT_K2_ZERO_FILL -> zero-fill warps per lattice CTA it ran with (0: the
-   gradient kernel wrote the zero rows).  Other options: RNNT_STATUS_INVALID_VALUE. */
+/* What the last call actually did: MRNNT_OPT_K2_ZERO_FILL -> 0, 1..4 or 32 as above.  Other options:
+   RNNT_STATUS_INVALID_VALUE. */
 RNNTStatus mrnnt_get_option(mrnnt_handle_t h, int option, int *value);
 /* Durations in ms of K1, K2, K3 of the last call (MRNNT_OPT_TIMING on, stream synchronised). */
 RNNTStatus mrnnt_last_timings(mrnnt_handle_t h, float ms_k1_k2_k3[3]);

@@ -3,7 +3,7 @@
 Shapes, batch sizes, vocabulary sizes, blank positions, alignment bands, layouts (packed / padded) and element types
 (float32 / bfloat16) are drawn at random from ranges that cross every dispatch boundary of the engine: one or several
 chain warps per direction (32 states each), 1..8 CTAs per utterance in the lattice kernel, streaming and generic
-kernels, tiles with and without live rows, T == S, S == 0, T == 1.
+kernels, tiles with and without live rows, T == S, S == 0, T == 1; who writes the gradient's zero rows rotates too.
 """
 import os
 
@@ -66,6 +66,9 @@ def test_random_sweep(seed):
     h = mr.LossHandle(dev_acts, torch.from_numpy(np.ascontiguousarray(labels)).cuda(),
                       torch.from_numpy(case.T).cuda(), torch.from_numpy(case.S).cuda())
     h.set_option(_lib.OPT_K2_PARTS, parts)
+    # who zeroes the dead rows: automatic, the gradient kernel's consumers, 1 / 2 warps of the lattice kernel, the
+    # gradient kernel's own zero-fill warp
+    h.set_option(_lib.OPT_K2_ZERO_FILL, (-1, 0, 1, 2, 32)[seed % 5])
     if case.alignment is not None:
         h.restrict_to_alignment(torch.from_numpy(case.alignment).cuda(), case.max_shift, case.blank)
     grads = torch.full_like(dev_acts, float("nan"))

@@ -328,6 +328,10 @@ def test_forward_into_gradient_buffer(gu, name):
     g1 = torch.full_like(acts, float("nan"))
     costs = h.enqueue_forward(wide.blank, grads=g1).clone()
     assert h.get_option(_lib.OPT_K2_ZERO_FILL) == 2
+    torch.cuda.synchronize()
+    dead = h.debug(_lib.DBG_ROWMETA) == -2
+    assert dead.any() and bool((g1[torch.from_numpy(dead).to(dev)] == 0).all()), "the forward half zeroes the dead rows"
+    assert bool(torch.isnan(g1[torch.from_numpy(~dead).to(dev)]).all()), "... and nothing else"
     h.enqueue_backward(g1)
     torch.cuda.synchronize()
     _check_costs(costs.cpu().numpy(), o64.costs)
@@ -342,6 +346,68 @@ def test_forward_into_gradient_buffer(gu, name):
     assert not torch.isnan(g2).any()
     assert np.abs(g2.cpu().numpy() - o64.grads).max() <= GRAD_ATOL
     h.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 32], ids=["k3_consumers", "k2_1warp", "k2_2warps", "k3_zero_warp"])
+@pytest.mark.parametrize("restricted", [False, True], ids=["free", "aligned"])
+def test_every_way_of_zeroing_the_dead_rows(gu, mode, restricted):
+    """MRNNT_OPT_K2_ZERO_FILL: the same gradients whoever writes the rows that are zero by construction, on a shape
+    the streaming kernels take (V = 1000), with and without an alignment band; the backward half on its own as well."""
+    import monotonic_rnnt_b200 as mr
+    from monotonic_rnnt_b200 import _lib
+    case = fixtures.random_case("zero_modes", 4242, B=6, V=1000, T_range=(20, 45), S_range=(3, 14), dist="uniform")
+    if restricted:
+        al = fixtures.random_alignment(np.random.default_rng(9), case.T, case.S, case.labels)
+        case = case.with_alignment(al, 1)
+    o64 = _oracle(case, "f64_from_f32")
+    dev = torch.device("cuda", 0)
+    acts = torch.from_numpy(case.acts).to(dev)
+    h = mr.LossHandle(acts, torch.from_numpy(case.labels).to(dev), torch.from_numpy(case.T).to(dev),
+                      torch.from_numpy(case.S).to(dev))
+    if restricted:
+        h.restrict_to_alignment(torch.from_numpy(case.alignment).to(dev), case.max_shift, case.blank)
+    h.set_option(_lib.OPT_K2_ZERO_FILL, mode)
+    for _ in range(3):   # (the hand-out counters must come back to zero after every call)
+        g = torch.full_like(acts, float("nan"))
+        costs = h.cost_and_grad(case.blank, g).numpy()
+        assert h.get_option(_lib.OPT_K2_ZERO_FILL) == mode
+        _check_costs(costs, o64.costs)
+        assert not torch.isnan(g).any()
+        assert np.abs(g.cpu().numpy() - o64.grads).max() <= GRAD_ATOL
+    # two halves, the backward one with no help from the forward one
+    g = torch.full_like(acts, float("nan"))
+    h.enqueue_forward(case.blank, want_grads=True)
+    h.enqueue_backward(g)
+    torch.cuda.synchronize()
+    assert not torch.isnan(g).any()
+    assert np.abs(g.cpu().numpy() - o64.grads).max() <= GRAD_ATOL
+    h.close()
+
+
+def test_automatic_choice_of_who_zeroes_the_dead_rows(gu):
+    """A tight alignment band (nearly all rows dead): the zero-fill warps of the LSE and gradient kernels; a band that
+    restricts nothing, or no band: the lattice kernel's fill (small shapes: its recursions are most of the call)."""
+    import monotonic_rnnt_b200 as mr
+    from monotonic_rnnt_b200 import _lib
+    case = fixtures.random_case("zero_auto", 99, B=4, V=1000, T_range=(30, 40), S_range=(10, 14), dist="uniform")
+    al = fixtures.random_alignment(np.random.default_rng(3), case.T, case.S, case.labels)
+    dev = torch.device("cuda", 0)
+    acts = torch.from_numpy(case.acts).to(dev)
+    for shift, want in ((None, 2), (0, 32), (1000, 2)):
+        c = case if shift is None else case.with_alignment(al, shift)
+        o64 = _oracle(c, "f64_from_f32")
+        h = mr.LossHandle(acts, torch.from_numpy(c.labels).to(dev), torch.from_numpy(c.T).to(dev),
+                          torch.from_numpy(c.S).to(dev))
+        if shift is not None:
+            h.restrict_to_alignment(torch.from_numpy(c.alignment).to(dev), shift, c.blank)
+        for _ in range(2):
+            g = torch.full_like(acts, float("nan"))
+            costs = h.cost_and_grad(c.blank, g).numpy()
+            assert h.get_option(_lib.OPT_K2_ZERO_FILL) == want
+            _check_costs(costs, o64.costs)
+            assert not torch.isnan(g).any()
+            assert np.abs(g.cpu().numpy() - o64.grads).max() <= GRAD_ATOL
+        h.close()
 
 
 @pytest.mark.parametrize("name,extra", [("rand_v32", (0, 0, 0)), ("rand_v32", (3, 2, 4)), ("rand_v17_shift1", (1, 5, 0)),
