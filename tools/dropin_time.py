@@ -17,12 +17,17 @@ acts = torch.empty((wl.rows, wl.V), dtype=torch.float32, device=dev)
 _lib.check(_lib.load().mrnnt_synth_uniform(acts.data_ptr(), wl.elements, 0, 0, torch.cuda.current_stream().cuda_stream), "s")
 labels = torch.from_numpy(wl.labels).to(dev); T = torch.from_numpy(wl.T).to(dev); S = torch.from_numpy(wl.S).to(dev)
 grads = torch.empty_like(acts); costs = torch.zeros(wl.B, dtype=torch.float32)
+if wl.alignment is not None:   # the align-restricted entry (monotonic_rnnt.cu:116-150)
+    al = torch.from_numpy(wl.alignment).to(dev)
+    call = lambda: mod.gpu_monotonic_rnnt_align_restrict(acts, labels, T, S, al, wl.max_shift, costs, grads, wl.blank, 0)
+else:
+    call = lambda: mod.gpu_monotonic_rnnt(acts, labels, T, S, costs, grads, wl.blank, 0)
 for _ in range(5):
-    assert mod.gpu_monotonic_rnnt(acts, labels, T, S, costs, grads, wl.blank, 0) == 0
+    assert call() == 0
 torch.cuda.synchronize(); t0 = time.perf_counter()
 n = 50
 for _ in range(n):
-    mod.gpu_monotonic_rnnt(acts, labels, T, S, costs, grads, wl.blank, 0)
+    call()
 torch.cuda.synchronize()
 ms = (time.perf_counter() - t0) / n * 1e3
 print(f"{wl.name}: reference torch binding on these headers: {ms:.3f} ms per call ({wl.B / ms * 1e3:.0f} utt/s), cost[0]={costs[0].item():.4f}")
