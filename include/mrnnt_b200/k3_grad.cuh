@@ -258,9 +258,9 @@ static __global__ void __launch_bounds__((NW + 2) * kWarp, 1)
                 const float4 c = coef_sh[stage * 32 + r];
                 uint4 *gv = reinterpret_cast<uint4 *>(grads + row * V);
                 if (c.x == kNegInfF) {
-                    // a zero row; without write_dead somebody else zeroes the rows the plan calls dead (the lattice
-                    // kernel's fill, or a zero-fill warp: zero_fill.cuh) and this is one only if it is not one of those
-                    // (k2_zero_dead_rows) and marked them in the label slot
+                    // a zero row; without write_dead somebody else zeroes the rows the plan calls dead (marked in the
+                    // label slot; the lattice kernel's fill or a zero-fill warp, zero_fill.cuh), and only a row
+                    // INSIDE the lattice that came out as zero (masked logits) is written here
                     const uint4 z = make_uint4(0u, 0u, 0u, 0u);  // +0.0 in either element type
                     if (write_dead || __float_as_int(c.w) != kRowDead)
                         for (int j = lane; j < NV; j += kWarp) st_stream_u4(gv + j, z);

@@ -20,7 +20,7 @@ static void run(const void *acts, const int *labels, const int *meta, RawRow *lp
         long long zero[32][4] = {};
         cudaMemcpyToSymbol(g_k1_trace, zero, sizeof(zero));
         cudaEventRecord(e0);
-        kern<<<148, (NW + 1) * 32, tl.smem_bytes>>>((const E *)acts, labels, meta, lp, rows, V, 0, tl.G, tl.stages);
+        kern<<<148, (NW + 1) * 32, tl.smem_bytes>>>((const E *)acts, labels, meta, lp, rows, V, 0, tl.G, tl.stages, ZeroFill{}, tl.smem_bytes);
         cudaError_t el = cudaGetLastError();
         cudaEventRecord(e1); cudaError_t es = cudaEventSynchronize(e1);
         if (rep == 0) printf("launch: %s, sync: %s\n", cudaGetErrorString(el), cudaGetErrorString(es));
