@@ -133,6 +133,13 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------
 # reference arm: the reference's CPU implementation on the host cores
 # ----------------------------------------------------------------------------------------------------
+def _host_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -145,7 +152,9 @@ def run_reference(args) -> None:
                            else None)  # the override exists for tests/test_host_cpu.py only
     kind = "reference" if oracle.have_ref() else "port"
     runner = oracle.run_ref if kind == "reference" else oracle.run
-    cores = oracle.num_threads(reference=(kind == "reference"))
+    # all the host threads this process may use, named explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers,
+    # and the reference's own default (num_threads = 0 -> omp_get_max_threads()) would then time ONE thread
+    cores = _host_threads()
     per_utt = int(wl.T[0]) * (int(wl.S[0]) + 1) * wl.V
 
     all_acts = mr.synth.uniform_logits(wl.B * per_utt, wl.logits_seed, 0)  # generated once, outside the timing
@@ -154,7 +163,7 @@ def run_reference(args) -> None:
         acts = all_acts[: B * per_utt]
         t0 = time.perf_counter()
         res = runner(acts, wl.labels[:B], wl.T[:B], wl.S[:B], wl.V, blank=wl.blank, precision="f32",
-                     want_grads=True, num_threads=0)
+                     want_grads=True, num_threads=cores)
         dt = time.perf_counter() - t0
         assert np.isfinite(res.costs).all()
         return dt
@@ -251,17 +260,37 @@ def run_b200(args) -> None:
     abi_args = (handle._h, ctypes.c_int(wl.blank), ctypes.c_void_p(stream.cuda_stream),
                 ctypes.c_void_p(costs_host.data_ptr()), ctypes.c_void_p(grads.data_ptr()))
 
+    # N > 1: the path's only collective, the all-GPU sum of the summed cost (4 bytes), is done by the kernels themselves
+    # over peer memory (monotonic_rnnt_b200/peer.py, include/mrnnt_b200/peer_reduce.cuh): the step is the SAME call as
+    # at N = 1 and returns with the costs and the world's sum on the host.  If the boards cannot be mapped (no CUDA IPC
+    # between the ranks) the step falls back to an NCCL all-reduce on a side stream; the JSON line says which.
+    boards, collective = None, "none (1 GPU)"
+    if world > 1:
+        collective = "fused: peer-memory stores from the gradient kernel (NVLink), no collective kernel"
+        try:
+            if args.collective == "nccl":
+                raise _lib.RNNTError(0, "--collective nccl")
+            boards = mr.peer.PeerBoards(device=dev)
+            handle.set_peer_reduce(boards, cost_sum_host)
+        except _lib.RNNTError as exc:
+            boards = None
+            collective = f"nccl all-reduce on a side stream ({exc})"
+        flag = torch.tensor([1 if boards is not None else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)     # all ranks take the same path
+        if int(flag.item()) == 0 and boards is not None:
+            handle.set_peer_reduce(None, None)
+            boards = None
+            collective = "nccl all-reduce on a side stream (a peer could not map the boards)"
+
     def one_step():
-        if world == 1:
-            st = abi_call(*abi_args)  # costs on the host on return (one stream synchronisation inside)
+        if world == 1 or boards is not None:
+            st = abi_call(*abi_args)  # costs (and the world's sum) on the host on return (one stream synchronisation inside)
             if st != 0:
                 _lib.check(st, "mrnnt_cost_and_grad")
             return
-        # N > 1: the same three kernels without a host round trip in between.  The costs are final after K2, so the
-        # path's only collective (all-reduce of the summed cost, 4 bytes over NVLink) and the copies of the costs to
-        # the host run on a side stream / NCCL's stream WHILE K3 streams the gradients on the compute stream
-        # (measured: no SM needs to be set aside for them); ONE host synchronisation at the end of the step, at
-        # which the gradients are complete and the per-utterance costs and the global sum are on the host.
+        # Fallback at N > 1: the same three kernels without a host round trip in between.  The costs are final after
+        # K2, so the all-reduce and the copies of the costs to the host run on a side stream / NCCL's stream next to K3
+        # on the compute stream; ONE host synchronisation at the end of the step.
         st = fwd_call(*fwd_args)                       # K1, K2
         if st != 0:
             _lib.check(st, "mrnnt_enqueue_forward_into")
@@ -311,6 +340,15 @@ def run_b200(args) -> None:
         dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
     ms_per_step = float(ms_total.item()) / args.steps
     value = world * wl.B / (ms_per_step / 1000.0)
+    # the world's sum as the kernels exchanged it, against a library all-reduce of the same costs (outside the timing)
+    collective_check = None
+    if world > 1:
+        fused_total = float(cost_sum_host.item())
+        want = torch.tensor([float(costs_host.double().sum())], dtype=torch.float64, device=dev)
+        dist.all_reduce(want)
+        collective_check = {"world_sum": fused_total, "nccl_f64_sum_of_the_same_costs": float(want.item()),
+                            "rel_diff": abs(fused_total - float(want.item())) / abs(float(want.item()))}
+        assert collective_check["rel_diff"] < 1e-5, collective_check
 
     # ---- the same K steps through the asynchronous entry (mrnnt_enqueue: costs stay on the device, no host round trip
     #      per step, one synchronisation at the end): what a training loop that never looks at the costs sees ----
@@ -389,10 +427,15 @@ def run_b200(args) -> None:
         T.copy_(T_h, non_blocking=True)
         S.copy_(S_h, non_blocking=True)
         h = mr.LossHandle(acts, labels, T, S, lengths_host=(wl.T, wl.S))
-        h.cost_and_grad(wl.blank, grads, costs_host)     # returns with the costs on the host
+        if boards is not None:
+            h.set_peer_reduce(boards, cost_sum_host)     # (a new handle takes the boards over at their epoch)
+        h.cost_and_grad(wl.blank, grads, costs_host)     # returns with the costs (and the world's sum) on the host
+        h.sync_peer_epoch()
         h.close()
 
     e2e_steps = max(3, min(args.steps, 20))
+    if boards is not None:
+        handle.sync_peer_epoch()
     e2e_step()
     barrier()
     if clocks:
@@ -418,14 +461,14 @@ def run_b200(args) -> None:
         oracle.build()
         kind = "reference" if oracle.have_ref() else "port"
         runner = oracle.run_ref if kind == "reference" else oracle.run
-        cores = oracle.num_threads(reference=(kind == "reference"))
+        cores = _host_threads()
         acts_np = acts_h.numpy()
         times, res = [], None
         t_budget = time.perf_counter()
         for i in range(3):
             t1 = time.perf_counter()
             res = runner(acts_np, wl.labels, wl.T, wl.S, wl.V, blank=wl.blank, precision="f32", want_grads=True,
-                         num_threads=0)
+                         num_threads=cores)
             times.append(time.perf_counter() - t1)
             if time.perf_counter() - t_budget > 20.0:
                 break
@@ -470,7 +513,8 @@ def run_b200(args) -> None:
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": _config(wl),
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": _config(wl, {"collective": collective}),
+        "collective_check": collective_check,
         "roofline": {"kernel": "k3_grad_tma_kernel", "bound": "hbm", "achieved": k3_gbs, "peak": peak, "unit": "GB/s",
                      "frac": k3_gbs / peak, "traffic": _traffic("k3_grad_tma_kernel"), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": k3_bytes, "ms_per_launch": float(k_ms[2]),
@@ -519,6 +563,8 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-CPU baseline/checker leg")
+    ap.add_argument("--collective", choices=["fused", "nccl"], default="fused",
+                    help="N > 1: the sum of the costs over peer memory inside the gradient kernel, or NCCL on a side stream")
     ap.add_argument("--reserve-sms", type=int, default=0,
                     help="N > 1: SMs the gradient kernel leaves to the concurrent all-reduce")
     args = ap.parse_args()

@@ -384,12 +384,15 @@ class Engine {
             shared_fill_ctr_ = pair + (shared_seq_ & 1u);
             shared_fill_clear_ = pair + ((shared_seq_ + 1u) & 1u);
         }
+        // the all-GPU sum of the costs (set_peer_reduce): inside the gradient kernel when there is one
+        peer_in_k3_ = peer_.world > 0 && grads_dev != nullptr;
         RNNTStatus st = enqueue_forward(blank, stream, grads_dev != nullptr, grads_dev);
         if (st == RNNT_STATUS_SUCCESS && grads_dev != nullptr) {
             k3_follows_k2_ = !timing_;  // (the timing events between the kernels would break the dependent launch)
             st = enqueue_backward(stream, grads_dev, nullptr);
             k3_follows_k2_ = false;
         }
+        peer_in_k3_ = false;
         shared_fill_ctr_ = shared_fill_clear_ = nullptr;
         return st;
     }
@@ -417,8 +420,35 @@ class Engine {
         mark(2, stream);
         mark(3, stream);
         if (want_grads) coef_blank_ = blank;
+        // a forward half or a cost-only call: no gradient kernel to carry the exchange, it gets a launch of its own
+        if (peer_.world > 0 && !peer_in_k3_) {
+            peer_reduce_kernel<<<1, kWarp, 0, stream>>>(peer_args(true));
+            if (launched() != RNNT_STATUS_SUCCESS) return RNNT_STATUS_EXECUTION_FAILED;
+        }
         return RNNT_STATUS_SUCCESS;
     }
+
+    // The all-GPU sum of the summed cost without a collective library (peer_reduce.cuh): `boards[r]` is rank r's board
+    // (peer_board_bytes(world) zeroed bytes of device memory) as mapped into this process, `total_out` (device or
+    // host-mapped, may be nullptr) receives the world's sum with every one-shot call and every forward half from now
+    // on.  All ranks must make the same sequence of such calls.  world == 0 turns it off.
+    RNNTStatus set_peer_reduce(int rank, int world, void *const *boards, float *total_out) {
+        peer_ = PeerReduce{};
+        if (world == 0) return RNNT_STATUS_SUCCESS;
+        if (world < 0 || world > kPeerMaxWorld || rank < 0 || rank >= world || boards == nullptr) return RNNT_STATUS_INVALID_VALUE;
+        for (int r = 0; r < world; ++r) {
+            if (boards[r] == nullptr || (reinterpret_cast<uintptr_t>(boards[r]) & 7)) return RNNT_STATUS_INVALID_VALUE;
+            peer_.boards[r] = static_cast<unsigned long long *>(boards[r]);
+        }
+        peer_.rank = rank;
+        peer_.world = world;
+        peer_.total_out = total_out;
+        peer_.epoch = 0u;
+        return RNNT_STATUS_SUCCESS;
+    }
+    // Steps already exchanged through the boards by ANOTHER handle (the epoch belongs to the boards, not to the handle).
+    void set_peer_epoch(unsigned epoch) { peer_.epoch = epoch; }
+    unsigned peer_epoch() const { return peer_.epoch; }
 
     // Second half: K3, the gradient w.r.t. the logits.  scale_dev (optional, B floats on the device): utterance
     // b's gradient rows are multiplied by scale_dev[b] as they are written -- the upstream gradient of the
@@ -473,6 +503,7 @@ class Engine {
     void set_reserved_sms(int n) { reserved_sms_ = n < 0 ? 0 : n; }
     int last_k2_zero_warps() const { return last_k2_zero_warps_; }
     void set_k2_zero_fill(int warps) { k2_zero_warps_ = warps; }
+    void set_dynamic_tiles(int mode) { dynamic_tiles_ = mode < 0 ? -1 : (mode != 0); }
     // Upper limit for the CTAs per utterance of the lattice kernel's coefficient phase (0: automatic).
     void set_k2_parts(int parts) { k2_parts_ = parts < 0 ? 0 : parts; }
     // Consumer warps per CTA of the streaming kernels (8 or 16); tuning knob for the bench.
@@ -558,6 +589,21 @@ class Engine {
     bool k1_compact(const StreamTiling &tl) const {
         if (k1_compact_ >= 0) return k1_compact_ != 0;
         return alignment_ != nullptr || shape_.U > 0 || tl.G <= 4;
+    }
+
+    // The gradient kernel's tiles handed out through a counter instead of round-robin by CTA index (kK3Dynamic,
+    // k3_grad.cuh).  What it removes is the end of the kernel, where the CTAs of a fixed split finish up to ~15 us apart
+    // (ncu: SMs active 91 % of the kernel's duration on c2); what it costs, measured, is a few percent of streaming
+    // rate on long inputs.  tools/kernel_times.py --dyn 0,1: c2 K3 205 -> 191 us, bfloat16 c2 unchanged, c3 1290 ->
+    // 1368 us, c4 4469 -> 4588 us, c5 (alignment band, most tiles dead: one request per dead tile) 521 -> 664 us.
+    // Hence: dense inputs of up to kDynamicTilesPerCta tiles per CTA.
+    static constexpr int64_t kDynamicTilesPerCta = 400;
+    bool dynamic_tiles(const StreamTiling &tl) const {
+        const int64_t ntiles = (shape_.rows + tl.G - 1) / tl.G;
+        const int64_t sms = device_info().sm_count;
+        if (ntiles + 16 * sms >= (int64_t(1) << 31)) return false;
+        if (dynamic_tiles_ >= 0) return dynamic_tiles_ != 0;
+        return alignment_ == nullptr && shape_.U == 0 && ntiles <= kDynamicTilesPerCta * sms;
     }
 
     template <typename E, int NW, int C>
@@ -732,8 +778,9 @@ class Engine {
 
     // (dead tiles are skipped under the same conditions as in K1, and only when nobody has to zero them here)
     int k3_flags(const StreamTiling &tl) const {
-        if (k3_write_dead_) return kK3WriteDead;
-        return k1_compact(tl) ? kK3Compact : 0;
+        const int dyn = dynamic_tiles(tl) ? kK3Dynamic : 0;
+        if (k3_write_dead_) return kK3WriteDead | dyn;
+        return dyn ? dyn : (k1_compact(tl) ? kK3Compact : 0);
     }
 
     template <typename E, int NW, bool SCALED>
@@ -757,7 +804,8 @@ class Engine {
         // predecessor to wait for, and an ordinary launch orders it behind whatever precedes it in the stream)
         if (launch_kernel(kern, grid, (NW + (zero_warp ? 2 : 1)) * kWarp, smem, stream, pdl_ && k3_follows_k2_,
                           static_cast<const E *>(acts_), ws_.coef, static_cast<E *>(grads), shape_.rows, V_, blank, tl.G,
-                          tl.stages, ws_.rowutt, scale, cost_mirror(), flags, zero, tl.smem_bytes) != cudaSuccess)
+                          tl.stages, ws_.rowutt, scale, cost_mirror(), flags, zero, tl.smem_bytes,
+                          ws_.k2_flags + stream_ctr_word(B_), peer_args(peer_in_k3_)) != cudaSuccess)
             return RNNT_STATUS_EXECUTION_FAILED;
         return launched();
     }
@@ -776,7 +824,7 @@ class Engine {
         }
         k3_grad_generic_kernel<E><<<generic_grid(dev), kGenericWarps * kWarp, 0, stream>>>(
             static_cast<const E *>(acts_), ws_.coef, static_cast<E *>(grads), shape_.rows, V_, blank, ws_.rowutt, scale,
-            cost_mirror());
+            cost_mirror(), peer_args(peer_in_k3_));
         return launched();
     }
 
@@ -786,6 +834,17 @@ class Engine {
     }
 
     size_t elem_bytes() const { return bf16_ ? 2 : 4; }
+
+    // the exchange of this call (a new epoch), or none
+    PeerReduce peer_args(bool active) {
+        PeerReduce p{};
+        if (!active || peer_.world <= 0) return p;
+        if (++peer_.epoch == 0u) peer_.epoch = 2u;  // (0 is the boards' initial state; keep the parity sequence)
+        p = peer_;
+        p.costs = ws_.costs;
+        p.B = B_;
+        return p;
+    }
 
     // who copies the costs into a synchronous call's host-mapped staging buffer: the gradient kernel when there is
     // one (the write then overlaps it), else the lattice kernel
@@ -823,6 +882,7 @@ class Engine {
     bool force_generic_ = false;
     int k1_warps_ = 24;
     int k1_compact_ = -1;  // -1: automatic (k1_compact()), 0 / 1: forced
+    int dynamic_tiles_ = -1;  // the gradient kernel's tiles through a counter: -1 automatic (dynamic_tiles()), 0 / 1 forced
     int k3_warps_ = 24;
     int k2_parts_ = 0;     // 0: automatic
     int k2_occ_ = 0;       // CTAs of the lattice kernel per SM for (k2_occ_kernel_, k2_occ_smem_)
@@ -839,6 +899,8 @@ class Engine {
     unsigned shared_seq_ = 0u;
     int last_k2_zero_warps_ = 0;        // what the last lattice launch ran with
     int k2_zero_warps_ = -1;            // warps per lattice CTA for the zero fill: -1 automatic, 0 off
+    PeerReduce peer_{};           // set_peer_reduce(): world > 0 when on; epoch = the last one used
+    bool peer_in_k3_ = false;     // this call's exchange rides in the gradient kernel
     bool k3_follows_k2_ = false;  // K3 is being enqueued directly behind K2 (enqueue(), not a separate backward)
     unsigned epoch_ = 0u;  // launch counter published through Workspace::k2_flags
     float *costs_mapped_ = nullptr;  // set for the duration of a synchronous compute(): host-mapped copy of the costs

@@ -194,6 +194,44 @@ __device__ long long g_k1_trace[32][4];  // per warp: cycles waiting, cycles wor
 #define MRNNT_K1_ADD(w, i, v) do { } while (0)
 #endif
 
+// Dynamic tile hand-out (the gradient kernel's producer, kK3Dynamic in k3_grad.cuh): tiles come from a counter,
+// `kGrabDepth` requests in flight per producer -- an atomic on one hot word takes microseconds to come back while the GPU
+// streams at full bandwidth, a tile lasts about one.  The first two tiles of a CTA are fixed (blockIdx.x, blockIdx.x + gridDim.x), the counter hands
+// out the ones from 2 * gridDim.x on, in order: the CTAs keep working on one moving window of the input.
+constexpr int kGrabDepth = 8;
+struct TileGrabber {
+    unsigned raw[kGrabDepth];
+    unsigned *ctr;  // {tiles handed out, producers finished}; zero between launches
+    int lane;
+    __device__ __forceinline__ unsigned grab() { return lane == 0 ? atomicAdd(ctr, 1u) : 0u; }
+    __device__ __forceinline__ void start(unsigned *c, int l) {
+        ctr = c;
+        lane = l;
+#pragma unroll
+        for (int i = 0; i < kGrabDepth; ++i) raw[i] = grab();
+    }
+    // the next tile (warp-uniform), and one more request
+    __device__ __forceinline__ int64_t next() {
+        const int64_t t = static_cast<int64_t>(__shfl_sync(0xffffffffu, raw[0], 0)) + 2 * static_cast<int64_t>(gridDim.x);
+#pragma unroll
+        for (int i = 0; i + 1 < kGrabDepth; ++i) raw[i] = raw[i + 1];
+        raw[kGrabDepth - 1] = grab();
+        return t;
+    }
+    // The last producer to finish leaves the counters as it found them (every request of this launch has been
+    // answered by then: a producer looks at its own outstanding ones before it reports).
+    __device__ __forceinline__ void finish() {
+        unsigned seen = 0u;
+#pragma unroll
+        for (int i = 0; i < kGrabDepth; ++i) seen |= __shfl_sync(0xffffffffu, raw[i], 0);
+        if (lane == 0 && atomicAdd(ctr + 1, (seen & 0u) + 1u) == gridDim.x - 1u) {
+            ctr[0] = 0u;
+            ctr[1] = 0u;
+            __threadfence();
+        }
+    }
+};
+
 struct StreamTiling {
     int G = 0;       // rows per tile: a power of two in 1..32
     int stages = 0;  // ring depth
@@ -325,9 +363,9 @@ static __global__ void __launch_bounds__((NW + (COMPACT ? 2 : 1)) * kWarp, 1)
             const int64_t row = (blockIdx.x + k * gridDim.x) * G + (lane % G);
             return (k < nloc && row < rows) ? __ldg(rowmeta + row) : kRowDead;
         };
-        int mb0 = load_batch(0), mb1 = load_batch(TPB);
         int stage = 0;
         uint32_t phase = 0;
+        int mb0 = load_batch(0), mb1 = load_batch(TPB);
         for (int64_t k0 = 0; k0 < nloc; k0 += TPB) {
             const int mb = mb0;
             mb0 = mb1;

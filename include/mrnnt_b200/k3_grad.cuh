@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "zero_fill.cuh"
 #include "k1_lse.cuh"
+#include "peer_reduce.cuh"
 
 namespace mrnnt {
 
@@ -60,8 +61,10 @@ template <typename E>
 static __global__ void __launch_bounds__(kGenericWarps * kWarp)
     k3_grad_generic_kernel(const E *__restrict__ acts, const float4 *__restrict__ coef, E *__restrict__ grads,
                            int64_t rows, int V, int blank, const int *__restrict__ rowutt,
-                           const float *__restrict__ scale, CostMirror mirror) {
+                           const float *__restrict__ scale, CostMirror mirror, PeerReduce peer) {
     mirror_costs(mirror, blockDim.x);
+    const bool peer_warp = blockIdx.x == 0 && threadIdx.x < kWarp;  // (peer_reduce.cuh)
+    if (peer_warp) peer_publish(peer);
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * kGenericWarps + (threadIdx.x >> 5);
     const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kGenericWarps;
@@ -83,6 +86,7 @@ static __global__ void __launch_bounds__(kGenericWarps * kWarp)
             g[v] = Elem<E>::from_float(gv * sc);
         }
     }
+    if (peer_warp) peer_collect(peer);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -94,6 +98,11 @@ static __global__ void __launch_bounds__(kGenericWarps * kWarp)
 constexpr int kK3WriteDead = 1;  // write the zero rows (off: somebody else zeroes the rows the plan calls dead)
 constexpr int kK3Compact = 2;    // tiles without a live row take no ring slot (needs kK3WriteDead off)
 constexpr int kK3ZeroShared = 4; // the zero-fill warp continues a fill the LSE kernel's zero-fill warp has begun
+constexpr int kK3Dynamic = 8;    // tiles are handed out through a counter (`dyn`) instead of round-robin by CTA index: a
+                                 // CTA on an SM that streams faster takes more of them, and the kernel ends when the
+                                 // work does, not when the unluckiest CTA has got through its fixed share.  The first
+                                 // two tiles of a CTA are fixed (no waiting for the counter at the start); the slots
+                                 // carry their tile's index as in the compact mode, which this mode includes
 // With a ZeroFill (dst != nullptr) the kernel is launched with one more warp, which zeroes the plan's dead rows next to
 // the consumer warps (zero_fill.cuh) out of kZeroFillBytes of shared memory behind the ring: where nearly all rows
 // are dead, writing the zeros takes longer than everything else, and it need not wait for anything.
@@ -105,7 +114,8 @@ template <typename E, int NW, bool SCALED>
 static __global__ void __launch_bounds__((NW + 2) * kWarp, 1)
     k3_grad_tma_kernel(const E *__restrict__ acts, const float4 *__restrict__ coef, E *__restrict__ grads,
                        int64_t rows, int V, int blank, int G, int stages, const int *__restrict__ rowutt,
-                       const float *__restrict__ scale, CostMirror mirror, int flags, ZeroFill zero, size_t ring_bytes) {
+                       const float *__restrict__ scale, CostMirror mirror, int flags, ZeroFill zero, size_t ring_bytes,
+                       unsigned *__restrict__ dyn, PeerReduce peer) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NE = Elem<E>::kPerVec;
     const size_t tile_elems = static_cast<size_t>(G) * V;
@@ -135,13 +145,19 @@ static __global__ void __launch_bounds__((NW + 2) * kWarp, 1)
     }
     pdl_wait();  // the coefficients come from the lattice kernel; everything above overlapped its tail
     mirror_costs(mirror, (NW + 1) * kWarp);
+    // the sum of this GPU's costs goes out to the peers now and the world's sum is picked up when this warp has got
+    // through its rows (peer_reduce.cuh): the exchange rides along with the gradient pass
+    const bool peer_warp = blockIdx.x == 0 && warp == 0;
+    if (peer_warp) peer_publish(peer);
 
     const int64_t ntiles = (rows + G - 1) / G;
     const int64_t nloc = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const bool write_dead = (flags & kK3WriteDead) != 0;
     // compact (only without write_dead): tiles without a live row take no ring slot; the slots carry their tile's
     // index, the consumers walk the slots and stop at a terminator (as in the LSE kernel's COMPACT variant)
-    const bool compact = (flags & kK3Compact) != 0;
+    const bool dynamic = (flags & kK3Dynamic) != 0;
+    const bool compact = (flags & kK3Compact) != 0 && !dynamic;
+    const bool slot_names_tile = compact || dynamic;
 
     if (warp == NW) {
         // ---------------- producer warp ----------------
@@ -149,7 +165,7 @@ static __global__ void __launch_bounds__((NW + 2) * kWarp, 1)
         int stage = 0;
         uint32_t phase = 0;
         auto fill_slot = [&](int64_t k, const float4 &c, float sc, uint32_t mask) {
-            const int64_t row0 = (blockIdx.x + k * gridDim.x) * G;
+            const int64_t row0 = (dynamic ? k : blockIdx.x + k * gridDim.x) * G;  // (dynamic: k is the tile itself)
             mbar_wait(empty + stage, phase ^ 1u);
             coef_sh[stage * 32 + lane] = c;
             if (SCALED) scale_sh[stage * 32 + lane] = sc;
@@ -165,7 +181,42 @@ static __global__ void __launch_bounds__((NW + 2) * kWarp, 1)
                 phase ^= 1u;
             }
         };
-        if (!compact) {
+        if (dynamic) {
+            TileGrabber grabber;  // (k1_lse.cuh)
+            grabber.start(dyn, lane);
+            auto load_coef = [&](int64_t tile) {
+                const int64_t row = tile * G + lane;
+                return (tile < ntiles && lane < G && row < rows) ? __ldg(coef + row) : make_float4(kNegInfF, 0.f, 0.f, 0.f);
+            };
+            auto load_scale = [&](int64_t tile) {
+                const int64_t row = tile * G + lane;
+                return (SCALED && tile < ntiles && lane < G && row < rows) ? __ldg(scale + __ldg(rowutt + row)) : 1.0f;
+            };
+            int64_t t0 = blockIdx.x, t1 = static_cast<int64_t>(blockIdx.x) + gridDim.x;
+            float4 c0 = load_coef(t0), c1 = load_coef(t1);
+            float s0 = load_scale(t0), s1 = load_scale(t1);
+            while (t0 < ntiles) {
+                const int64_t t2 = grabber.next();
+                const float4 c2 = load_coef(t2);
+                const float s2 = load_scale(t2);
+                const uint32_t mask = __ballot_sync(0xffffffffu, !(c0.x == kNegInfF));
+                if (write_dead || mask != 0u) fill_slot(t0, c0, s0, mask);
+                t0 = t1; c0 = c1; s0 = s1;
+                t1 = t2; c1 = c2; s1 = s2;
+            }
+            for (int i = 0; i < stages; ++i) {  // one terminator per slot, as in the compact mode
+                mbar_wait(empty + stage, phase ^ 1u);
+                if (lane == 0) {
+                    tile_sh[stage] = -1;
+                    mbar_arrive_expect_tx(full + stage, 0u);
+                }
+                if (++stage == stages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+            grabber.finish();
+        } else if (!compact) {
             auto load_coef = [&](int64_t k) {
                 const int64_t row = (blockIdx.x + k * gridDim.x) * G + lane;
                 return (k < nloc && lane < G && row < rows) ? __ldg(coef + row) : make_float4(kNegInfF, 0.f, 0.f, 0.f);
@@ -245,15 +296,15 @@ static __global__ void __launch_bounds__((NW + 2) * kWarp, 1)
         // q walks the rows of the slot uses u = 0, 1, ... in order (G rows each)
         const int NV = V / NE;
         const int64_t nq = nloc * G;
-        for (int64_t q = warp; compact || q < nq; q += NW) {
+        for (int64_t q = warp; slot_names_tile || q < nq; q += NW) {
             const int64_t u = q / G;
             const int r = static_cast<int>(q - u * G);
             const int stage = static_cast<int>(u % stages);
             const uint32_t phase = static_cast<uint32_t>((u / stages) & 1);
             mbar_wait(full + stage, phase);
-            const int64_t k = compact ? tile_sh[stage] : u;
+            const int64_t k = slot_names_tile ? tile_sh[stage] : u;
             if (k < 0) break;
-            const int64_t row = (blockIdx.x + k * gridDim.x) * G + r;
+            const int64_t row = (dynamic ? k : blockIdx.x + k * gridDim.x) * G + r;
             if (row < rows) {
                 const float4 c = coef_sh[stage * 32 + r];
                 uint4 *gv = reinterpret_cast<uint4 *>(grads + row * V);
@@ -290,6 +341,7 @@ static __global__ void __launch_bounds__((NW + 2) * kWarp, 1)
             __syncwarp();
             if (lane == 0) mbar_arrive(empty + stage);
         }
+        if (peer_warp) peer_collect(peer);
     }
 }
 

@@ -60,7 +60,10 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 // counters of the zero fill (zero_fill.cuh): two of the OWNED protocol, then the two alternating ones of the SHARED
 // protocol
 __host__ __device__ inline size_t k2_zero_ctr_word(int B) { return (2 * static_cast<size_t>(B) + 63) / 64 * 64 + 64; }
-__host__ __device__ inline size_t k2_flag_words(int B) { return k2_zero_ctr_word(B) + 4; }
+// ... and, a cache line further on, the tile hand-out counter of the gradient kernel's dynamic mode (k3_grad.cuh):
+// {tiles handed out, producers finished}; zero between launches
+__host__ __device__ inline size_t stream_ctr_word(int B) { return k2_zero_ctr_word(B) + 64; }
+__host__ __device__ inline size_t k2_flag_words(int B) { return stream_ctr_word(B) + 4; }
 inline size_t workspace_bytes(const Shape &sh) {
     const size_t rows = static_cast<size_t>(sh.rows);
     const size_t B = static_cast<size_t>(sh.B);

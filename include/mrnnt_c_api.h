@@ -87,6 +87,30 @@ RNNTStatus mrnnt_enqueue_backward(mrnnt_handle_t h, void *stream, float *gradien
  * same pointer, only writes the others.  The buffer must not be written in between. */
 RNNTStatus mrnnt_enqueue_forward_into(mrnnt_handle_t h, int blank_label, void *stream, float *gradients);
 
+/* ---- multi-GPU: the all-GPU sum of the summed cost, the path's only collective ------------------------
+ * Done by the kernels themselves over peer memory (NVLink / NVSwitch) instead of by a collective library's kernel
+ * behind them (include/mrnnt_b200/peer_reduce.cuh): every rank owns a "board" of a few bytes in device memory, mapped
+ * into all peers with CUDA IPC.  One process per GPU:
+ *   1. mrnnt_peer_board_create(world, &own, handle)       own board (zeroed) + its 64-byte IPC handle
+ *   2. exchange the handles (any host-side transport), mrnnt_peer_board_open(handle_r, &boards[r]) for r != rank,
+ *      boards[rank] = own; a host barrier, so that nobody publishes into a board that is not there yet
+ *   3. mrnnt_set_peer_reduce(h, rank, world, boards, total_out, epoch) on every handle that takes part
+ * From then on every mrnnt_cost_and_grad / mrnnt_enqueue / mrnnt_enqueue_forward[_into] of that handle also leaves
+ * sum_over_ranks(sum_b cost_b) in *total_out (device or host-mapped pinned memory; NULL: nowhere): with gradients the
+ * exchange rides inside the gradient kernel (one store per peer when the costs are final, one poll at the kernel's
+ * end), else in a one-warp launch behind the lattice kernel.  All ranks must make the same sequence of such calls
+ * (it is a collective).  The epoch counts the exchanges a set of boards has carried: pass 0 for fresh boards, and
+ * when a NEW handle takes over boards already in use, mrnnt_peer_epoch() of the handle that used them last.
+ * A rank whose peers do not show up within 2 s gets NaN instead of hanging the GPU.  world <= 8 (one NVSwitch
+ * domain); in one process (several handles on one device or on peer-enabled devices) plain device pointers do. */
+RNNTStatus mrnnt_peer_board_create(int world, void **board_dev, unsigned char ipc_handle[64]);
+RNNTStatus mrnnt_peer_board_open(const unsigned char ipc_handle[64], void **peer_ptr);
+RNNTStatus mrnnt_peer_board_close(void *peer_ptr);
+RNNTStatus mrnnt_peer_board_destroy(void *board_dev);
+RNNTStatus mrnnt_set_peer_reduce(mrnnt_handle_t h, int rank, int world, void *const *boards, float *total_out,
+                                 unsigned epoch);
+unsigned mrnnt_peer_epoch(mrnnt_handle_t h);
+
 /* One-shot convenience: size check + set_workspace + optional restrict_to_alignment + cost_and_grad. */
 RNNTStatus rnnt_loss_grad_gpu(const float *acts, const int *labels, const int *T_dev, const int *S_dev,
                               const int *T_host, const int *S_host, int B, int V, int blank_label,
@@ -103,9 +127,11 @@ enum {
     MRNNT_OPT_RESERVED_SMS = 6,  /* SMs the gradient kernel leaves free for a concurrent collective (0)    */
     MRNNT_OPT_PDL = 7,           /* programmatic dependent launch of K2 behind K1 and K3 behind K2 (1)     */
     MRNNT_OPT_K1_COMPACT = 8,    /* K1 variant that gives dead tiles no ring slot: 1 / 0 forced, -1 automatic */
-    MRNNT_OPT_K2_ZERO_FILL = 9   /* who zeroes the gradient's dead rows: 0 the gradient kernel's consumer warps; 1..4
+    MRNNT_OPT_K2_ZERO_FILL = 9,  /* who zeroes the gradient's dead rows: 0 the gradient kernel's consumer warps; 1..4
                                     that many warps per lattice CTA, while the recursions run; 32 one more warp of
                                     the gradient kernel, next to its consumers; -1 automatic                    */
+    MRNNT_OPT_DYNAMIC_TILES = 10 /* the gradient kernel hands its tiles out through a counter instead of round-robin by
+                                    CTA index: 1 / 0 forced, -1 automatic                                       */
 };
 RNNTStatus mrnnt_set_option(mrnnt_handle_t h, int option, int value);
 /* What the last call actually did: MRNNT_OPT_K2_ZERO_FILL -> 0, 1..4 or 32 as above.  Other options:

@@ -5,7 +5,7 @@ The package is a thin host-side mirror of the reference's PyTorch operator inter
 (include/mrnnt_c_api.h).  The directory name carries a hyphen, so import it as
 ``monotonic_rnnt_b200`` (the shim module of that name at the repository root does the loading).
 """
-from . import _lib, build, shard, synth  # noqa: F401
+from . import _lib, build, peer, shard, synth  # noqa: F401
 from ._lib import RNNTError  # noqa: F401
 from .rnnt_op import (  # noqa: F401
     LossHandle,
@@ -16,4 +16,4 @@ from .rnnt_op import (  # noqa: F401
 )
 
 __all__ = ["LossHandle", "MonotonicRNNTFunction", "MonotonicRNNTLoss", "monotonic_rnnt_loss", "workspace_size",
-           "RNNTError", "build", "shard", "synth"]
+           "RNNTError", "build", "peer", "shard", "synth"]

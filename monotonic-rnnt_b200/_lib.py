@@ -22,6 +22,7 @@ OPT_RESERVED_SMS = 6
 OPT_PDL = 7
 OPT_K1_COMPACT = 8
 OPT_K2_ZERO_FILL = 9
+OPT_DYNAMIC_TILES = 10
 DBG_DENOM, DBG_ALPHA, DBG_BETA, DBG_LP, DBG_BAND, DBG_ROWMETA, DBG_LL, DBG_ROWSTART = range(1, 9)
 
 # every symbol include/mrnnt_c_api.h and include/rnnt_entrypoint.h declare
@@ -32,6 +33,8 @@ EXPORTED_SYMBOLS = (
     "mrnnt_debug_copy", "mrnnt_synth_uniform", "mrnnt_build_info", "mrnnt_last_timings",
     "mrnnt_enqueue_forward", "mrnnt_enqueue_backward", "mrnnt_enqueue_forward_into", "mrnnt_create_padded",
     "mrnnt_get_workspace_size_padded", "mrnnt_set_dtype",
+    "mrnnt_peer_board_create", "mrnnt_peer_board_open", "mrnnt_peer_board_close", "mrnnt_peer_board_destroy",
+    "mrnnt_set_peer_reduce", "mrnnt_peer_epoch",
 )
 
 
@@ -73,6 +76,16 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mrnnt_debug_copy.argtypes = [vp, ci, vp, sz]
     lib.mrnnt_last_timings.argtypes = [vp, vp]
     lib.mrnnt_synth_uniform.argtypes = [vp, ctypes.c_int64, ctypes.c_uint64, ctypes.c_int64, vp]
+    lib.mrnnt_peer_board_create.argtypes = [ci, ctypes.POINTER(vp), vp]
+    lib.mrnnt_peer_board_open.argtypes = [vp, ctypes.POINTER(vp)]
+    lib.mrnnt_peer_board_close.argtypes = [vp]
+    lib.mrnnt_peer_board_destroy.argtypes = [vp]
+    lib.mrnnt_set_peer_reduce.argtypes = [vp, ci, ci, ctypes.POINTER(vp), vp, ctypes.c_uint]
+    lib.mrnnt_peer_epoch.argtypes = [vp]
+    lib.mrnnt_peer_epoch.restype = ctypes.c_uint
+    for name in ("mrnnt_peer_board_create", "mrnnt_peer_board_open", "mrnnt_peer_board_close",
+                 "mrnnt_peer_board_destroy", "mrnnt_set_peer_reduce"):
+        getattr(lib, name).restype = ci
     lib.mrnnt_build_info.argtypes = []
     lib.mrnnt_build_info.restype = ctypes.c_char_p
     for name in ("mrnnt_get_workspace_size", "mrnnt_create", "mrnnt_workspace_size", "mrnnt_set_workspace",

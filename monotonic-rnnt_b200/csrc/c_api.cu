@@ -7,6 +7,7 @@
 // All of them are thin shells over mrnnt::Engine (include/mrnnt_b200/engine.cuh), which is header-only
 // so that the reference's framework bindings can compile the same kernels from `-I include` alone.
 #include <cstdio>
+#include <cstring>
 #include <new>
 #include <vector>
 
@@ -239,6 +240,9 @@ RNNTStatus mrnnt_set_option(mrnnt_handle_t h, int option, int value) {
         case MRNNT_OPT_K2_ZERO_FILL:
             h->manager.engine().set_k2_zero_fill(value);
             return RNNT_STATUS_SUCCESS;
+        case MRNNT_OPT_DYNAMIC_TILES:
+            h->manager.engine().set_dynamic_tiles(value);
+            return RNNT_STATUS_SUCCESS;
         default:
             return RNNT_STATUS_INVALID_VALUE;
     }
@@ -323,6 +327,63 @@ RNNTStatus mrnnt_debug_copy(mrnnt_handle_t h, int what, void *dst_host, size_t d
     if (cudaMemcpy(dst_host, src, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return RNNT_STATUS_MEMOPS_FAILED;
     return RNNT_STATUS_SUCCESS;
 }
+
+/* ---- the all-GPU sum of the summed cost over peer memory (include/mrnnt_b200/peer_reduce.cuh) ---- */
+RNNTStatus mrnnt_peer_board_create(int world, void **board_dev, unsigned char ipc_handle[64]) {
+    if (board_dev == nullptr || world <= 0 || world > mrnnt::kPeerMaxWorld) return RNNT_STATUS_INVALID_VALUE;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the C ABI carries the IPC handle as 64 bytes");
+    void *p = nullptr;
+    // (an allocation of its own: an IPC handle names a whole cudaMalloc block)
+    if (cudaMalloc(&p, mrnnt::peer_board_bytes(mrnnt::kPeerMaxWorld)) != cudaSuccess) return RNNT_STATUS_MEMOPS_FAILED;
+    if (cudaMemset(p, 0, mrnnt::peer_board_bytes(mrnnt::kPeerMaxWorld)) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+        (void)cudaFree(p);
+        return RNNT_STATUS_MEMOPS_FAILED;
+    }
+    if (ipc_handle != nullptr) {
+        cudaIpcMemHandle_t hnd;
+        if (cudaIpcGetMemHandle(&hnd, p) != cudaSuccess) {
+            (void)cudaGetLastError();
+            (void)cudaFree(p);
+            return RNNT_STATUS_EXECUTION_FAILED;
+        }
+        std::memcpy(ipc_handle, &hnd, 64);
+    }
+    *board_dev = p;
+    return RNNT_STATUS_SUCCESS;
+}
+
+RNNTStatus mrnnt_peer_board_open(const unsigned char ipc_handle[64], void **peer_ptr) {
+    if (ipc_handle == nullptr || peer_ptr == nullptr) return RNNT_STATUS_INVALID_VALUE;
+    cudaIpcMemHandle_t hnd;
+    std::memcpy(&hnd, ipc_handle, 64);
+    void *p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return RNNT_STATUS_EXECUTION_FAILED;
+    }
+    *peer_ptr = p;
+    return RNNT_STATUS_SUCCESS;
+}
+
+RNNTStatus mrnnt_peer_board_close(void *peer_ptr) {
+    if (peer_ptr == nullptr) return RNNT_STATUS_SUCCESS;
+    return cudaIpcCloseMemHandle(peer_ptr) == cudaSuccess ? RNNT_STATUS_SUCCESS : RNNT_STATUS_MEMOPS_FAILED;
+}
+
+RNNTStatus mrnnt_peer_board_destroy(void *board_dev) {
+    if (board_dev == nullptr) return RNNT_STATUS_SUCCESS;
+    return cudaFree(board_dev) == cudaSuccess ? RNNT_STATUS_SUCCESS : RNNT_STATUS_MEMOPS_FAILED;
+}
+
+RNNTStatus mrnnt_set_peer_reduce(mrnnt_handle_t h, int rank, int world, void *const *boards, float *total_out,
+                                 unsigned epoch) {
+    if (h == nullptr) return RNNT_STATUS_INVALID_VALUE;
+    const RNNTStatus st = h->manager.engine().set_peer_reduce(rank, world, boards, total_out);
+    if (st == RNNT_STATUS_SUCCESS) h->manager.engine().set_peer_epoch(epoch);
+    return st;
+}
+
+unsigned mrnnt_peer_epoch(mrnnt_handle_t h) { return h == nullptr ? 0u : h->manager.engine().peer_epoch(); }
 
 RNNTStatus mrnnt_synth_uniform(float *dst_dev, int64_t n, uint64_t seed, int64_t index_offset, void *stream) {
     if (dst_dev == nullptr || n < 0) return RNNT_STATUS_INVALID_VALUE;

@@ -130,6 +130,26 @@ class LossHandle:
         _lib.check(self._lib.mrnnt_get_option(self._h, option, ctypes.byref(v)), "mrnnt_get_option")
         return int(v.value)
 
+    def set_peer_reduce(self, boards, total_out: Optional[torch.Tensor]) -> None:
+        """From now on every call of this handle also leaves the sum over all ranks of the summed cost in
+        ``total_out`` (one float32, on the device or in pinned host memory); see ``peer.PeerBoards`` and
+        include/mrnnt_c_api.h (mrnnt_set_peer_reduce).  ``boards=None`` turns it off.  A handle that takes over boards
+        another handle has used continues at ``boards.epoch``; ``sync_peer_epoch()`` writes it back."""
+        if boards is None:
+            _lib.check(self._lib.mrnnt_set_peer_reduce(self._h, 0, 0, None, None, 0), "mrnnt_set_peer_reduce")
+            self._boards = None
+            return
+        if total_out is not None and (total_out.dtype != torch.float32 or total_out.numel() != 1):
+            raise ValueError("total_out: one float32")
+        self._boards, self._peer_total = boards, total_out
+        _lib.check(self._lib.mrnnt_set_peer_reduce(self._h, boards.rank, boards.world, boards.c_array(),
+                                                   None if total_out is None else total_out.data_ptr(), boards.epoch),
+                   "mrnnt_set_peer_reduce")
+
+    def sync_peer_epoch(self) -> None:
+        if getattr(self, "_boards", None) is not None:
+            self._boards.epoch = int(self._lib.mrnnt_peer_epoch(self._h))
+
     def last_timings(self):
         """(ms_K1, ms_K2, ms_K3) of the last call; needs set_option(OPT_TIMING, 1) and a synchronised stream."""
         out = (ctypes.c_float * 3)()

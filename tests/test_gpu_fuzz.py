@@ -69,6 +69,7 @@ def test_random_sweep(seed):
     # who zeroes the dead rows: automatic, the gradient kernel's consumers, 1 / 2 warps of the lattice kernel, the
     # gradient kernel's own zero-fill warp
     h.set_option(_lib.OPT_K2_ZERO_FILL, (-1, 0, 1, 2, 32)[seed % 5])
+    h.set_option(_lib.OPT_DYNAMIC_TILES, (-1, 0, 1)[(seed // 5) % 3])   # the gradient kernel's tiles by counter: automatic, off, on
     if case.alignment is not None:
         h.restrict_to_alignment(torch.from_numpy(case.alignment).cuda(), case.max_shift, case.blank)
     grads = torch.full_like(dev_acts, float("nan"))

@@ -348,11 +348,13 @@ def test_forward_into_gradient_buffer(gu, name):
     h.close()
 
 
+@pytest.mark.parametrize("dyn", [0, 1], ids=["round_robin", "dynamic_tiles"])
 @pytest.mark.parametrize("mode", [0, 1, 2, 32], ids=["k3_consumers", "k2_1warp", "k2_2warps", "k3_zero_warp"])
 @pytest.mark.parametrize("restricted", [False, True], ids=["free", "aligned"])
-def test_every_way_of_zeroing_the_dead_rows(gu, mode, restricted):
+def test_every_way_of_zeroing_the_dead_rows(gu, mode, restricted, dyn):
     """MRNNT_OPT_K2_ZERO_FILL: the same gradients whoever writes the rows that are zero by construction, on a shape
-    the streaming kernels take (V = 1000), with and without an alignment band; the backward half on its own as well."""
+    the streaming kernels take (V = 1000), with and without an alignment band; the backward half on its own as well.
+    MRNNT_OPT_DYNAMIC_TILES: the same again with the streaming kernels' tiles handed out through a counter."""
     import monotonic_rnnt_b200 as mr
     from monotonic_rnnt_b200 import _lib
     case = fixtures.random_case("zero_modes", 4242, B=6, V=1000, T_range=(20, 45), S_range=(3, 14), dist="uniform")
@@ -367,6 +369,7 @@ def test_every_way_of_zeroing_the_dead_rows(gu, mode, restricted):
     if restricted:
         h.restrict_to_alignment(torch.from_numpy(case.alignment).to(dev), case.max_shift, case.blank)
     h.set_option(_lib.OPT_K2_ZERO_FILL, mode)
+    h.set_option(_lib.OPT_DYNAMIC_TILES, dyn)
     for _ in range(3):   # (the hand-out counters must come back to zero after every call)
         g = torch.full_like(acts, float("nan"))
         costs = h.cost_and_grad(case.blank, g).numpy()

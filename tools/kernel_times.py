@@ -19,7 +19,7 @@ from monotonic_rnnt_b200 import _lib  # noqa: E402
 
 
 def run(name: str, iters: int, combos, padded: bool = False, bf16: bool = False, compact: int = -1,
-        zeros=(-1,)) -> None:
+        zeros=(-1,), dyn: int = -1) -> None:
     wl = mr.synth.workload(name)
     dev = torch.device("cuda", 0)
     lib = _lib.load()
@@ -43,6 +43,7 @@ def run(name: str, iters: int, combos, padded: bool = False, bf16: bool = False,
         h.restrict_to_alignment(torch.from_numpy(wl.alignment).to(dev), wl.max_shift, wl.blank)
     h.set_option(_lib.OPT_TIMING, 1)
     h.set_option(_lib.OPT_K1_COMPACT, compact)
+    h.set_option(_lib.OPT_DYNAMIC_TILES, dyn)
     costs = torch.empty(wl.B, dtype=torch.float32).pin_memory()
     n4 = wl.elements * (2 if bf16 else 4)
     for k1w, k3w, zf in [(a, b, z) for a, b in combos for z in zeros]:
@@ -62,7 +63,7 @@ def run(name: str, iters: int, combos, padded: bool = False, bf16: bool = False,
         k = np.median(np.array(ts), axis=0)
         w = float(np.median(wall))
         print(f"{wl.name}{' BF16' if bf16 else ''}{' PADDED rows=' + str(acts.numel() // wl.V) if padded else ''} B={wl.B} V={wl.V} rows={wl.rows} "
-              f"k1w={k1w} k3w={k3w} zero={zf}: "
+              f"k1w={k1w} k3w={k3w} zero={zf} dyn={dyn}: "
               f"K1 {k[0]*1e3:7.1f} us ({n4/k[0]/1e6:6.0f} GB/s of 1xN)  K2 {k[1]*1e3:7.1f} us  "
               f"K3 {k[2]*1e3:7.1f} us ({2*n4/k[2]/1e6:6.0f} GB/s of 2xN)  call {w*1e3:7.1f} us "
               f"({3*n4/w/1e6:6.0f} GB/s of 3xN, {wl.B/w*1e3:8.0f} utt/s)", flush=True)
@@ -84,8 +85,10 @@ if __name__ == "__main__":
     ap.add_argument("--bf16", action="store_true", help="bfloat16 logits and gradients")
     ap.add_argument("--compact", type=int, default=-1, help="K1 dead-tile compaction: 1 / 0 forced, -1 automatic")
     ap.add_argument("--padded", action="store_true", help="feed the padded [B,T,S+1,V] tensor instead of packed rows")
+    ap.add_argument("--dyn", default="-1", help="comma list of MRNNT_OPT_DYNAMIC_TILES values (0 / 1, -1 automatic)")
     ap.add_argument("--zero", default="-1", help="comma list of MRNNT_OPT_K2_ZERO_FILL values to compare")
     a = ap.parse_args()
     combos = [tuple(int(x) for x in c.split(":")) for c in a.combos.split(",")]
     for name in a.workloads:
-        run(name, a.iters, combos, a.padded, a.bf16, a.compact, [int(z) for z in a.zero.split(',')])
+        for d in [int(x) for x in a.dyn.split(',')]:
+            run(name, a.iters, combos, a.padded, a.bf16, a.compact, [int(z) for z in a.zero.split(',')], d)
