@@ -39,7 +39,15 @@ import numpy as np  # noqa: E402
 
 METRIC = "loss_grad_utterances_per_sec"
 UNIT = "utt/s"
-WORKLOAD = "c2"  # BASELINE.json configs[1]
+WORKLOAD = "c2"  # BASELINE.json configs[1]; --workload c3 / c4 / c5 reports the other named shapes the same way
+WORKLOAD_NAMES = {
+    "c2": "synthetic B={B} T={T} S={S} V={V} fp32 logits, fixed lengths (BASELINE.json configs[1]) per GPU",
+    "c3": "synthetic B={B} T<={T} S<={S} V={V} fp32 logits, random per-utterance T_b/S_b, packed "
+          "(BASELINE.json configs[2]) per GPU",
+    "c4": "large-vocab B={B} T={T} S={S} V={V} fp32 logits (BASELINE.json configs[3]) per GPU",
+    "c5": "alignment-restricted B={B} T={T} S={S} V={V} fp32 logits, max distance 5 (BASELINE.json configs[4]) per GPU",
+}
+CPU_SAMPLE_BYTES = 4 << 30   # the host baseline / checker runs on a prefix of the batch of at most this many logit bytes
 
 
 def _peaks():
@@ -55,13 +63,12 @@ def _traffic(kernel: str):
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(path):
         with open(path) as f:
-            return json.load(f).get(WORKLOAD, {}).get(kernel)
+            return json.load(f).get(WORKLOAD, {}).get(kernel)  # (captures exist for c2 only: null elsewhere)
     return None
 
 
 def _config(wl, extra=None):
-    cfg = {"workload": f"{wl.name}: synthetic B={wl.B} T={int(wl.T.max())} S={int(wl.S.max())} V={wl.V} fp32 logits, "
-                       f"fixed lengths (BASELINE.json configs[1]) per GPU",
+    cfg = {"workload": f"{wl.name}: " + WORKLOAD_NAMES[wl.name].format(B=wl.B, T=int(wl.T.max()), S=int(wl.S.max()), V=wl.V),
            "batch_per_gpu": wl.B, "rows_per_gpu": wl.rows, "logit_bytes_per_gpu": wl.elements * 4,
            "algorithmic_bytes_per_step_per_gpu": wl.algorithmic_bytes, "l2": "inputs>L2 (no flush needed)",
            "parallelism": "utterance-sharded, one all-reduce of the summed cost"}
@@ -140,6 +147,21 @@ def _host_threads() -> int:
         return max(1, os.cpu_count() or 1)
 
 
+def _cpu_sample(wl, max_utts=None):
+    """A prefix of the batch for the host legs: (k, rows_k, labels, alignment) with the labels / the alignment re-strided
+    to the prefix's own maxima (the reference derives both strides from the lengths it is given,
+    cpu_workspace_manager.h:44,122) and at most CPU_SAMPLE_BYTES of logits -- which also keeps the reference's int
+    indexing below 2^31 elements (c4 as a whole overflows it)."""
+    rows_b = wl.T.astype(np.int64) * (wl.S.astype(np.int64) + 1)
+    cum = np.cumsum(rows_b) * wl.V * 4
+    k = int(np.searchsorted(cum, CPU_SAMPLE_BYTES, side="right"))
+    k = max(1, min(wl.B, k, max_utts or wl.B))
+    s_max = max(1, int(wl.S[:k].max()))
+    labels = np.ascontiguousarray(wl.labels[:k, :s_max])
+    align = None if wl.alignment is None else np.ascontiguousarray(wl.alignment[:k, : int(wl.T[:k].max())])
+    return k, int(rows_b[:k].sum()), labels, align
+
+
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -155,25 +177,25 @@ def run_reference(args) -> None:
     # all the host threads this process may use, named explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers,
     # and the reference's own default (num_threads = 0 -> omp_get_max_threads()) would then time ONE thread
     cores = _host_threads()
-    per_utt = int(wl.T[0]) * (int(wl.S[0]) + 1) * wl.V
-
-    all_acts = mr.synth.uniform_logits(wl.B * per_utt, wl.logits_seed, 0)  # generated once, outside the timing
+    k_max, rows_max, _, _ = _cpu_sample(wl)
+    all_acts = mr.synth.uniform_logits(rows_max * wl.V, wl.logits_seed, 0)  # generated once, outside the timing
 
     def step(B):
-        acts = all_acts[: B * per_utt]
+        k, rows_k, labels, align = _cpu_sample(wl, B)
+        acts = all_acts[: rows_k * wl.V]
         t0 = time.perf_counter()
-        res = runner(acts, wl.labels[:B], wl.T[:B], wl.S[:B], wl.V, blank=wl.blank, precision="f32",
-                     want_grads=True, num_threads=cores)
+        res = runner(acts, labels, wl.T[:k], wl.S[:k], wl.V, blank=wl.blank, alignment=align, max_shift=wl.max_shift,
+                     precision="f32", want_grads=True, num_threads=cores)
         dt = time.perf_counter() - t0
         assert np.isfinite(res.costs).all()
         return dt
 
     # bounded sample: as many utterances of the workload as keep the whole run within ~2 minutes
-    probe_B = min(wl.B, max(1, cores))
+    probe_B = min(k_max, max(1, cores))
     t_probe = step(probe_B)
     per_utt_s = t_probe / probe_B
     budget = 120.0 / max(1, args.steps + args.warmup)
-    B = int(max(1, min(wl.B, budget / per_utt_s)))
+    B = int(max(1, min(k_max, budget / per_utt_s)))
     if B >= cores:
         B = B // cores * cores
     for _ in range(args.warmup):
@@ -181,8 +203,11 @@ def run_reference(args) -> None:
     t = [step(B) for _ in range(args.steps)]
     ms = 1000.0 * sum(t) / len(t)
     value = B / (ms / 1000.0)
-    sample = (f"{B} of the {wl.B} utterances of {wl.name} per step (full T={int(wl.T[0])} S={int(wl.S[0])} V={wl.V}), "
-              f"CpuRNNTComputer<float>::cost_and_grad, -O2 -fopenmp, {cores} threads")
+    sample = (f"the first {B} of the {wl.B} utterances of {wl.name} per step (full T<={int(wl.T.max())} "
+              f"S<={int(wl.S.max())} V={wl.V}"
+              + (f", alignment band +-{wl.max_shift}" if wl.alignment is not None else "")
+              + f"), CpuRNNTComputer<float>::cost_and_grad, -O2 -fopenmp, {cores} threads (the reference runs one "
+              f"utterance per thread)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -418,7 +443,10 @@ def run_b200(args) -> None:
     labels_h = torch.from_numpy(wl.labels).pin_memory()
     T_h = torch.from_numpy(wl.T).pin_memory()
     S_h = torch.from_numpy(wl.S).pin_memory()
-    h2d = acts_h.numel() * 4 + labels_h.numel() * 4 + T_h.numel() * 4 + S_h.numel() * 4
+    align_h = None if wl.alignment is None else torch.from_numpy(wl.alignment).pin_memory()
+    align_d = None if align_h is None else torch.empty_like(align_h, device=dev)
+    h2d = acts_h.numel() * 4 + labels_h.numel() * 4 + T_h.numel() * 4 + S_h.numel() * 4 \
+        + (0 if align_h is None else align_h.numel() * 4)
     d2h = wl.B * 4
 
     def e2e_step():
@@ -427,13 +455,16 @@ def run_b200(args) -> None:
         T.copy_(T_h, non_blocking=True)
         S.copy_(S_h, non_blocking=True)
         h = mr.LossHandle(acts, labels, T, S, lengths_host=(wl.T, wl.S))
+        if align_h is not None:
+            align_d.copy_(align_h, non_blocking=True)
+            h.restrict_to_alignment(align_d, wl.max_shift, wl.blank)
         if boards is not None:
             h.set_peer_reduce(boards, cost_sum_host)     # (a new handle takes the boards over at their epoch)
         h.cost_and_grad(wl.blank, grads, costs_host)     # returns with the costs (and the world's sum) on the host
         h.sync_peer_epoch()
         h.close()
 
-    e2e_steps = max(3, min(args.steps, 20))
+    e2e_steps = max(3, min(args.steps, 20 if h2d < (4 << 30) else 3))
     if boards is not None:
         handle.sync_peer_epoch()
     e2e_step()
@@ -462,30 +493,35 @@ def run_b200(args) -> None:
         kind = "reference" if oracle.have_ref() else "port"
         runner = oracle.run_ref if kind == "reference" else oracle.run
         cores = _host_threads()
-        acts_np = acts_h.numpy()
+        k, rows_k, labels_k, align_k = _cpu_sample(wl)
+        acts_np = acts_h.numpy().reshape(-1)[: rows_k * wl.V]
         times, res = [], None
         t_budget = time.perf_counter()
         for i in range(3):
             t1 = time.perf_counter()
-            res = runner(acts_np, wl.labels, wl.T, wl.S, wl.V, blank=wl.blank, precision="f32", want_grads=True,
-                         num_threads=cores)
+            res = runner(acts_np, labels_k, wl.T[:k], wl.S[:k], wl.V, blank=wl.blank, alignment=align_k,
+                         max_shift=wl.max_shift, precision="f32", want_grads=True, num_threads=cores)
             times.append(time.perf_counter() - t1)
             if time.perf_counter() - t_budget > 20.0:
                 break
         best = min(times)
-        cpu_baseline = {"value": wl.B / best, "unit": UNIT, "cores": cores, "kind": kind,
-                        "sample": f"the full {wl.name} batch ({wl.B} utterances), best of {len(times)} runs of "
+        which = f"the full {wl.name} batch ({wl.B} utterances)" if k == wl.B else \
+            f"the first {k} of the {wl.B} utterances of {wl.name} ({rows_k * wl.V * 4 / 1e9:.2f} GB of logits)"
+        cpu_baseline = {"value": k / best, "unit": UNIT, "cores": cores, "kind": kind,
+                        "sample": f"{which}, best of {len(times)} runs of "
                                   f"CpuRNNTComputer<float>::cost_and_grad (-O2 -fopenmp), {best * 1000:.0f} ms"}
-        g = grads.cpu().numpy()
-        parity = {"checker": f"oracle/{'_ref' if kind == 'reference' else 'liboracle'} f32 on the same inputs",
-                  "cost_max_rel": float(np.max(np.abs(costs_gpu - res.costs) / np.abs(res.costs))),
+        g = grads[:rows_k].cpu().numpy()
+        parity = {"checker": f"oracle/{'_ref' if kind == 'reference' else 'liboracle'} f32 on the same inputs ({which})",
+                  "cost_max_rel": float(np.max(np.abs(costs_gpu[:k] - res.costs) / np.abs(res.costs))),
                   "grad_max_abs_vs_f32_cpu": float(np.abs(g - res.grads).max()),
-                  "note": "the float CPU reference itself is only ~4e-4 from exact arithmetic on this shape "
+                  "note": "the float CPU reference itself is only ~4e-4 from exact arithmetic on c2 "
                           "(SURVEY D6); tests/test_gpu_fullsize.py checks against the double-precision oracle"}
 
     # ---- secondary: the reference's own CUDA path (unmodified tests/test_time.cu for sm_100a) on this GPU -----
     ref_cuda = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    ref_cuda_runs = (wl.alignment is None and wl.elements < 2 ** 31 and int(wl.T.min()) == int(wl.T.max())
+                     and int(wl.S.min()) == int(wl.S.max()))   # its program takes one (T, S) and indexes with int
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and ref_cuda_runs:
         from oracle import oracle
         del acts_h
         r = oracle.run_ref_gpu(wl.B, int(wl.T[0]), int(wl.S[0]), wl.V)
@@ -508,6 +544,12 @@ def run_b200(args) -> None:
     # lattice kernel has already written when its zero fill is on (those are charged to K2 below)
     zero_bytes_in_k2 = 4 * dead_rows * wl.V if zero_fill_warps > 0 else 0
     k3_bytes = 2 * 4 * n - zero_bytes_in_k2
+    zero_note = None
+    if wl.alignment is not None and zero_fill_warps == 0:
+        # tight alignment band: the zero rows are written by one extra warp in K1 and one in K3 out of ONE counter
+        # (DESIGN 3.2), the split is not known on the host: K3 is charged with none of them (a lower bound)
+        k3_bytes = 2 * 4 * n - 4 * dead_rows * wl.V
+        zero_note = "zero rows written by the fill warps of K1 and K3 from one counter; K3 charged with none of them"
     k3_gbs = k3_bytes / (k_ms[2] * 1e-3) / 1e9
     call_gbs = wl.algorithmic_bytes / (ms_per_step * 1e-3) / 1e9
     line = {
@@ -519,7 +561,7 @@ def run_b200(args) -> None:
                      "frac": k3_gbs / peak, "traffic": _traffic("k3_grad_tma_kernel"), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": k3_bytes, "ms_per_launch": float(k_ms[2]),
                      "zero_rows_written_by_k2_bytes": zero_bytes_in_k2, "k2_zero_fill_warps": zero_fill_warps,
-                     "dead_rows": dead_rows},
+                     "dead_rows": dead_rows, "zero_rows_note": zero_note},
         "kernels_ms": {"k1_lse_gather": float(k_ms[0]), "k2_lattice": float(k_ms[1]), "k3_grad": float(k_ms[2]),
                        "sum": float(k_ms.sum()), "k1_GBps_of_4N": 4 * n / (k_ms[0] * 1e-3) / 1e9},
         "call_roofline": {"algorithmic_bytes": wl.algorithmic_bytes, "achieved_GBps": call_gbs,
@@ -557,17 +599,21 @@ def _emit(fd: int, line: dict) -> None:
 
 
 def main() -> None:
+    global WORKLOAD
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--workload", choices=sorted(WORKLOAD_NAMES), default=WORKLOAD,
+                    help="the named shape (BASELINE.json configs[1..4]); the contract's bench line is c2, the default")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-CPU baseline/checker leg")
     ap.add_argument("--collective", choices=["fused", "nccl"], default="fused",
                     help="N > 1: the sum of the costs over peer memory inside the gradient kernel, or NCCL on a side stream")
     ap.add_argument("--reserve-sms", type=int, default=0,
                     help="N > 1: SMs the gradient kernel leaves to the concurrent all-reduce")
     args = ap.parse_args()
+    WORKLOAD = args.workload
     args.out_fd = _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
