@@ -345,6 +345,21 @@ def run_b200(args) -> None:
     clocks = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         one_step()
+    if boards is not None:
+        # the exchange must have worked on EVERY rank before anything is timed through it (a peer whose stores do not
+        # arrive leaves NaN after the kernel's 2 s time-out): otherwise all ranks switch to the NCCL step, and say so
+        want = torch.tensor([float(costs_host.double().sum())], dtype=torch.float64, device=dev)
+        dist.all_reduce(want)
+        got = float(cost_sum_host.item())
+        ok = np.isfinite(got) and abs(got - float(want.item())) <= 1e-5 * abs(float(want.item()))
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            handle.set_peer_reduce(None, None)
+            boards = None
+            collective = "nccl all-reduce on a side stream (the peer-memory exchange failed its check in warm-up)"
+            for _ in range(3):
+                one_step()
 
     # ---- timed region: value ---------------------------------------------------------------------
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
