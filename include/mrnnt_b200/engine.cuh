@@ -346,6 +346,42 @@ class Engine {
         band_dirty_ = true;
     }
 
+    // Fill the device logits from PINNED host memory (cudaHostAlloc / cudaHostRegister; `host_acts` has the layout and
+    // type of acts): only the rows the lattice reads cross the bus, by a kernel that loads them straight from host
+    // memory (plan.cuh::upload_live_rows_kernel).  Dead rows of the device array keep whatever they held -- no kernel
+    // of a later call on this handle reads them.  Needs the workspace; call it after restrict_to_alignment (the band
+    // decides which rows are live; widening the band later needs a new upload).  Asynchronous on `stream`.
+    RNNTStatus upload_live_rows(const void *host_acts, cudaStream_t stream) {
+        if (host_acts == nullptr) return RNNT_STATUS_INVALID_VALUE;
+        RNNTStatus st = ensure_shape();
+        if (st != RNNT_STATUS_SUCCESS) return st;
+        if (base_ == nullptr) return RNNT_STATUS_INVALID_VALUE;
+        const DeviceInfo &dev = device_info();
+        if (!dev.ok) return RNNT_STATUS_EXECUTION_FAILED;
+        void *src = nullptr;  // (the device's view of the pinned block; fails for pageable memory)
+        if (cudaHostGetDevicePointer(&src, const_cast<void *>(host_acts), 0) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return RNNT_STATUS_INVALID_VALUE;
+        }
+        st = setup(stream);
+        if (st != RNNT_STATUS_SUCCESS) return st;
+        void *dst = const_cast<void *>(acts_);
+        const size_t row_bytes = static_cast<size_t>(V_) * elem_bytes();
+        const uintptr_t bits = reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | row_bytes;
+        const int grid = dev.sm_count * 8;
+        if ((bits & 15) == 0) {
+            upload_live_rows_kernel<uint4><<<grid, kUploadThreads, 0, stream>>>(
+                static_cast<const uint4 *>(src), static_cast<uint4 *>(dst), ws_.rowmeta, shape_.rows, static_cast<int>(row_bytes / 16));
+        } else if ((bits & 3) == 0) {
+            upload_live_rows_kernel<uint32_t><<<grid, kUploadThreads, 0, stream>>>(
+                static_cast<const uint32_t *>(src), static_cast<uint32_t *>(dst), ws_.rowmeta, shape_.rows, static_cast<int>(row_bytes / 4));
+        } else {
+            upload_live_rows_kernel<uint16_t><<<grid, kUploadThreads, 0, stream>>>(
+                static_cast<const uint16_t *>(src), static_cast<uint16_t *>(dst), ws_.rowmeta, shape_.rows, static_cast<int>(row_bytes / 2));
+        }
+        return launched();
+    }
+
     const Shape &shape() const { return shape_; }
     const Workspace &workspace() const { return ws_; }
     bool has_workspace() const { return base_ != nullptr; }

@@ -268,4 +268,34 @@ static __global__ void __launch_bounds__(256) rowmeta_kernel(const int *__restri
     }
 }
 
+// Host -> device upload of the logits that will be read (Engine::upload_live_rows): a warp per row, live rows only,
+// straight out of pinned host memory over PCIe into the device array the kernels stream from.  The copy engine moves
+// whole tensors; which rows the lattice reads is known from the plan (rowmeta), and the rows it calls dead -- 27 % of
+// c2, ~95 % under c5's alignment band -- are never read by any kernel, so they need not cross the bus.  UNIT is the
+// widest access the row size and the two base addresses allow (16 bytes wherever the streaming kernels apply).
+constexpr int kUploadThreads = 256;
+template <typename UNIT>
+static __global__ void __launch_bounds__(kUploadThreads) upload_live_rows_kernel(const UNIT *__restrict__ src,
+                                                                                 UNIT *__restrict__ dst,
+                                                                                 const int *__restrict__ rowmeta,
+                                                                                 int64_t rows, int units_per_row) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(kUploadThreads) + threadIdx.x) >> 5;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * kUploadThreads) >> 5;
+    for (int64_t row = warp0; row < rows; row += nwarps) {
+        if (__ldg(rowmeta + row) == kRowDead) continue;  // (warp-uniform)
+        const UNIT *s = src + row * units_per_row;
+        UNIT *d = dst + row * units_per_row;
+        int i = lane;
+        for (; i + 7 * 32 < units_per_row; i += 8 * 32) {  // eight loads in flight per lane: 4 KB per warp at 16 bytes
+            UNIT v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __ldcs(s + i + j * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) d[i + j * 32] = v[j];
+        }
+        for (; i < units_per_row; i += 32) d[i] = __ldcs(s + i);
+    }
+}
+
 }  // namespace mrnnt

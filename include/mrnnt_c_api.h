@@ -64,6 +64,13 @@ void mrnnt_free_workspace(mrnnt_handle_t h);
  * that call's stream; `alignments` must stay valid until then.  May be called repeatedly. */
 RNNTStatus mrnnt_restrict_to_alignment(mrnnt_handle_t h, const int *alignments, int max_shift, int blank_idx);
 
+/* No counterpart in the reference, whose callers bring the logits to the device themselves (pytorch_binding/
+ * monotonic_rnnt.cu:85-88 takes CUDA tensors): fill the handle's device `acts` from PINNED host memory of the same layout
+ * and type, moving only the rows the lattice reads (the plan's dead rows -- a quarter of a plain batch, ~95 % under a
+ * tight alignment band -- are never read by any kernel and stay as they are).  Asynchronous on `stream`; needs the
+ * workspace; call after mrnnt_restrict_to_alignment.  RNNT_STATUS_INVALID_VALUE if `host_acts` is not pinned. */
+RNNTStatus mrnnt_upload_acts(mrnnt_handle_t h, const void *host_acts, void *stream);
+
 /* GpuRNNTComputer<float>::cost_and_grad / cost (reference include/gpu_rnnt.h:27-235) and therefore
  * compute_rnnt_loss (include/rnnt_entrypoint.h:24-25).  `stream` is a cudaStream_t / CUstream.
  * gradients == NULL selects cost only.  costs are valid on return (one stream synchronisation). */

@@ -34,7 +34,7 @@ EXPORTED_SYMBOLS = (
     "mrnnt_enqueue_forward", "mrnnt_enqueue_backward", "mrnnt_enqueue_forward_into", "mrnnt_create_padded",
     "mrnnt_get_workspace_size_padded", "mrnnt_set_dtype",
     "mrnnt_peer_board_create", "mrnnt_peer_board_open", "mrnnt_peer_board_close", "mrnnt_peer_board_destroy",
-    "mrnnt_set_peer_reduce", "mrnnt_peer_epoch",
+    "mrnnt_set_peer_reduce", "mrnnt_peer_epoch", "mrnnt_upload_acts",
 )
 
 
@@ -63,6 +63,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mrnnt_free_workspace.argtypes = [vp]
     lib.mrnnt_free_workspace.restype = None
     lib.mrnnt_restrict_to_alignment.argtypes = [vp, vp, ci, ci]
+    lib.mrnnt_upload_acts.argtypes = [vp, vp, vp]
+    lib.mrnnt_upload_acts.restype = ci
     lib.mrnnt_cost_and_grad.argtypes = [vp, ci, vp, vp, vp]
     lib.mrnnt_enqueue.argtypes = [vp, ci, vp, vp]
     lib.mrnnt_enqueue_forward.argtypes = [vp, ci, vp, ci]

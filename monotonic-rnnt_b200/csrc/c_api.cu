@@ -148,6 +148,11 @@ RNNTStatus mrnnt_restrict_to_alignment(mrnnt_handle_t h, const int *alignments, 
     return RNNT_STATUS_SUCCESS;
 }
 
+RNNTStatus mrnnt_upload_acts(mrnnt_handle_t h, const void *host_acts, void *stream) {
+    if (h == nullptr) return RNNT_STATUS_INVALID_VALUE;
+    return h->manager.engine().upload_live_rows(host_acts, static_cast<cudaStream_t>(stream));
+}
+
 RNNTStatus mrnnt_cost_and_grad(mrnnt_handle_t h, int blank_label, void *stream, float *costs_host, float *gradients) {
     if (h == nullptr) return RNNT_STATUS_INVALID_VALUE;
     return h->manager.engine().compute(blank_label, static_cast<cudaStream_t>(stream), costs_host, gradients);

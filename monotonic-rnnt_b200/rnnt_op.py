@@ -163,6 +163,17 @@ class LossHandle:
         _lib.check(self._lib.mrnnt_restrict_to_alignment(self._h, alignment.data_ptr(), int(max_shift), int(blank_idx)),
                    "mrnnt_restrict_to_alignment")
 
+    def upload_acts(self, host_acts: torch.Tensor, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """Fill the device ``acts`` of this handle from a PINNED host tensor of the same shape and dtype, moving only
+        the rows the lattice reads (mrnnt_upload_acts); asynchronous on ``stream``.  After restrict_to_alignment."""
+        if host_acts.is_cuda or not host_acts.is_pinned() or not host_acts.is_contiguous():
+            raise TypeError("host_acts must be a contiguous pinned host tensor")
+        if host_acts.dtype != self.acts.dtype or host_acts.numel() != self.acts.numel():
+            raise TypeError("host_acts must have the dtype and the size of acts")
+        with self._device():
+            st = stream if stream is not None else torch.cuda.current_stream(self.acts.device)
+            _lib.check(self._lib.mrnnt_upload_acts(self._h, host_acts.data_ptr(), st.cuda_stream), "mrnnt_upload_acts")
+
     def _device(self):
         """Make acts' device current for the call; free when it already is (the usual case)."""
         idx = self.acts.device.index
