@@ -286,15 +286,17 @@ static __global__ void __launch_bounds__(kUploadThreads) upload_live_rows_kernel
         if (__ldg(rowmeta + row) == kRowDead) continue;  // (warp-uniform)
         const UNIT *s = src + row * units_per_row;
         UNIT *d = dst + row * units_per_row;
-        int i = lane;
-        for (; i + 7 * 32 < units_per_row; i += 8 * 32) {  // eight loads in flight per lane: 4 KB per warp at 16 bytes
+        // eight loads in flight per lane (4 KB per warp at 16 bytes), ALL issued before the first store waits for one:
+        // a round trip over PCIe takes microseconds, so the ragged end of a row is predicated, not a loop of its own
+        for (int base = lane; base < units_per_row; base += 8 * 32) {
             UNIT v[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __ldcs(s + i + j * 32);
+            for (int j = 0; j < 8; ++j)
+                if (base + j * 32 < units_per_row) v[j] = __ldcs(s + base + j * 32);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) d[i + j * 32] = v[j];
+            for (int j = 0; j < 8; ++j)
+                if (base + j * 32 < units_per_row) d[base + j * 32] = v[j];
         }
-        for (; i < units_per_row; i += 32) d[i] = __ldcs(s + i);
     }
 }
 
