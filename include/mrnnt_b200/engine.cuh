@@ -539,7 +539,11 @@ class Engine {
     void set_reserved_sms(int n) { reserved_sms_ = n < 0 ? 0 : n; }
     int last_k2_zero_warps() const { return last_k2_zero_warps_; }
     void set_k2_zero_fill(int warps) { k2_zero_warps_ = warps; }
-    void set_dynamic_tiles(int mode) { dynamic_tiles_ = mode < 0 ? -1 : (mode != 0); }
+    // -1 automatic, 0 off, 1 on; 2..100: on, with that percentage of a CTA's share fixed before the counter takes over
+    void set_dynamic_tiles(int mode) {
+        dynamic_tiles_ = mode < 0 ? -1 : (mode != 0);
+        dynamic_fixed_pct_ = mode >= 2 ? (mode > 100 ? 100 : mode) : kDynamicFixedPct;
+    }
     // Upper limit for the CTAs per utterance of the lattice kernel's coefficient phase (0: automatic).
     void set_k2_parts(int parts) { k2_parts_ = parts < 0 ? 0 : parts; }
     // Consumer warps per CTA of the streaming kernels (8 or 16); tuning knob for the bench.
@@ -814,7 +818,12 @@ class Engine {
 
     // (dead tiles are skipped under the same conditions as in K1, and only when nobody has to zero them here)
     int k3_flags(const StreamTiling &tl) const {
-        const int dyn = dynamic_tiles(tl) ? kK3Dynamic : 0;
+        int dyn = 0;
+        if (dynamic_tiles(tl)) {
+            const int64_t share = (shape_.rows + tl.G - 1) / tl.G / device_info().sm_count;
+            const int64_t fixed = share * dynamic_fixed_pct_ / 100;
+            dyn = kK3Dynamic | (static_cast<int>(fixed < 2 ? 2 : fixed > 0x3fffff ? 0x3fffff : fixed) << kK3FixedShift);
+        }
         if (k3_write_dead_) return kK3WriteDead | dyn;
         return dyn ? dyn : (k1_compact(tl) ? kK3Compact : 0);
     }
@@ -918,6 +927,8 @@ class Engine {
     bool force_generic_ = false;
     int k1_warps_ = 24;
     int k1_compact_ = -1;  // -1: automatic (k1_compact()), 0 / 1: forced
+    static constexpr int kDynamicFixedPct = 0;  // (0: two fixed tiles per CTA, everything else through the counter)
+    int dynamic_fixed_pct_ = kDynamicFixedPct;
     int dynamic_tiles_ = -1;  // the gradient kernel's tiles through a counter: -1 automatic (dynamic_tiles()), 0 / 1 forced
     int k3_warps_ = 24;
     int k2_parts_ = 0;     // 0: automatic

@@ -203,16 +203,18 @@ struct TileGrabber {
     unsigned raw[kGrabDepth];
     unsigned *ctr;  // {tiles handed out, producers finished}; zero between launches
     int lane;
+    int64_t first;  // the counter's tile 0: the CTAs' fixed tiles come before it
     __device__ __forceinline__ unsigned grab() { return lane == 0 ? atomicAdd(ctr, 1u) : 0u; }
-    __device__ __forceinline__ void start(unsigned *c, int l) {
+    __device__ __forceinline__ void start(unsigned *c, int l, int fixed_per_cta = 2) {
         ctr = c;
         lane = l;
+        first = static_cast<int64_t>(fixed_per_cta) * gridDim.x;
 #pragma unroll
         for (int i = 0; i < kGrabDepth; ++i) raw[i] = grab();
     }
     // the next tile (warp-uniform), and one more request
     __device__ __forceinline__ int64_t next() {
-        const int64_t t = static_cast<int64_t>(__shfl_sync(0xffffffffu, raw[0], 0)) + 2 * static_cast<int64_t>(gridDim.x);
+        const int64_t t = static_cast<int64_t>(__shfl_sync(0xffffffffu, raw[0], 0)) + first;
 #pragma unroll
         for (int i = 0; i + 1 < kGrabDepth; ++i) raw[i] = raw[i + 1];
         raw[kGrabDepth - 1] = grab();

@@ -98,6 +98,7 @@ static __global__ void __launch_bounds__(kGenericWarps * kWarp)
 constexpr int kK3WriteDead = 1;  // write the zero rows (off: somebody else zeroes the rows the plan calls dead)
 constexpr int kK3Compact = 2;    // tiles without a live row take no ring slot (needs kK3WriteDead off)
 constexpr int kK3ZeroShared = 4; // the zero-fill warp continues a fill the LSE kernel's zero-fill warp has begun
+constexpr int kK3FixedShift = 8; // flags >> 8: with kK3Dynamic, how many tiles of a CTA are fixed before the counter takes over
 constexpr int kK3Dynamic = 8;    // tiles are handed out through a counter (`dyn`) instead of round-robin by CTA index: a
                                  // CTA on an SM that streams faster takes more of them, and the kernel ends when the
                                  // work does, not when the unluckiest CTA has got through its fixed share.  The first
@@ -182,8 +183,18 @@ static __global__ void __launch_bounds__((NW + 2) * kWarp, 1)
             }
         };
         if (dynamic) {
+            // the first `fixed` tiles of a CTA are its round-robin share (flags >> kK3FixedShift, at least two), the
+            // counter hands out the rest: the hand-out only has to even out the END of the kernel
+            int fixed = flags >> kK3FixedShift;
+            if (static_cast<int64_t>(fixed) * gridDim.x > ntiles) fixed = static_cast<int>(ntiles / gridDim.x);
+            if (fixed < 2) fixed = 2;
             TileGrabber grabber;  // (k1_lse.cuh)
-            grabber.start(dyn, lane);
+            grabber.start(dyn, lane, fixed);
+            int kfix = 2;
+            auto next_tile = [&]() -> int64_t {
+                if (kfix < fixed) return blockIdx.x + static_cast<int64_t>(kfix++) * gridDim.x;
+                return grabber.next();
+            };
             auto load_coef = [&](int64_t tile) {
                 const int64_t row = tile * G + lane;
                 return (tile < ntiles && lane < G && row < rows) ? __ldg(coef + row) : make_float4(kNegInfF, 0.f, 0.f, 0.f);
@@ -196,7 +207,7 @@ static __global__ void __launch_bounds__((NW + 2) * kWarp, 1)
             float4 c0 = load_coef(t0), c1 = load_coef(t1);
             float s0 = load_scale(t0), s1 = load_scale(t1);
             while (t0 < ntiles) {
-                const int64_t t2 = grabber.next();
+                const int64_t t2 = next_tile();
                 const float4 c2 = load_coef(t2);
                 const float s2 = load_scale(t2);
                 const uint32_t mask = __ballot_sync(0xffffffffu, !(c0.x == kNegInfF));
