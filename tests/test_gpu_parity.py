@@ -387,6 +387,33 @@ def test_every_way_of_zeroing_the_dead_rows(gu, mode, restricted, dyn):
     h.close()
 
 
+@pytest.mark.parametrize("pct", [60, 100], ids=["60pct_fixed", "all_fixed_but_the_remainder"])
+def test_fixed_share_before_the_tile_counter(gu, pct):
+    """MRNNT_OPT_DYNAMIC_TILES = 2..100: that percentage of a CTA's round-robin share of the gradient kernel's tiles is
+    fixed, the counter hands out the rest -- on a shape with several tiles per CTA, three calls in a row (the counter must
+    come back to zero), bit-identical to the round-robin hand-out."""
+    import monotonic_rnnt_b200 as mr
+    from monotonic_rnnt_b200 import _lib
+    case = fixtures.random_case("fixed_share", 515, B=8, V=1000, T_range=(60, 80), S_range=(10, 14), dist="uniform")
+    o64 = _oracle(case, "f64_from_f32")
+    dev = torch.device("cuda", 0)
+    acts = torch.from_numpy(case.acts).to(dev)
+    h = mr.LossHandle(acts, torch.from_numpy(case.labels).to(dev), torch.from_numpy(case.T).to(dev),
+                      torch.from_numpy(case.S).to(dev))
+    h.set_option(_lib.OPT_DYNAMIC_TILES, 0)
+    g0 = torch.full_like(acts, float("nan"))
+    c0 = h.cost_and_grad(case.blank, g0).numpy().copy()
+    h.set_option(_lib.OPT_DYNAMIC_TILES, pct)
+    for _ in range(3):
+        g = torch.full_like(acts, float("nan"))
+        costs = h.cost_and_grad(case.blank, g).numpy()
+        np.testing.assert_array_equal(costs, c0)
+        assert torch.equal(g, g0)
+    _check_costs(c0, o64.costs)
+    assert np.abs(g0.cpu().numpy() - o64.grads).max() <= GRAD_ATOL
+    h.close()
+
+
 def test_automatic_choice_of_who_zeroes_the_dead_rows(gu):
     """A tight alignment band (nearly all rows dead): the zero-fill warps of the LSE and gradient kernels; a band that
     restricts nothing, or no band: the lattice kernel's fill (small shapes: its recursions are most of the call)."""
