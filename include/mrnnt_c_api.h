@@ -138,7 +138,8 @@ enum {
                                     that many warps per lattice CTA, while the recursions run; 32 one more warp of
                                     the gradient kernel, next to its consumers; -1 automatic                    */
     MRNNT_OPT_DYNAMIC_TILES = 10 /* the gradient kernel hands its tiles out through a counter instead of round-robin by
-                                    CTA index: 1 / 0 forced, -1 automatic                                       */
+                                    CTA index: 1 / 0 forced, -1 automatic; 2..100: through the counter once that
+                                    percentage of a CTA's round-robin share has been worked off                  */
 };
 RNNTStatus mrnnt_set_option(mrnnt_handle_t h, int option, int value);
 /* What the last call actually did: MRNNT_OPT_K2_ZERO_FILL -> 0, 1..4 or 32 as above.  Other options:
