@@ -11,6 +11,10 @@ namespace mrnnt {
 
 constexpr int kZeroFillBytes = 8192;  // zeroed shared memory every bulk store reads from (tools/zero_probe.cu: 8 KB
                                       // stores from one warp per SM already reach the write bandwidth of the GPU)
+#ifndef MRNNT_ZERO_FILL_DEPTH
+#define MRNNT_ZERO_FILL_DEPTH 2
+#endif
+constexpr int kZeroFillDepth = MRNNT_ZERO_FILL_DEPTH;  // units a zero-fill warp holds while as many grabs are in flight
 struct ZeroFill {
     unsigned char *dst;   // the gradient buffer
     const int *rowmeta;   // [rows]
@@ -29,8 +33,8 @@ __device__ __forceinline__ void bulk_s2g(void *gdst, const void *ssrc, uint32_t 
 // some warps with twice the bytes of others.  The grab for the unit three ahead and the row flags of the unit two
 // ahead are in flight while a unit is processed.  A lane that sees the first row of a run of dead rows stores the
 // whole run, 8 KB at a time.  Two protocols:
-//  * OWNED (one kernel does the whole fill): warp `fw` of the `nfw` zero-fill warps of the grid takes the units fw and
-//    fw + nfw without asking, the counter hands out the ones from 2 * nfw on, and the last warp to finish sets
+//  * OWNED (one kernel does the whole fill): warp `fw` of the `nfw` zero-fill warps of the grid takes the units fw,
+//    fw + nfw, ... (kZeroFillDepth of them) without asking, the counter hands out the ones behind those, and the last warp to finish sets
 //    `ctr` = {units handed out, warps finished} back to zero for the next launch.
 //  * SHARED (!OWNED; the kernels of one call take turns at one counter, each for as long as it runs): every unit comes
 //    from the counter, which nobody resets here (the engine alternates between two, and the lattice kernel of a call
@@ -54,30 +58,37 @@ __device__ __forceinline__ void zero_dead_rows_impl(const ZeroFill &a, int fw, i
     };
     auto unit_of = [&](unsigned raw) {
         const unsigned v = __shfl_sync(0xffffffffu, raw, 0);
-        return (!OWNED && v == kNoUnit) ? nunits : static_cast<int64_t>(v) + (OWNED ? 2 * nfw : 0);
+        return (!OWNED && v == kNoUnit) ? nunits : static_cast<int64_t>(v) + (OWNED ? static_cast<int64_t>(kZeroFillDepth) * nfw : 0);
     };
     auto load = [&](int64_t u) {
         const int64_t r = u * kWarp + lane;
         return (u < nunits && r < rows) ? __ldg(meta + r) : 0;
     };
-    unsigned raw_a = grab(), raw_b = grab();
-    int64_t u0, u1;
+    // kZeroFillDepth units are held (index known, row flags loaded or on their way) and as many grabs are in flight
+    constexpr int D = kZeroFillDepth;
+    unsigned raw[D];
+    int64_t u[D];
+    int m[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) raw[i] = grab();
     if (OWNED) {
-        u0 = fw;
-        u1 = fw + nfw;
+#pragma unroll
+        for (int i = 0; i < D; ++i) u[i] = fw + static_cast<int64_t>(i) * nfw;
     } else {
-        u0 = unit_of(raw_a);
-        u1 = unit_of(raw_b);
-        raw_a = grab();
-        raw_b = grab();
+#pragma unroll
+        for (int i = 0; i < D; ++i) u[i] = unit_of(raw[i]);
+#pragma unroll
+        for (int i = 0; i < D; ++i) raw[i] = grab();
     }
-    int m0 = load(u0), m1 = load(u1);
-    while (u0 < nunits) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) m[i] = load(u[i]);
+    while (u[0] < nunits) {
         if (!OWNED) stopped = stopped || stop();
-        const unsigned raw_c = grab();
-        const int64_t u2 = unit_of(raw_a);
-        const int m2 = load(u2);
-        const bool dead = m0 == kRowDead;
+        const unsigned raw_new = grab();
+        const int64_t u_new = unit_of(raw[0]);
+        const int m_new = load(u_new);
+        const int64_t u0 = u[0];
+        const bool dead = m[0] == kRowDead;
         const uint32_t mask = __ballot_sync(0xffffffffu, dead);
         if (dead && (lane == 0 || ((mask >> (lane - 1)) & 1u) == 0u)) {
             const uint32_t inv = ~(mask >> lane);  // (the shift fills with zeros: inv != 0 unless lane == 0 and all dead)
@@ -97,20 +108,25 @@ __device__ __forceinline__ void zero_dead_rows_impl(const ZeroFill &a, int fw, i
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         }
-        u0 = u1;
-        m0 = m1;
-        u1 = u2;
-        m1 = m2;
-        raw_a = raw_b;
-        raw_b = raw_c;
+#pragma unroll
+        for (int i = 0; i + 1 < D; ++i) {
+            u[i] = u[i + 1];
+            m[i] = m[i + 1];
+            raw[i] = raw[i + 1];
+        }
+        u[D - 1] = u_new;
+        m[D - 1] = m_new;
+        raw[D - 1] = raw_new;
     }
     // the stores must have left shared memory before the CTA gives it up; the kernel's end makes them visible
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     if (OWNED) {
         // the last warp to finish leaves the counters as it found them (every grab of this launch has been made by
-        // then: a warp looks at its last two grabs before it reports)
-        const unsigned seen = __shfl_sync(0xffffffffu, raw_a, 0) + __shfl_sync(0xffffffffu, raw_b, 0);
+        // then: a warp looks at its outstanding grabs before it reports)
+        unsigned seen = 0u;
+#pragma unroll
+        for (int i = 0; i < D; ++i) seen += __shfl_sync(0xffffffffu, raw[i], 0);
         if (lane == 0 && atomicAdd(ctr + 1, seen * 0u + 1u) == static_cast<unsigned>(nfw) - 1u) {
             ctr[0] = 0u;
             ctr[1] = 0u;
