@@ -12,8 +12,10 @@ cost per step.  Rank 0 prints ONE JSON line.
   value     whole-job utterances/s with inputs resident in HBM; the timed region is K calls of the C-ABI
             entry (mrnnt_cost_and_grad: K1 -> K2 -> K3, async D2H of the B costs, one stream sync)
             bracketed by barrier + synchronize, CUDA events on the launch stream, max over ranks.
-  e2e       same metric through the public host API with HOST buffers: every step copies the step's
-            logits/labels/lengths from pinned host memory, builds the handle, runs, reads costs back.
+  e2e       same metric through the public host API with HOST buffers: every step brings the step's
+            logits/labels/lengths from pinned host memory to the device, builds the handle, runs, reads costs
+            back.  Measured two ways (e2e_paths): the whole tensor through the copy engine, and the rows the
+            lattice reads only (mrnnt_upload_acts: a kernel pulls them from host memory); e2e is the faster.
   roofline  dominant kernel (K3, gradient: reads the live logits, writes every gradient) timed per launch
             with CUDA events recorded around it on the same stream in a second, instrumented pass of K steps.
   cpu_baseline  the reference's own CPU implementation (oracle/_ref, compiled from the unmodified
@@ -21,6 +23,8 @@ cost per step.  Rank 0 prints ONE JSON line.
             checker of the GPU result (costs / gradients), which is the only reason bench.py touches oracle/.
 Inputs (0.79 GB logits + 0.79 GB gradients per step) exceed the 126 MB L2, so no L2 flush is needed
 between iterations (config.l2: "inputs>L2").
+--workload c3|c4|c5 puts the other shapes BASELINE.json names through the same contract (the driver's line is c2,
+the default); their host legs run on a prefix of the batch of at most 4 GiB of logits.
 """
 from __future__ import annotations
 
