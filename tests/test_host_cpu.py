@@ -220,3 +220,30 @@ def test_bench_reference_arm_schema():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1"],
                          capture_output=True, text=True, env=env, timeout=60)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+@pytest.mark.parametrize("name", ["c2", "c3", "c4", "c5"])
+def test_bench_cpu_sample_is_a_bounded_prefix(name):
+    """bench.py's host legs (CPU baseline, checker, reference arm) run on a prefix of the batch: at most 4 GiB of
+    logits (so the reference's int indexing stays in range), labels / alignment re-strided to the prefix's
+    own maxima (the reference derives both strides from the lengths it is given)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    import monotonic_rnnt_b200 as mr
+    wl = mr.synth.workload(name)
+    k, rows_k, labels, align = bench._cpu_sample(wl)
+    assert 1 <= k <= wl.B
+    assert rows_k == int((wl.T[:k].astype(np.int64) * (wl.S[:k].astype(np.int64) + 1)).sum())
+    assert rows_k * wl.V < 2 ** 31 and (rows_k * wl.V * 4 <= bench.CPU_SAMPLE_BYTES or k == 1)
+    assert labels.shape == (k, int(wl.S[:k].max())) and labels.flags["C_CONTIGUOUS"]
+    np.testing.assert_array_equal(labels, wl.labels[:k, : labels.shape[1]])
+    if wl.alignment is None:
+        assert align is None
+    else:
+        assert align.shape == (k, int(wl.T[:k].max())) and align.flags["C_CONTIGUOUS"]
+    if name == "c2":
+        assert k == wl.B          # the headline shape is checked whole
+    k1, rows_1, _, _ = bench._cpu_sample(wl, 1)
+    assert k1 == 1 and rows_1 == int(wl.T[0]) * (int(wl.S[0]) + 1)
