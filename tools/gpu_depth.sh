@@ -1,4 +1,6 @@
-# zero-fill pipeline depth 2 / 3 / 4: kernel times on c2, c3, c5 and a parity run of the zero-fill tests for each
+# zero-fill pipeline depth 2 / 3 / 4: kernel times on c2, c3, c5 and a parity run of the zero-fill tests for each.
+# Needs lib/d3_libmonotonic_rnnt.bin and d4_...: monotonic_rnnt_b200.build.build(force=True,
+# extra_flags=['-DMRNNT_ZERO_FILL_DEPTH=3']) copied aside, likewise 4, then the default build again.
 set -x
 L=monotonic-rnnt_b200/lib
 cp $L/libmonotonic_rnnt.so $L/d2_libmonotonic_rnnt.bin
