@@ -195,10 +195,15 @@ __device__ long long g_k1_trace[32][4];  // per warp: cycles waiting, cycles wor
 #endif
 
 // Dynamic tile hand-out (the gradient kernel's producer, kK3Dynamic in k3_grad.cuh): tiles come from a counter,
-// `kGrabDepth` requests in flight per producer -- an atomic on one hot word takes microseconds to come back while the GPU
-// streams at full bandwidth, a tile lasts about one.  The first two tiles of a CTA are fixed (blockIdx.x, blockIdx.x + gridDim.x), the counter hands
+// `kGrabDepth` requests in flight per producer -- an atomic on one hot word takes a microsecond or two to come back while
+// the GPU streams at full bandwidth, a tile lasts about one; every request in flight is also a tile bound to its CTA
+// before the CTA gets to it, i.e. a hand-out that follows the SMs less closely (tools/gpu_grab.sh, K3 on c2 in the
+// stream: depth 1..4 189-190 us, 8 193, 16 197, 32 230; with one request the call as a whole was slower).  The first two tiles of a CTA are fixed (blockIdx.x, blockIdx.x + gridDim.x), the counter hands
 // out the ones from 2 * gridDim.x on, in order: the CTAs keep working on one moving window of the input.
-constexpr int kGrabDepth = 8;
+#ifndef MRNNT_GRAB_DEPTH
+#define MRNNT_GRAB_DEPTH 3
+#endif
+constexpr int kGrabDepth = MRNNT_GRAB_DEPTH;
 struct TileGrabber {
     unsigned raw[kGrabDepth];
     unsigned *ctr;  // {tiles handed out, producers finished}; zero between launches
