@@ -138,14 +138,18 @@ static __global__ void gather_lengths_kernel(const int *__restrict__ T, const in
 // going through cudaFree / cudaMalloc: the reference's torch binding creates and frees the workspace on every loss
 // call (pytorch_binding/monotonic_rnnt.cu:99-111), and the driver's allocator costs milliseconds for blocks of this
 // size (measured: 2.9 ms per call against 0.36 ms with a workspace that stays).  At most kWorkspaceCacheBlocks
-// blocks per module are kept; the smallest sufficient one is reused.
+// blocks and g_ws_cache_limit bytes per module are kept (workspace_cache_set_limit; 0 turns the cache off: every
+// free_workspace() is then a cudaFree, as in the reference); the smallest sufficient block is reused;
+// workspace_cache_trim() gives everything back to the driver.
 constexpr int kWorkspaceCacheBlocks = 4;
+constexpr size_t kWorkspaceCacheDefaultLimit = size_t(1) << 30;  // 1 GiB (c3's workspace is 91 MB, c4's 56 MB)
 struct CachedBlock {
     void *ptr = nullptr;
     size_t bytes = 0;
     int device = -1;
 };
 static CachedBlock g_ws_cache[kWorkspaceCacheBlocks];
+static size_t g_ws_cache_limit = kWorkspaceCacheDefaultLimit;
 static std::mutex g_ws_cache_mutex;
 
 inline void *workspace_cache_take(size_t bytes, int device, size_t *got) {
@@ -162,23 +166,68 @@ inline void *workspace_cache_take(size_t bytes, int device, size_t *got) {
     g_ws_cache[best] = CachedBlock();
     return p;
 }
-// returns a block the cache had to give up for the new one (to be cudaFree'd by the caller), or nullptr
-inline void *workspace_cache_put(void *ptr, size_t bytes, int device) {
-    std::lock_guard<std::mutex> lock(g_ws_cache_mutex);
-    int slot = -1;
-    for (int i = 0; i < kWorkspaceCacheBlocks; ++i) {
-        if (g_ws_cache[i].ptr == nullptr) {
-            slot = i;
-            break;
+// Free `ptr` on its own device, whatever the current device is.
+inline void workspace_free_on(void *ptr, int device) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess) cur = -1;
+    if (cur != device && device >= 0) (void)cudaSetDevice(device);
+    (void)cudaFree(ptr);
+    if (cur != device && cur >= 0) (void)cudaSetDevice(cur);
+}
+// Keeps the block, or frees it (cache off, block above the byte limit); blocks the cache gives up for it are freed too.
+inline void workspace_cache_put(void *ptr, size_t bytes, int device) {
+    CachedBlock drop[kWorkspaceCacheBlocks + 1];
+    int ndrop = 0;
+    {
+        std::lock_guard<std::mutex> lock(g_ws_cache_mutex);
+        if (bytes > g_ws_cache_limit) {
+            drop[ndrop++] = CachedBlock{ptr, bytes, device};
+        } else {
+            int slot = -1;
+            for (int i = 0; i < kWorkspaceCacheBlocks && slot < 0; ++i)
+                if (g_ws_cache[i].ptr == nullptr) slot = i;
+            if (slot < 0) {  // full: the smallest cached block goes
+                slot = 0;
+                for (int i = 1; i < kWorkspaceCacheBlocks; ++i)
+                    if (g_ws_cache[i].bytes < g_ws_cache[slot].bytes) slot = i;
+                drop[ndrop++] = g_ws_cache[slot];
+            }
+            g_ws_cache[slot] = CachedBlock{ptr, bytes, device};
+            // the byte limit: largest blocks first out
+            for (;;) {
+                size_t total = 0;
+                int big = -1;
+                for (int i = 0; i < kWorkspaceCacheBlocks; ++i) {
+                    if (g_ws_cache[i].ptr == nullptr) continue;
+                    total += g_ws_cache[i].bytes;
+                    if (big < 0 || g_ws_cache[i].bytes > g_ws_cache[big].bytes) big = i;
+                }
+                if (total <= g_ws_cache_limit || big < 0) break;
+                drop[ndrop++] = g_ws_cache[big];
+                g_ws_cache[big] = CachedBlock();
+            }
         }
-        if (slot < 0 || g_ws_cache[i].bytes < g_ws_cache[slot].bytes) slot = i;  // else evict the smallest
     }
-    void *evicted = g_ws_cache[slot].ptr;
-    if (evicted != nullptr && g_ws_cache[slot].bytes >= bytes) return ptr;  // everything cached is larger: drop the new one
-    g_ws_cache[slot].ptr = ptr;
-    g_ws_cache[slot].bytes = bytes;
-    g_ws_cache[slot].device = device;
-    return evicted;
+    for (int i = 0; i < ndrop; ++i) workspace_free_on(drop[i].ptr, drop[i].device);
+}
+inline void workspace_cache_trim() {
+    CachedBlock drop[kWorkspaceCacheBlocks];
+    {
+        std::lock_guard<std::mutex> lock(g_ws_cache_mutex);
+        for (int i = 0; i < kWorkspaceCacheBlocks; ++i) {
+            drop[i] = g_ws_cache[i];
+            g_ws_cache[i] = CachedBlock();
+        }
+    }
+    for (const CachedBlock &c : drop)
+        if (c.ptr != nullptr) workspace_free_on(c.ptr, c.device);
+}
+inline void workspace_cache_set_limit(size_t bytes) {
+    {
+        std::lock_guard<std::mutex> lock(g_ws_cache_mutex);
+        g_ws_cache_limit = bytes;
+    }
+    if (bytes == 0) workspace_cache_trim();
 }
 
 // Kernel launch, optionally as a programmatic dependent of the previous kernel in the stream (common.cuh).
@@ -315,6 +364,7 @@ class Engine {
         size_t bytes = 0;
         const RNNTStatus st = workspace_size(&bytes);
         if (st != RNNT_STATUS_SUCCESS) return st;
+        release_owned();  // (a second create_workspace() without free_workspace(): the first block is not leaked)
         int device = 0;
         if (cudaGetDevice(&device) != cudaSuccess) return RNNT_STATUS_EXECUTION_FAILED;
         size_t got = bytes;
@@ -327,22 +377,19 @@ class Engine {
     }
 
     void free_workspace() {
-        if (owned_ != nullptr) {
-            // like cudaFree, return only when nothing on the device can still touch the block; then keep it
-            (void)cudaDeviceSynchronize();
-            void *drop = workspace_cache_put(owned_, owned_bytes_, owned_device_);
-            if (drop != nullptr) cudaFree(drop);
-        }
-        owned_ = nullptr;
+        release_owned();
         base_ = nullptr;
     }
 
     // Restrict the lattice to a band around `alignments` ([B, T_max] device ints).  Takes effect at the
     // next compute() on that call's stream; `alignments` must stay valid until then.
-    void restrict_to_alignment(const int *alignments, int max_shift, int blank_idx) {
+    // `stride`: ints per utterance in `alignments`; 0 = the reference's rule, max_b T_b (cpu_workspace_manager.h:208).
+    // A stride below max_b T_b is refused by the next compute call (RNNT_STATUS_INVALID_VALUE).
+    void restrict_to_alignment(const int *alignments, int max_shift, int blank_idx, int stride = 0) {
         alignment_ = alignments;
         max_shift_ = max_shift;
         align_blank_ = blank_idx;
+        align_stride_ = stride;
         band_dirty_ = true;
     }
 
@@ -393,15 +440,24 @@ class Engine {
         RNNTStatus st = ensure_shape();
         if (st != RNNT_STATUS_SUCCESS) return st;
         if (base_ == nullptr || blank < 0 || blank >= V_) return RNNT_STATUS_INVALID_VALUE;
-        const CostStage stage = acquire_cost_stage(static_cast<size_t>(B_));
+        if (peer_failed_) return RNNT_STATUS_EXECUTION_FAILED;  // an exchange gave up earlier: final (peer_reduce.cuh)
+        // (one word behind the costs: the exchange's "gave up" flag)
+        const CostStage stage = acquire_cost_stage(static_cast<size_t>(B_) + 1);
         costs_mapped_ = stage.host;
+        if (stage.host != nullptr) reinterpret_cast<volatile unsigned *>(stage.host)[B_] = 0u;
         st = enqueue(blank, stream, grads_dev);
         costs_mapped_ = nullptr;
         if (st == RNNT_STATUS_SUCCESS && stage.host == nullptr &&
             cudaMemcpyAsync(costs_host, ws_.costs, sizeof(float) * B_, cudaMemcpyDeviceToHost, stream) != cudaSuccess)
             st = RNNT_STATUS_MEMOPS_FAILED;
         if (st == RNNT_STATUS_SUCCESS && cudaStreamSynchronize(stream) != cudaSuccess) st = RNNT_STATUS_EXECUTION_FAILED;
-        if (st == RNNT_STATUS_SUCCESS && stage.host != nullptr) std::memcpy(costs_host, stage.host, sizeof(float) * B_);
+        if (st == RNNT_STATUS_SUCCESS && stage.host != nullptr) {
+            std::memcpy(costs_host, stage.host, sizeof(float) * B_);
+            if (reinterpret_cast<volatile unsigned *>(stage.host)[B_] != 0u) {
+                peer_failed_ = true;
+                st = RNNT_STATUS_EXECUTION_FAILED;
+            }
+        }
         if (st != RNNT_STATUS_SUCCESS && stage.host != nullptr) (void)cudaStreamSynchronize(stream);  // nothing may still write into it
         release_cost_stage(stage);
         return st;
@@ -480,8 +536,16 @@ class Engine {
         peer_.world = world;
         peer_.total_out = total_out;
         peer_.epoch = 0u;
+        peer_.timeout_ns = peer_timeout_ns_;
+        peer_failed_ = false;
         return RNNT_STATUS_SUCCESS;
     }
+    // How long the collect waits for the slowest peer before it gives up for good (0: without limit).
+    void set_peer_timeout_ms(unsigned ms) {
+        peer_timeout_ns_ = static_cast<unsigned long long>(ms) * 1000000ull;
+        peer_.timeout_ns = peer_timeout_ns_;
+    }
+    bool peer_failed() const { return peer_failed_; }
     // Steps already exchanged through the boards by ANOTHER handle (the epoch belongs to the boards, not to the handle).
     void set_peer_epoch(unsigned epoch) { peer_.epoch = epoch; }
     unsigned peer_epoch() const { return peer_.epoch; }
@@ -529,7 +593,11 @@ class Engine {
     ~Engine() {
         if (timing_)
             for (auto &e : ev_) cudaEventDestroy(e);
+        release_owned();  // (mrnnt_destroy without mrnnt_free_workspace)
     }
+
+    // Kernel launches this engine has made so far (set-up kernels included).
+    unsigned long long launch_count() const { return launches_; }
 
     // Force the generic (non-TMA) streaming kernels; used by the tests to cross-check both variants.
     void set_force_generic(bool v) { force_generic_ = v; }
@@ -557,7 +625,24 @@ class Engine {
         if (timing_) cudaEventRecord(ev_[i], stream);
     }
 
-    static RNNTStatus launched() { return cudaGetLastError() == cudaSuccess ? RNNT_STATUS_SUCCESS : RNNT_STATUS_EXECUTION_FAILED; }
+    RNNTStatus launched() {
+        ++launches_;
+        return cudaGetLastError() == cudaSuccess ? RNNT_STATUS_SUCCESS : RNNT_STATUS_EXECUTION_FAILED;
+    }
+
+    // Hand the block create_workspace() allocated back (to the module's cache, or to the driver).  Like cudaFree it
+    // returns only when nothing on the block's device can still touch it.
+    void release_owned() {
+        if (owned_ == nullptr) return;
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess) cur = -1;
+        if (cur != owned_device_) (void)cudaSetDevice(owned_device_);
+        (void)cudaDeviceSynchronize();
+        if (cur != owned_device_ && cur >= 0) (void)cudaSetDevice(cur);
+        workspace_cache_put(owned_, owned_bytes_, owned_device_);
+        if (base_ == owned_) base_ = nullptr;
+        owned_ = nullptr;
+    }
 
     RNNTStatus setup(cudaStream_t stream) {
         if (plan_dirty_) {
@@ -572,7 +657,9 @@ class Engine {
                 if (smem > static_cast<size_t>(device_info().max_smem_optin) - 1024) return RNNT_STATUS_INVALID_VALUE;
                 if (!ensure_dynamic_smem(band_kernel, smem)) return RNNT_STATUS_EXECUTION_FAILED;
             }
-            band_kernel<<<B_, kBandThreads, smem, stream>>>(T_dev_, S_dev_, shape_.T_max, alignment_, max_shift_,
+            if (alignment_ != nullptr && align_stride_ != 0 && align_stride_ < shape_.T_max) return RNNT_STATUS_INVALID_VALUE;
+            band_kernel<<<B_, kBandThreads, smem, stream>>>(T_dev_, S_dev_, shape_.T_max, alignment_,
+                                                            align_stride_ > 0 ? align_stride_ : shape_.T_max, max_shift_,
                                                             align_blank_, ws_.band);
             if (launched() != RNNT_STATUS_SUCCESS) return RNNT_STATUS_EXECUTION_FAILED;
             const int64_t blocks64 = (shape_.rows + 255) / 256;
@@ -745,7 +832,11 @@ class Engine {
         a.rows = shape_.rows;
         a.B = B_;
         a.phase_ctas = 0;
-        if (K > 0) {
+        // (a padded tensor with many label positions per frame can ask for more shared memory than an SM has while its
+        // longest label sequence still fits the row of warps: the block-wide kernel takes it then)
+        const bool warp_kernel_fits =
+            K > 0 && k2_smem_bytes(shape_.width(), k2_row_warps(states, K)) <= static_cast<size_t>(dev.max_smem_optin);
+        if (warp_kernel_fits) {
             a.row_warps = k2_row_warps(states, K);
             a.chunk_bufs = k2_chunk_bufs(a.row_warps);
             // the zero fill needs bulk-copy granularity (16 bytes) and whole warps next to the chain warps and
@@ -888,6 +979,7 @@ class Engine {
         p = peer_;
         p.costs = ws_.costs;
         p.B = B_;
+        p.status_out = costs_mapped_ != nullptr ? reinterpret_cast<unsigned *>(costs_mapped_) + B_ : nullptr;
         return p;
     }
 
@@ -922,6 +1014,8 @@ class Engine {
     bool plan_dirty_ = true;
     bool band_dirty_ = true;
     const int *alignment_ = nullptr;
+    int align_stride_ = 0;  // ints per utterance in alignment_ (0: max_b T_b)
+    unsigned long long launches_ = 0;
     int max_shift_ = 0;
     int align_blank_ = 0;
     bool force_generic_ = false;
@@ -947,6 +1041,8 @@ class Engine {
     int last_k2_zero_warps_ = 0;        // what the last lattice launch ran with
     int k2_zero_warps_ = -1;            // warps per lattice CTA for the zero fill: -1 automatic, 0 off
     PeerReduce peer_{};           // set_peer_reduce(): world > 0 when on; epoch = the last one used
+    unsigned long long peer_timeout_ns_ = kPeerDefaultTimeoutNs;
+    bool peer_failed_ = false;    // a collect of this handle gave up: every later synchronous call fails
     bool peer_in_k3_ = false;     // this call's exchange rides in the gradient kernel
     bool k3_follows_k2_ = false;  // K3 is being enqueued directly behind K2 (enqueue(), not a separate backward)
     unsigned epoch_ = 0u;  // launch counter published through Workspace::k2_flags

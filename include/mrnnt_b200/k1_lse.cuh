@@ -231,7 +231,12 @@ struct TileGrabber {
         unsigned seen = 0u;
 #pragma unroll
         for (int i = 0; i < kGrabDepth; ++i) seen |= __shfl_sync(0xffffffffu, raw[i], 0);
-        if (lane == 0 && atomicAdd(ctr + 1, (seen & 0u) + 1u) == gridDim.x - 1u) {
+        // (the report must not be issued before the answers have arrived: the asm turns `seen` -- and with it the
+        // outstanding atomics' results -- into a zero the compiler cannot fold away, and the fence orders lane 0's
+        // grabs before its report whatever the compiler does)
+        asm volatile("and.b32 %0, %0, 0;" : "+r"(seen));
+        __threadfence();
+        if (lane == 0 && atomicAdd(ctr + 1, seen + 1u) == gridDim.x - 1u) {
             ctr[0] = 0u;
             ctr[1] = 0u;
             __threadfence();

@@ -77,8 +77,8 @@ struct K2Args {
     double *ll_bwd;
     float *costs;
     float *costs_mapped;  // optional second copy of the costs in host-mapped pinned memory (nullptr: none)
-    unsigned *flags;   // [2B] per utterance: phase-A arrival counter, "recursion done" epoch (zeroed at set-up)
-    unsigned epoch;    // value published by this launch (never 0)
+    unsigned *flags;   // two alternating sets of kK2FlagWords hand-over words per utterance (plan.cuh), zeroed at set-up
+    unsigned epoch;    // launch counter (never 0): picks the set, and is the value part 0 publishes when its recursions are done
     int T_max;
     int S_max;
     int ld;            // rows per frame: 0 = packed layout (S_b + 1 per utterance), else the fixed U of a padded tensor
@@ -592,10 +592,19 @@ __device__ __forceinline__ void k2_st_release(unsigned *p, unsigned v) {
 __device__ __forceinline__ void k2_await(const unsigned *flag, unsigned value) {
     while (k2_ld_acquire(flag) != value) __nanosleep(100);
 }
+__device__ __forceinline__ void k2_await_ge(const unsigned *flag, unsigned value) {
+    while (k2_ld_acquire(flag) < value) __nanosleep(100);
+}
 
-// grid B * parts: CTA index = b * parts + part.  The engine sizes `parts` so that the whole grid is co-resident
-// (parts * B <= SM count), and CTAs are dispatched in index order, so a waiting CTA never keeps the CTA it
-// waits for off the machine.
+// grid B * parts: CTA index = b * parts + part.  No CTA ever waits for a CTA that may not have been dispatched yet, so
+// the kernel cannot deadlock whatever else shares the device (a second lattice launch on another stream, another
+// process under MPS, fewer SMs than the occupancy query saw):
+//   * the rows of phases A and C are handed out in blocks through per-utterance counters (`parts` only says how many
+//     CTAs were launched to share them).  Part 0 takes blocks too; once the counter has run out it waits for the blocks
+//     that were TAKEN -- by CTAs that are therefore running -- and does everything itself if no helper ever shows up;
+//   * a helper waits for its own utterance's part 0 only, a CTA with a lower index (CTAs are dispatched in index order).
+// Every CTA keeps one request for a block in flight while it works on the previous one.
+// The hand-over words come in two sets that take turns (plan.cuh: kK2FlagWords); this launch clears the other set.
 // Barrier among the warps that run the phases (all of them, or all but the zero-fill warps -- those take part in
 // nothing else: their stores wait on the memory system).
 __device__ __forceinline__ void k2_phase_sync(int zero_warps) {
@@ -603,9 +612,36 @@ __device__ __forceinline__ void k2_phase_sync(int zero_warps) {
     else asm volatile("bar.sync 1, %0;" ::"r"((kK2Warps - zero_warps) * kWarp) : "memory");
 }
 
+// One block hand-out loop (phase A or C), whole phase-warp set.  `next`: the counter; `held` (thread `tid` 0 only): a
+// request made earlier, or kK2NoTicket.  fn(block, nblocks) does the rows.  Returns when the counter has run out.
+constexpr unsigned kK2NoTicket = 0xffffffffu;
+template <typename Fn>
+__device__ __forceinline__ void k2_block_loop(unsigned *next, unsigned *done, unsigned held, int nblk, int tid, int zw,
+                                              unsigned *ticket_sh, Fn fn) {
+    unsigned nxt = held;
+    for (int it = 0;; ++it) {
+        if (tid == 0) {
+            if (nxt == kK2NoTicket) nxt = atomicAdd(next, 1u);
+            ticket_sh[it & 1] = nxt;
+            // (the answer is looked at one block later: its round trip hides behind this block's rows)
+            nxt = nxt < static_cast<unsigned>(nblk) ? atomicAdd(next, 1u) : nxt;
+        }
+        k2_phase_sync(zw);
+        const unsigned blk = ticket_sh[it & 1];
+        if (blk >= static_cast<unsigned>(nblk)) break;
+        fn(static_cast<int>(blk), nblk);
+        if (done != nullptr) {
+            __threadfence();
+            k2_phase_sync(zw);
+            if (tid == 0) atomicAdd(done, 1u);
+        }
+    }
+}
+
 template <int K>
 static __global__ void __launch_bounds__(kK2Threads) k2_lattice_kernel(K2Args a) {
     extern __shared__ __align__(128) unsigned char k2_smem[];
+    __shared__ unsigned ticket_sh[2];
     const int parts = a.parts;
     const int warp = threadIdx.x >> 5;
     const int zw = a.zero_warps;           // warps 0..zw-1 do the zero fill and nothing else
@@ -622,8 +658,8 @@ static __global__ void __launch_bounds__(kK2Threads) k2_lattice_kernel(K2Args a)
     const int b = blockIdx.x / parts;
     const int part = blockIdx.x - b * parts;
     const int tid = threadIdx.x - zw * kWarp;  // thread index among the phase warps; tid 0 leads
-    unsigned *arrived = a.flags + 2 * b;  // phase-A arrivals of this utterance's parts
-    unsigned *done = arrived + 1;         // epoch of the last finished recursion
+    unsigned *fl = a.flags + (static_cast<size_t>(a.epoch & 1u) * a.B + b) * kK2FlagWords;
+    unsigned *a_next = fl, *a_done = fl + 1, *c_next = fl + 2, *done = fl + 3;
     if (warp < zw) {
         // ---- zero fill: this warp's share of the batch's dead rows, nothing else (and nothing K1 wrote) ----
         if (warp == 0) MRNNT_K2_STAMP(53);
@@ -632,18 +668,27 @@ static __global__ void __launch_bounds__(kK2Threads) k2_lattice_kernel(K2Args a)
         return;
     }
     const int nphase = kK2Threads - zw * kWarp;
+    const int nblk = 2 * parts;  // blocks per phase: two per launched CTA
     MRNNT_K2_STAMP(0);
+    // the first request for a block of phase A needs nothing of K1's: its round trip overlaps the wait for K1
+    unsigned held = (parts > 1 && tid == 0) ? atomicAdd(a_next, 1u) : kK2NoTicket;
     pdl_wait();  // K1's records
-    if (blockIdx.x == 0 && tid == 0 && a.zero_clear != nullptr) *a.zero_clear = 0u;
-
-    // ---- phase A: transition weights, all parts ----
-    k2_weight_rows(a, b, part, parts, tid, nphase);
-    if (parts > 1) {
-        __threadfence();
-        k2_phase_sync(zw);
-        if (tid == 0) atomicAdd(arrived, 1u);
+    if (blockIdx.x == 0) {
+        if (tid == 0 && a.zero_clear != nullptr) *a.zero_clear = 0u;
+        // the other set of hand-over words, for the next launch (its last user, the previous launch, is long gone)
+        unsigned *other = a.flags + static_cast<size_t>((a.epoch + 1u) & 1u) * a.B * kK2FlagWords;
+        for (int i = tid; i < a.B * kK2FlagWords; i += nphase) other[i] = 0u;
     }
 
+    // ---- phase A: transition weights ----
+    if (parts > 1) {
+        k2_block_loop(a_next, a_done, held, nblk, tid, zw, ticket_sh,
+                      [&](int blk, int n) { k2_weight_rows(a, b, blk, n, tid, nphase); });
+    } else {
+        k2_weight_rows(a, b, 0, 1, tid, nphase);
+    }
+
+    unsigned held_c = kK2NoTicket;
     if (part == 0) {
         // ---- phase B: the two recursions ----
         MRNNT_K2_STAMP(60);
@@ -660,10 +705,8 @@ static __global__ void __launch_bounds__(kK2Threads) k2_lattice_kernel(K2Args a)
         }
         if (tid == 0) {
             mbar_init_fence();
-            if (parts > 1) {
-                k2_await(arrived, static_cast<unsigned>(parts));
-                *arrived = 0u;  // every part has arrived; nobody touches the counter again in this launch
-            }
+            // every block of phase A has been taken (the counter ran out above); the takers are running CTAs
+            if (parts > 1) k2_await_ge(a_done, static_cast<unsigned>(nblk));
         }
         k2_phase_sync(zw);  // (parts == 1: this is also what orders phase A before the bulk copies)
         MRNNT_K2_STAMP(61);
@@ -694,11 +737,20 @@ static __global__ void __launch_bounds__(kK2Threads) k2_lattice_kernel(K2Args a)
         MRNNT_K2_STAMP(51);
     } else {
         if (!a.need_beta) return;
-        if (tid == 0) k2_await(done, a.epoch);
+        // a helper asks for its first block of phase C while it waits for the recursions of its utterance's part 0
+        if (tid == 0) {
+            held_c = atomicAdd(c_next, 1u);
+            k2_await(done, a.epoch);
+        }
         k2_phase_sync(zw);
     }
-    // ---- phase C: gradient coefficients, all parts ----
-    k2_coef_rows(a, b, part, parts, tid, nphase);
+    // ---- phase C: gradient coefficients ----
+    if (parts > 1) {
+        k2_block_loop(c_next, nullptr, held_c, nblk, tid, zw, ticket_sh,
+                      [&](int blk, int n) { k2_coef_rows(a, b, blk, n, tid, nphase); });
+    } else {
+        k2_coef_rows(a, b, 0, 1, tid, nphase);
+    }
     k2_phase_sync(zw);
     MRNNT_K2_STAMP(52);
 }
@@ -720,6 +772,10 @@ static __global__ void __launch_bounds__(kK2Threads) k2_lattice_wide_kernel(K2Ar
     Cell *beta = a.beta + R;
     const int tid = threadIdx.x;
     if (b == 0 && tid == 0 && a.zero_clear != nullptr) *a.zero_clear = 0u;
+    if (b == 0) {  // (keeps the alternation of the hand-over words intact should launches of the two kernels ever mix)
+        unsigned *other = a.flags + static_cast<size_t>((a.epoch + 1u) & 1u) * a.B * kK2FlagWords;
+        for (int i = tid; i < a.B * kK2FlagWords; i += kK2Threads) other[i] = 0u;
+    }
 
     // K1's (max, sum) -> the denominator pair, in place (what phase A of the main kernel does); rows K1 skipped
     // hold garbage before and after, and are masked wherever they are read

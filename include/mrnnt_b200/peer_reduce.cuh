@@ -16,8 +16,14 @@
 //
 // The two parities make a slot safe to overwrite: rank r can only publish epoch e + 2 after it has collected epoch
 // e + 1, which every peer published after it had collected epoch e.
-// A peer that never shows up (crashed process) must not hang the GPU: the collect gives up after kPeerTimeoutNs and
-// leaves NaN.
+// A peer that never shows up (crashed process) must not hang the GPU for ever: the collect gives up after
+// `timeout_ns` (PeerReduce; the host's default is kPeerDefaultTimeoutNs = 60 s, ranks of a training job drift by
+// seconds around checkpoints, evaluation and first-step initialisation; 0 waits without limit) and leaves NaN.
+// Giving up is FINAL for this rank's board: the slot invariant above no longer holds once a rank has moved on without
+// collecting, so the board's `failed` word is set, every later publish through that board is suppressed (the peers
+// then time out as well instead of reading sums that belong to another step) and every later collect leaves NaN at
+// once; the host sees it in `status_out` and mrnnt_* calls of the handle return RNNT_STATUS_EXECUTION_FAILED from
+// then on (Engine::compute).  Recovery = new boards.
 #pragma once
 
 #include <cstdint>
@@ -27,7 +33,7 @@
 namespace mrnnt {
 
 constexpr int kPeerMaxWorld = 8;                          // one NVSwitch domain
-constexpr unsigned long long kPeerTimeoutNs = 2000000000ull;  // 2 s
+constexpr unsigned long long kPeerDefaultTimeoutNs = 60000000000ull;  // 60 s
 
 struct PeerReduce {
     unsigned long long *boards[kPeerMaxWorld];  // rank r's board as mapped into this process (boards[rank]: our own)
@@ -36,9 +42,15 @@ struct PeerReduce {
     int B;
     int rank, world;                            // world == 0: no reduce
     unsigned epoch;                             // > 0, the same on every rank for the same step
+    unsigned long long timeout_ns;              // collect gives up after this long (0: never)
+    unsigned *status_out;                       // optional (device or host-mapped): set to 1 when a collect gave up
 };
 
-__host__ __device__ inline size_t peer_board_bytes(int world) { return 2 * static_cast<size_t>(world) * 8; }
+// 2 * world slots, then the board's `failed` word (8 bytes: only its owner writes it)
+__host__ __device__ inline size_t peer_board_bytes(int world) { return 2 * static_cast<size_t>(world) * 8 + 8; }
+__device__ __forceinline__ unsigned long long *peer_failed_word(const PeerReduce &p) {
+    return p.boards[p.rank] + 2 * static_cast<size_t>(p.world);
+}
 
 __device__ __forceinline__ unsigned long long peer_pack(float v, unsigned epoch) {
     return (static_cast<unsigned long long>(epoch) << 32) | static_cast<unsigned long long>(__float_as_uint(v));
@@ -48,6 +60,7 @@ __device__ __forceinline__ unsigned long long peer_pack(float v, unsigned epoch)
 __device__ __forceinline__ void peer_publish(const PeerReduce &p) {
     if (p.world <= 0) return;
     const int lane = threadIdx.x & 31;
+    if (*reinterpret_cast<volatile unsigned long long *>(peer_failed_word(p)) != 0ull) return;  // (warp-uniform)
     float s = 0.0f;
     for (int i = lane; i < p.B; i += 32) s += p.costs[i];
 #pragma unroll
@@ -64,8 +77,8 @@ __device__ __forceinline__ void peer_collect(const PeerReduce &p) {
     if (p.world <= 0) return;
     const int lane = threadIdx.x & 31;
     float mine = 0.0f;
-    bool ok = true;
-    if (lane < p.world) {
+    bool ok = *reinterpret_cast<volatile unsigned long long *>(peer_failed_word(p)) == 0ull;
+    if (ok && lane < p.world) {
         const unsigned long long *slot = p.boards[p.rank] + (p.epoch & 1u) * static_cast<unsigned>(p.world) + lane;
         unsigned long long t0 = 0ull, v;
         for (unsigned spins = 0;; ++spins) {
@@ -75,7 +88,7 @@ __device__ __forceinline__ void peer_collect(const PeerReduce &p) {
                 unsigned long long now;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
                 if (t0 == 0ull) t0 = now;
-                else if (now - t0 > kPeerTimeoutNs) {
+                else if (p.timeout_ns != 0ull && now - t0 > p.timeout_ns) {
                     ok = false;
                     break;
                 }
@@ -86,8 +99,12 @@ __device__ __forceinline__ void peer_collect(const PeerReduce &p) {
     ok = __all_sync(0xffffffffu, ok);
     float total = 0.0f;
     for (int r = 0; r < p.world; ++r) total += __shfl_sync(0xffffffffu, mine, r);  // rank order: the same bits everywhere
-    if (lane == 0 && p.total_out != nullptr) {
-        *p.total_out = ok ? total : __int_as_float(0x7fc00000);
+    if (lane == 0) {
+        if (!ok) {
+            *peer_failed_word(p) = 1ull;  // final: see the head of this file
+            if (p.status_out != nullptr) *p.status_out = 1u;
+        }
+        if (p.total_out != nullptr) *p.total_out = ok ? total : __int_as_float(0x7fc00000);
         __threadfence_system();
     }
 }

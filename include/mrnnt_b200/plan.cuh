@@ -8,7 +8,7 @@
 // Layout of the packed inputs (unchanged from the reference, cpu_workspace_manager.h:46-49,117-135):
 //   acts   [rows, V]   rows = sum_b T_b*(S_b+1); row of (b,t,s) = row_start[b] + t*(S_b+1) + s
 //   labels [B, S_max]  S_max = max_b S_b
-//   alignment [B, T_max], T_max = max_b T_b
+//   alignment [B, T_max], T_max = max_b T_b   (or [B, align_stride] with align_stride >= T_max, an extension)
 #pragma once
 
 #include <cstddef>
@@ -48,18 +48,23 @@ struct Workspace {
     double *ll_fwd = nullptr;      // [B]     alpha(T-1, S)
     double *ll_bwd = nullptr;      // [B]     beta(0, 0)  (diagnostic, as in the reference)
     float *costs = nullptr;        // [B]     -ll_fwd
-    unsigned *k2_flags = nullptr;  // [k2_flag_words(B)] per utterance: phase-A arrivals, epoch of the last recursion;
-                                   //         then, in a cache line of their own, the zero fill's two counters
+    unsigned *k2_flags = nullptr;  // [k2_flag_words(B)] two alternating sets of kK2FlagWords hand-over words per utterance;
+                                   //         then, in cache lines of their own, the zero fill's and the tile hand-out's counters
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Bytes needed for `shape`.  A function of (B, T[], S[]) only, like the reference
 // (gpu_workspace_manager.h:242-247); the value differs (60 B/row + O(B*T_max) instead of 12 B/row).
-// words of Workspace::k2_flags: 2 per utterance, then (256 bytes clear of the flags that waiting CTAs poll) the
-// counters of the zero fill (zero_fill.cuh): two of the OWNED protocol, then the two alternating ones of the SHARED
-// protocol
-__host__ __device__ inline size_t k2_zero_ctr_word(int B) { return (2 * static_cast<size_t>(B) + 63) / 64 * 64 + 64; }
+// words of Workspace::k2_flags: two SETS of kK2FlagWords per utterance that take turns from launch to launch (a lattice
+// launch uses set `epoch & 1` and clears the other one for its successor: nothing in a launch ever has to reset a word
+// that a late CTA of the same launch might still touch), then (256 bytes clear of the flags that waiting CTAs poll)
+// the counters of the zero fill (zero_fill.cuh): two of the OWNED protocol, then the two alternating ones of the
+// SHARED protocol
+constexpr int kK2FlagWords = 4;  // per utterance: {phase-A blocks handed out, phase-A blocks done, phase-C blocks handed out, recursion done}
+__host__ __device__ inline size_t k2_zero_ctr_word(int B) {
+    return (2 * kK2FlagWords * static_cast<size_t>(B) + 63) / 64 * 64 + 64;
+}
 // ... and, a cache line further on, the tile hand-out counter of the gradient kernel's dynamic mode (k3_grad.cuh):
 // {tiles handed out, producers finished}; zero between launches
 __host__ __device__ inline size_t stream_ctr_word(int B) { return k2_zero_ctr_word(B) + 64; }
@@ -175,7 +180,8 @@ constexpr int kBandThreads = 256;
 
 static __global__ void __launch_bounds__(kBandThreads) band_kernel(const int *__restrict__ T, const int *__restrict__ S,
                                                              int T_max, const int *__restrict__ alignment,
-                                                             int max_shift, int blank_idx, int2 *__restrict__ band) {
+                                                             int align_stride, int max_shift, int blank_idx,
+                                                             int2 *__restrict__ band) {
     extern __shared__ int m_sh[];  // [T_b + 1] when alignment != nullptr
     __shared__ int warp_tot[kBandThreads / kWarp];
     __shared__ int carry_sh;
@@ -186,7 +192,7 @@ static __global__ void __launch_bounds__(kBandThreads) band_kernel(const int *__
         for (int t = threadIdx.x; t < T_max; t += kBandThreads) band_b[t] = make_int2(0, Sb);
         return;
     }
-    const int *al = alignment + static_cast<size_t>(b) * T_max;
+    const int *al = alignment + static_cast<size_t>(b) * align_stride;  // (the reference's stride: T_max)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         carry_sh = 0;

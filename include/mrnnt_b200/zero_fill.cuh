@@ -127,7 +127,9 @@ __device__ __forceinline__ void zero_dead_rows_impl(const ZeroFill &a, int fw, i
         unsigned seen = 0u;
 #pragma unroll
         for (int i = 0; i < D; ++i) seen += __shfl_sync(0xffffffffu, raw[i], 0);
-        if (lane == 0 && atomicAdd(ctr + 1, seen * 0u + 1u) == static_cast<unsigned>(nfw) - 1u) {
+        asm volatile("and.b32 %0, %0, 0;" : "+r"(seen));  // (a zero the compiler cannot fold: the grabs' answers are inputs of the report)
+        __threadfence();
+        if (lane == 0 && atomicAdd(ctr + 1, seen + 1u) == static_cast<unsigned>(nfw) - 1u) {
             ctr[0] = 0u;
             ctr[1] = 0u;
             __threadfence();

@@ -30,6 +30,8 @@ typedef struct mrnnt_handle_st *mrnnt_handle_t;
  * (reference include/gpu_workspace_manager.h:228-254) for callers that hold the lengths on the host.
  * Same validation: B <= 0, T_b <= 0, S_b < 0 or T_b < S_b -> RNNT_STATUS_INVALID_VALUE. */
 RNNTStatus mrnnt_get_workspace_size(const int *T_host, const int *S_host, int B, int V, size_t *size_bytes);
+/* The same under the name the reference's manager uses for it (gpu_workspace_manager.h:228): */
+RNNTStatus get_workspace_size(const int *T_host, const int *S_host, int B, int V, size_t *size_bytes);
 
 /* Handle = one GpuRNNTWorkspaceManager<float> (reference include/gpu_workspace_manager.h:33-52).
  * T_host / S_host may be NULL; the lengths are then fetched from the device once (blocking). */
@@ -59,10 +61,26 @@ RNNTStatus mrnnt_workspace_size(mrnnt_handle_t h, size_t *size_bytes);
 RNNTStatus mrnnt_set_workspace(mrnnt_handle_t h, void *workspace);
 RNNTStatus mrnnt_create_workspace(mrnnt_handle_t h);
 void mrnnt_free_workspace(mrnnt_handle_t h);
+/* Blocks handed back by mrnnt_free_workspace / GpuRNNTWorkspaceManager::free_workspace are kept for the next
+ * create_workspace of this library instead of going through cudaFree + cudaMalloc (the reference's torch binding
+ * allocates and frees the workspace on every loss call: 2.9 ms against 0.36 ms on B=32 T=150 S=40 V=1000).  At most 4
+ * blocks and `bytes` bytes are kept (default 1 GiB); 0 turns the cache off, free_workspace is then a cudaFree as in the
+ * reference.  mrnnt_trim_workspace_cache returns everything that is cached to the driver now. */
+void mrnnt_set_workspace_cache_limit(size_t bytes);
+void mrnnt_trim_workspace_cache(void);
 
 /* gpu_workspace_manager.h:191-219.  Recorded here, applied on the device by the next compute call on
  * that call's stream; `alignments` must stay valid until then.  May be called repeatedly. */
 RNNTStatus mrnnt_restrict_to_alignment(mrnnt_handle_t h, const int *alignments, int max_shift, int blank_idx);
+/* Same for an alignment array that is wider than the reference's [B, max_b T_b] (e.g. [B, T_dim] next to a padded acts
+ * tensor): `stride` ints per utterance, >= max_b T_b -- a smaller stride makes the next compute call return
+ * RNNT_STATUS_INVALID_VALUE (the reference mis-indexes such an array silently, cpu_workspace_manager.h:208). */
+RNNTStatus mrnnt_restrict_to_alignment_strided(mrnnt_handle_t h, const int *alignments, int stride, int max_shift,
+                                               int blank_idx);
+/* max_b T_b, max_b S_b and the row count of acts as this handle understands them (from the lengths it was given or has
+ * fetched): what a binding needs to check the second dimension of its labels / alignment tensors against, which the
+ * reference never does. */
+RNNTStatus mrnnt_get_shape(mrnnt_handle_t h, int *T_max, int *S_max, int64_t *rows);
 
 /* No counterpart in the reference, whose callers bring the logits to the device themselves (pytorch_binding/
  * monotonic_rnnt.cu:85-88 takes CUDA tensors): fill the handle's device `acts` from PINNED host memory of the same layout
@@ -108,7 +126,8 @@ RNNTStatus mrnnt_enqueue_forward_into(mrnnt_handle_t h, int blank_label, void *s
  * end), else in a one-warp launch behind the lattice kernel.  All ranks must make the same sequence of such calls
  * (it is a collective).  The epoch counts the exchanges a set of boards has carried: pass 0 for fresh boards, and
  * when a NEW handle takes over boards already in use, mrnnt_peer_epoch() of the handle that used them last.
- * A rank whose peers do not show up within 2 s gets NaN instead of hanging the GPU.  world <= 8 (one NVSwitch
+ * A rank whose peers do not show up within the time-out (mrnnt_set_peer_timeout_ms) gets NaN instead of hanging the
+ * GPU, and an error status from then on.  world <= 8 (one NVSwitch
  * domain); in one process (several handles on one device or on peer-enabled devices) plain device pointers do. */
 RNNTStatus mrnnt_peer_board_create(int world, void **board_dev, unsigned char ipc_handle[64]);
 RNNTStatus mrnnt_peer_board_open(const unsigned char ipc_handle[64], void **peer_ptr);
@@ -117,6 +136,12 @@ RNNTStatus mrnnt_peer_board_destroy(void *board_dev);
 RNNTStatus mrnnt_set_peer_reduce(mrnnt_handle_t h, int rank, int world, void *const *boards, float *total_out,
                                  unsigned epoch);
 unsigned mrnnt_peer_epoch(mrnnt_handle_t h);
+/* How long a rank waits for its slowest peer (default 60 s; 0 = without limit).  A rank that gives up gets NaN in
+ * *total_out, its board is marked failed for good -- it publishes nothing any more, so that its peers run into their own
+ * time-outs instead of reading sums of another step -- and mrnnt_cost_and_grad returns RNNT_STATUS_EXECUTION_FAILED from
+ * that call on (mrnnt_peer_failed).  Recovery: new boards (mrnnt_peer_board_create ...) and mrnnt_set_peer_reduce. */
+RNNTStatus mrnnt_set_peer_timeout_ms(mrnnt_handle_t h, unsigned milliseconds);
+int mrnnt_peer_failed(mrnnt_handle_t h);
 
 /* One-shot convenience: size check + set_workspace + optional restrict_to_alignment + cost_and_grad. */
 RNNTStatus rnnt_loss_grad_gpu(const float *acts, const int *labels, const int *T_dev, const int *S_dev,
@@ -137,13 +162,14 @@ enum {
     MRNNT_OPT_K2_ZERO_FILL = 9,  /* who zeroes the gradient's dead rows: 0 the gradient kernel's consumer warps; 1..4
                                     that many warps per lattice CTA, while the recursions run; 32 one more warp of
                                     the gradient kernel, next to its consumers; -1 automatic                    */
-    MRNNT_OPT_DYNAMIC_TILES = 10 /* the gradient kernel hands its tiles out through a counter instead of round-robin by
+    MRNNT_OPT_DYNAMIC_TILES = 10,/* the gradient kernel hands its tiles out through a counter instead of round-robin by
                                     CTA index: 1 / 0 forced, -1 automatic; 2..100: through the counter once that
                                     percentage of a CTA's round-robin share has been worked off                  */
+    MRNNT_OPT_LAUNCH_COUNT = 11  /* mrnnt_get_option only: kernel launches this handle has made so far (low 31 bits) */
 };
 RNNTStatus mrnnt_set_option(mrnnt_handle_t h, int option, int value);
-/* What the last call actually did: MRNNT_OPT_K2_ZERO_FILL -> 0, 1..4 or 32 as above.  Other options:
-   RNNT_STATUS_INVALID_VALUE. */
+/* What the last call actually did: MRNNT_OPT_K2_ZERO_FILL -> 0, 1..4 or 32 as above; MRNNT_OPT_LAUNCH_COUNT.  Other
+   options: RNNT_STATUS_INVALID_VALUE. */
 RNNTStatus mrnnt_get_option(mrnnt_handle_t h, int option, int *value);
 /* Durations in ms of K1, K2, K3 of the last call (MRNNT_OPT_TIMING on, stream synchronised). */
 RNNTStatus mrnnt_last_timings(mrnnt_handle_t h, float ms_k1_k2_k3[3]);

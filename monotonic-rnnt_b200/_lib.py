@@ -23,6 +23,7 @@ OPT_PDL = 7
 OPT_K1_COMPACT = 8
 OPT_K2_ZERO_FILL = 9
 OPT_DYNAMIC_TILES = 10
+OPT_LAUNCH_COUNT = 11
 DBG_DENOM, DBG_ALPHA, DBG_BETA, DBG_LP, DBG_BAND, DBG_ROWMETA, DBG_LL, DBG_ROWSTART = range(1, 9)
 
 # every symbol include/mrnnt_c_api.h and include/rnnt_entrypoint.h declare
@@ -35,6 +36,8 @@ EXPORTED_SYMBOLS = (
     "mrnnt_get_workspace_size_padded", "mrnnt_set_dtype",
     "mrnnt_peer_board_create", "mrnnt_peer_board_open", "mrnnt_peer_board_close", "mrnnt_peer_board_destroy",
     "mrnnt_set_peer_reduce", "mrnnt_peer_epoch", "mrnnt_upload_acts",
+    "get_workspace_size", "mrnnt_restrict_to_alignment_strided", "mrnnt_get_shape", "mrnnt_set_workspace_cache_limit",
+    "mrnnt_trim_workspace_cache", "mrnnt_set_peer_timeout_ms", "mrnnt_peer_failed",
 )
 
 
@@ -63,6 +66,20 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mrnnt_free_workspace.argtypes = [vp]
     lib.mrnnt_free_workspace.restype = None
     lib.mrnnt_restrict_to_alignment.argtypes = [vp, vp, ci, ci]
+    lib.mrnnt_restrict_to_alignment_strided.argtypes = [vp, vp, ci, ci, ci]
+    lib.mrnnt_restrict_to_alignment_strided.restype = ci
+    lib.mrnnt_get_shape.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ctypes.c_int64)]
+    lib.mrnnt_get_shape.restype = ci
+    lib.get_workspace_size.argtypes = [vp, vp, ci, ci, szp]
+    lib.get_workspace_size.restype = ci
+    lib.mrnnt_set_workspace_cache_limit.argtypes = [sz]
+    lib.mrnnt_set_workspace_cache_limit.restype = None
+    lib.mrnnt_trim_workspace_cache.argtypes = []
+    lib.mrnnt_trim_workspace_cache.restype = None
+    lib.mrnnt_set_peer_timeout_ms.argtypes = [vp, ctypes.c_uint]
+    lib.mrnnt_set_peer_timeout_ms.restype = ci
+    lib.mrnnt_peer_failed.argtypes = [vp]
+    lib.mrnnt_peer_failed.restype = ci
     lib.mrnnt_upload_acts.argtypes = [vp, vp, vp]
     lib.mrnnt_upload_acts.restype = ci
     lib.mrnnt_cost_and_grad.argtypes = [vp, ci, vp, vp, vp]

@@ -67,6 +67,10 @@ RNNTStatus mrnnt_get_workspace_size(const int *T_host, const int *S_host, int B,
     return RNNT_STATUS_SUCCESS;
 }
 
+RNNTStatus get_workspace_size(const int *T_host, const int *S_host, int B, int V, size_t *size_bytes) {
+    return mrnnt_get_workspace_size(T_host, S_host, B, V, size_bytes);
+}
+
 RNNTStatus mrnnt_create(mrnnt_handle_t *out, const float *acts, const int *labels, int B, const int *T_dev,
                         const int *S_dev, int V, const int *T_host, const int *S_host) {
     if (out == nullptr) return RNNT_STATUS_INVALID_VALUE;
@@ -147,6 +151,27 @@ RNNTStatus mrnnt_restrict_to_alignment(mrnnt_handle_t h, const int *alignments, 
     h->manager.restrict_to_alignment(alignments, max_shift, blank_idx);
     return RNNT_STATUS_SUCCESS;
 }
+
+RNNTStatus mrnnt_restrict_to_alignment_strided(mrnnt_handle_t h, const int *alignments, int stride, int max_shift,
+                                               int blank_idx) {
+    if (h == nullptr || alignments == nullptr || stride <= 0) return RNNT_STATUS_INVALID_VALUE;
+    h->manager.engine().restrict_to_alignment(alignments, max_shift, blank_idx, stride);
+    return RNNT_STATUS_SUCCESS;
+}
+
+RNNTStatus mrnnt_get_shape(mrnnt_handle_t h, int *T_max, int *S_max, int64_t *rows) {
+    if (h == nullptr) return RNNT_STATUS_INVALID_VALUE;
+    mrnnt::Engine &e = h->manager.engine();
+    const RNNTStatus st = e.ensure_shape();
+    if (st != RNNT_STATUS_SUCCESS) return st;
+    if (T_max != nullptr) *T_max = e.shape().T_max;
+    if (S_max != nullptr) *S_max = e.shape().S_max;
+    if (rows != nullptr) *rows = e.shape().rows;
+    return RNNT_STATUS_SUCCESS;
+}
+
+void mrnnt_set_workspace_cache_limit(size_t bytes) { mrnnt::workspace_cache_set_limit(bytes); }
+void mrnnt_trim_workspace_cache(void) { mrnnt::workspace_cache_trim(); }
 
 RNNTStatus mrnnt_upload_acts(mrnnt_handle_t h, const void *host_acts, void *stream) {
     if (h == nullptr) return RNNT_STATUS_INVALID_VALUE;
@@ -258,6 +283,9 @@ RNNTStatus mrnnt_get_option(mrnnt_handle_t h, int option, int *value) {
     switch (option) {
         case MRNNT_OPT_K2_ZERO_FILL:
             *value = h->manager.engine().last_k2_zero_warps();
+            return RNNT_STATUS_SUCCESS;
+        case MRNNT_OPT_LAUNCH_COUNT:
+            *value = static_cast<int>(h->manager.engine().launch_count() & 0x7fffffffull);
             return RNNT_STATUS_SUCCESS;
         default:
             return RNNT_STATUS_INVALID_VALUE;
@@ -389,6 +417,14 @@ RNNTStatus mrnnt_set_peer_reduce(mrnnt_handle_t h, int rank, int world, void *co
 }
 
 unsigned mrnnt_peer_epoch(mrnnt_handle_t h) { return h == nullptr ? 0u : h->manager.engine().peer_epoch(); }
+
+RNNTStatus mrnnt_set_peer_timeout_ms(mrnnt_handle_t h, unsigned milliseconds) {
+    if (h == nullptr) return RNNT_STATUS_INVALID_VALUE;
+    h->manager.engine().set_peer_timeout_ms(milliseconds);
+    return RNNT_STATUS_SUCCESS;
+}
+
+int mrnnt_peer_failed(mrnnt_handle_t h) { return (h != nullptr && h->manager.engine().peer_failed()) ? 1 : 0; }
 
 RNNTStatus mrnnt_synth_uniform(float *dst_dev, int64_t n, uint64_t seed, int64_t index_offset, void *stream) {
     if (dst_dev == nullptr || n < 0) return RNNT_STATUS_INVALID_VALUE;

@@ -106,6 +106,21 @@ class LossHandle:
                 _lib.check(self._lib.mrnnt_set_dtype(self._h, 1), "mrnnt_set_dtype")
             _lib.check(self._lib.mrnnt_workspace_size(self._h, ctypes.byref(size)), "mrnnt_workspace_size")
             self.workspace_bytes = int(size.value)
+            # The ABI derives the label stride (max_b S_b) and the packed row count from the LENGTHS, not from the
+            # tensors (cpu_workspace_manager.h:44,117-135); the reference mis-indexes a wider labels tensor silently
+            # (SURVEY appendix C-11).  Here the shapes are checked against what the engine has just derived.
+            t_max, s_max, rows = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int64(0)
+            _lib.check(self._lib.mrnnt_get_shape(self._h, ctypes.byref(t_max), ctypes.byref(s_max), ctypes.byref(rows)),
+                       "mrnnt_get_shape")
+            self.T_max, self.S_max, self.rows = int(t_max.value), int(s_max.value), int(rows.value)
+            if not self.padded:
+                if int(acts.shape[0]) != self.rows:
+                    self.close()
+                    raise ValueError(f"packed acts must have sum_b T_b*(S_b+1) = {self.rows} rows, got {int(acts.shape[0])}")
+                if self.S_max >= 1 and (labels.dim() != 2 or int(labels.shape[1]) != self.S_max):
+                    self.close()
+                    raise ValueError(f"packed layout: labels must be [B, max_b S_b] = [{self.B}, {self.S_max}] (the ABI strides "
+                                     f"it by max_b S_b), got {tuple(labels.shape)}")
             # caller-owned workspace, as the TensorFlow op does with allocate_temp (monotonic_rnnt_op.cu:117-123)
             self.workspace = torch.empty(self.workspace_bytes, dtype=torch.uint8, device=acts.device)
             _lib.check(self._lib.mrnnt_set_workspace(self._h, self.workspace.data_ptr()), "mrnnt_set_workspace")
@@ -146,6 +161,13 @@ class LossHandle:
                                                    None if total_out is None else total_out.data_ptr(), boards.epoch),
                    "mrnnt_set_peer_reduce")
 
+    def set_peer_timeout_ms(self, ms: int) -> None:
+        """How long a call waits for the slowest rank's cost sum (default 60 s, 0 = for ever); see mrnnt_c_api.h."""
+        _lib.check(self._lib.mrnnt_set_peer_timeout_ms(self._h, int(ms)), "mrnnt_set_peer_timeout_ms")
+
+    def peer_failed(self) -> bool:
+        return bool(self._lib.mrnnt_peer_failed(self._h))
+
     def sync_peer_epoch(self) -> None:
         if getattr(self, "_boards", None) is not None:
             self._boards.epoch = int(self._lib.mrnnt_peer_epoch(self._h))
@@ -159,9 +181,16 @@ class LossHandle:
     def restrict_to_alignment(self, alignment: torch.Tensor, max_shift: int, blank_idx: int) -> None:
         if not alignment.is_cuda or alignment.dtype != torch.int32 or not alignment.is_contiguous():
             raise TypeError("alignment must be a contiguous CUDA int32 tensor [B, T_max]")
+        if alignment.dim() != 2 or int(alignment.shape[0]) != self.B or int(alignment.shape[1]) < self.T_max:
+            raise ValueError(f"alignment must be [B, >= max_b T_b] = [{self.B}, >= {self.T_max}], got {tuple(alignment.shape)}")
         self._alignment = alignment  # keep alive until the next compute call consumes it
-        _lib.check(self._lib.mrnnt_restrict_to_alignment(self._h, alignment.data_ptr(), int(max_shift), int(blank_idx)),
-                   "mrnnt_restrict_to_alignment")
+        width = int(alignment.shape[1])
+        if width == self.T_max:      # the reference's layout (cpu_workspace_manager.h:208)
+            st = self._lib.mrnnt_restrict_to_alignment(self._h, alignment.data_ptr(), int(max_shift), int(blank_idx))
+        else:                        # wider (e.g. [B, T_dim] next to a padded acts tensor): its own row stride
+            st = self._lib.mrnnt_restrict_to_alignment_strided(self._h, alignment.data_ptr(), width, int(max_shift),
+                                                               int(blank_idx))
+        _lib.check(st, "mrnnt_restrict_to_alignment")
 
     def upload_acts(self, host_acts: torch.Tensor, stream: Optional[torch.cuda.Stream] = None) -> None:
         """Fill the device ``acts`` of this handle from a PINNED host tensor of the same shape and dtype, moving only

@@ -25,7 +25,7 @@ def _declared_functions():
         text = open(os.path.join(ROOT, "include", header)).read()
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
         text = re.sub(r"//[^\n]*", "", text)
-        names |= set(re.findall(r"\b(mrnnt_\w+|rnnt_loss_grad_gpu|compute_rnnt_loss)\s*\(", text))
+        names |= set(re.findall(r"\b(mrnnt_\w+|rnnt_loss_grad_gpu|compute_rnnt_loss|get_workspace_size)\s*\(", text))
     return names
 
 
