@@ -6,25 +6,37 @@
 
 One "step" = one pass of the hot path over one batch of synthetic input: the configuration BASELINE.json
 quotes the metric on (configs[1]: B=32 T=150 S=40 V=1000 fp32 logits, fixed lengths) per GPU.  Weak
-scaling: every rank runs that batch on its own logits; the only collective is one all-reduce of the summed
-cost per step.  Rank 0 prints ONE JSON line.
+scaling (default): every rank runs that batch on its own logits.  --scaling strong (BASELINE.json configs[2]: "batch-
+sharded at 1/2/4/8 B200"): ONE batch is cut over the ranks by utterance (monotonic_rnnt_b200/shard.py: LPT assignment,
+or --partition contiguous), every rank regenerates its utterances' logits from the global element index, runs the same
+call on its shard, and value = the batch's utterances / the slowest rank's step time; rank 0 then also runs the whole
+batch alone and asserts the gathered per-utterance costs equal it bit for bit.  Either way the only collective is the
+sum of the costs (inside the gradient kernel, over peer memory).  Rank 0 prints ONE JSON line.
 
   value     whole-job utterances/s with inputs resident in HBM; the timed region is K calls of the C-ABI
-            entry (mrnnt_cost_and_grad: K1 -> K2 -> K3, async D2H of the B costs, one stream sync)
-            bracketed by barrier + synchronize, CUDA events on the launch stream, max over ranks.
+            entry (mrnnt_cost_and_grad: K1 -> K2 -> K3, costs on the host on return, one stream sync)
+            bracketed by barrier + synchronize, CUDA events on the launch stream, max over ranks.  The K-step
+            region is run --blocks times (default 5); ms_per_step is the MEDIAN block (all blocks and the per-rank
+            times are in the line), so that one host hiccup in a 7 ms region cannot move the number.
   e2e       same metric through the public host API with HOST buffers: every step brings the step's
             logits/labels/lengths from pinned host memory to the device, builds the handle, runs, reads costs
-            back.  Measured two ways (e2e_paths): the whole tensor through the copy engine, and the rows the
-            lattice reads only (mrnnt_upload_acts: a kernel pulls them from host memory); e2e is the faster.
-  roofline  dominant kernel (K3, gradient: reads the live logits, writes every gradient) timed per launch
-            with CUDA events recorded around it on the same stream in a second, instrumented pass of K steps.
+            back.  Gradients stay on the device, as in the reference's contract (its GPU path leaves them there,
+            gpu_rnnt.h:229): the leg measures the upload + call.  Two ways (e2e_paths): the whole tensor through the
+            copy engine, and the rows the lattice reads only (mrnnt_upload_acts); e2e is the faster.
+  roofline  dominant kernel (K3, gradient) timed per launch with CUDA events recorded around it on the same stream
+            in a second, instrumented pass of K steps.  achieved = the bytes the kernel's job requires (read the logits
+            of live rows once + write the gradient rows it owns once) / duration; traffic = DRAM bytes per launch from
+            the committed ncu capture of this workload (profiles/traffic.json); dram_frac = traffic / duration / peak.
+            (The 12-bytes-per-logit convention of SURVEY 8d, which charges dead rows as read, is under call_roofline.)
   cpu_baseline  the reference's own CPU implementation (oracle/_ref, compiled from the unmodified
             reference sources) on the box's host cores, same inputs, bounded sample; also used here as the
-            checker of the GPU result (costs / gradients), which is the only reason bench.py touches oracle/.
+            checker of the GPU result (costs vs it, gradients vs the double-precision oracle: asserted), which is
+            the only reason bench.py touches oracle/.
 Inputs (0.79 GB logits + 0.79 GB gradients per step) exceed the 126 MB L2, so no L2 flush is needed
 between iterations (config.l2: "inputs>L2").
 --workload c3|c4|c5 puts the other shapes BASELINE.json names through the same contract (the driver's line is c2,
-the default); their host legs run on a prefix of the batch of at most 4 GiB of logits.
+the default); their host legs run on a prefix of the batch of at most 4 GiB of logits.  --workload c2v1025 / c4v5001:
+the same shapes with a vocabulary that is not a multiple of 4 (unaligned rows).
 """
 from __future__ import annotations
 
@@ -44,7 +56,10 @@ import numpy as np  # noqa: E402
 METRIC = "loss_grad_utterances_per_sec"
 UNIT = "utt/s"
 WORKLOAD = "c2"  # BASELINE.json configs[1]; --workload c3 / c4 / c5 reports the other named shapes the same way
+SCALING = "weak"
 WORKLOAD_NAMES = {
+    "c2v1025": "synthetic B={B} T={T} S={S} V={V} fp32 logits, fixed lengths: c2 with rows that are not whole 16-byte vectors, per GPU",
+    "c4v5001": "large-vocab B={B} T={T} S={S} V={V} fp32 logits: c4 with rows that are not whole 16-byte vectors, per GPU",
     "c2": "synthetic B={B} T={T} S={S} V={V} fp32 logits, fixed lengths (BASELINE.json configs[1]) per GPU",
     "c3": "synthetic B={B} T<={T} S<={S} V={V} fp32 logits, random per-utterance T_b/S_b, packed "
           "(BASELINE.json configs[2]) per GPU",
@@ -63,11 +78,11 @@ def _peaks():
 
 
 def _traffic(kernel: str):
-    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture, if any."""
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture of this workload, if any."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(path):
         with open(path) as f:
-            return json.load(f).get(WORKLOAD, {}).get(kernel)  # (captures exist for c2 only: null elsewhere)
+            return json.load(f).get(WORKLOAD, {}).get(kernel)
     return None
 
 
@@ -75,7 +90,7 @@ def _config(wl, extra=None):
     cfg = {"workload": f"{wl.name}: " + WORKLOAD_NAMES[wl.name].format(B=wl.B, T=int(wl.T.max()), S=int(wl.S.max()), V=wl.V),
            "batch_per_gpu": wl.B, "rows_per_gpu": wl.rows, "logit_bytes_per_gpu": wl.elements * 4,
            "algorithmic_bytes_per_step_per_gpu": wl.algorithmic_bytes, "l2": "inputs>L2 (no flush needed)",
-           "parallelism": "utterance-sharded, one all-reduce of the summed cost"}
+           "parallelism": "utterance-sharded, one sum of the costs over all GPUs"}
     if extra:
         cfg.update(extra)
     return cfg
@@ -151,14 +166,14 @@ def _host_threads() -> int:
         return max(1, os.cpu_count() or 1)
 
 
-def _cpu_sample(wl, max_utts=None):
+def _cpu_sample(wl, max_utts=None, max_bytes=None):
     """A prefix of the batch for the host legs: (k, rows_k, labels, alignment) with the labels / the alignment re-strided
     to the prefix's own maxima (the reference derives both strides from the lengths it is given,
     cpu_workspace_manager.h:44,122) and at most CPU_SAMPLE_BYTES of logits -- which also keeps the reference's int
     indexing below 2^31 elements (c4 as a whole overflows it)."""
     rows_b = wl.T.astype(np.int64) * (wl.S.astype(np.int64) + 1)
     cum = np.cumsum(rows_b) * wl.V * 4
-    k = int(np.searchsorted(cum, CPU_SAMPLE_BYTES, side="right"))
+    k = int(np.searchsorted(cum, max_bytes or CPU_SAMPLE_BYTES, side="right"))
     k = max(1, min(wl.B, k, max_utts or wl.B))
     s_max = max(1, int(wl.S[:k].max()))
     labels = np.ascontiguousarray(wl.labels[:k, :s_max])
@@ -236,7 +251,25 @@ def _bind_to_gpu_numa_node(index: int) -> None:
         pass  # no NVML / no permission: run unbound
 
 
+def _local_workload(mr, wl, args, rank, world):
+    """Weak scaling: the named batch on every rank.  Strong scaling: this rank's utterances of the ONE batch."""
+    import dataclasses
+    if SCALING != "strong" or world == 1:
+        return wl, None, None
+    if args.partition == "contiguous":
+        parts = [np.arange(a, b) for a, b in mr.shard.partition_contiguous(wl.T, wl.S, world)]
+    else:
+        parts = mr.shard.partition_lpt(wl.T, wl.S, world)
+    if min(len(p) for p in parts) == 0:
+        raise SystemExit(f"--scaling strong: {wl.B} utterances cannot feed {world} ranks")
+    sh = mr.shard.make_shard_indexed(wl.T, wl.S, wl.labels, parts[rank], alignment=wl.alignment)
+    local = dataclasses.replace(wl, B=len(parts[rank]), T=sh.T, S=sh.S, labels=sh.labels, alignment=sh.alignment)
+    return local, sh, parts
+
+
 def run_b200(args) -> None:
+    import ctypes
+
     import torch
     import torch.distributed as dist
 
@@ -263,14 +296,34 @@ def run_b200(args) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def gather_floats(x):
+        """One float per rank -> the list of all ranks' values (on every rank)."""
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        if world == 1:
+            return [float(x)]
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
+
     lib = _lib.load()
-    wl = mr.synth.workload(WORKLOAD)
+    wl_global = mr.synth.workload(WORKLOAD)
+    wl, shard, parts = _local_workload(mr, wl_global, args, rank, world)
+    strong = shard is not None
     n = wl.elements
     stream = torch.cuda.current_stream()
 
     # ---- inputs resident in HBM ------------------------------------------------------------------
     acts = torch.empty((wl.rows, wl.V), dtype=torch.float32, device=dev)
-    _lib.check(lib.mrnnt_synth_uniform(acts.data_ptr(), n, wl.logits_seed, rank * n, stream.cuda_stream), "synth")
+    if strong:
+        # every utterance's logits from its GLOBAL element index: the same bits as in the one-GPU run of the whole batch
+        off = 0
+        for r0, r1 in shard.row_ranges:
+            ne = (r1 - r0) * wl.V
+            _lib.check(lib.mrnnt_synth_uniform(acts.data_ptr() + 4 * off, ne, wl.logits_seed, r0 * wl.V,
+                                               stream.cuda_stream), "synth")
+            off += ne
+    else:
+        _lib.check(lib.mrnnt_synth_uniform(acts.data_ptr(), n, wl.logits_seed, rank * n, stream.cuda_stream), "synth")
     labels = torch.from_numpy(wl.labels).to(dev)
     T = torch.from_numpy(wl.T).to(dev)
     S = torch.from_numpy(wl.S).to(dev)
@@ -284,7 +337,6 @@ def run_b200(args) -> None:
 
     # the C-ABI entry itself, bound once (handle, blank, stream, costs on the host, gradients on the device): the
     # Python mirror adds argument checks and attribute look-ups that are not part of the path being measured
-    import ctypes
     abi_call = lib.mrnnt_cost_and_grad
     abi_args = (handle._h, ctypes.c_int(wl.blank), ctypes.c_void_p(stream.cuda_stream),
                 ctypes.c_void_p(costs_host.data_ptr()), ctypes.c_void_p(grads.data_ptr()))
@@ -351,7 +403,7 @@ def run_b200(args) -> None:
         one_step()
     if boards is not None:
         # the exchange must have worked on EVERY rank before anything is timed through it (a peer whose stores do not
-        # arrive leaves NaN after the kernel's 2 s time-out): otherwise all ranks switch to the NCCL step, and say so
+        # arrive leaves NaN after the kernel's time-out): otherwise all ranks switch to the NCCL step, and say so
         want = torch.tensor([float(costs_host.double().sum())], dtype=torch.float64, device=dev)
         dist.all_reduce(want)
         got = float(cost_sum_host.item())
@@ -365,25 +417,33 @@ def run_b200(args) -> None:
             for _ in range(3):
                 one_step()
 
-    # ---- timed region: value ---------------------------------------------------------------------
+    # ---- timed region: value.  `blocks` times EXACTLY K steps, each block bracketed by barrier + synchronize; a block's
+    #      time is the max over ranks of the CUDA-event time on the launch stream; the MEDIAN block is reported --------
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    if clocks:
-        clocks.start()
-    t0 = time.perf_counter()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        one_step()
-    ev1.record(stream)
-    barrier()
-    wall_ms = 1000.0 * (time.perf_counter() - t0)
-    if clocks:
-        clocks.pause()
-    ms_total = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
-    ms_per_step = float(ms_total.item()) / args.steps
-    value = world * wl.B / (ms_per_step / 1000.0)
+    block_rank_ms, block_launches, wall_ms = [], [], []
+    for _ in range(max(1, args.blocks)):
+        barrier()
+        if clocks:
+            clocks.start()
+        launches0 = handle.get_option(_lib.OPT_LAUNCH_COUNT)
+        t0 = time.perf_counter()
+        ev0.record(stream)
+        for _ in range(args.steps):
+            one_step()
+        ev1.record(stream)
+        barrier()
+        wall_ms.append(1000.0 * (time.perf_counter() - t0))
+        if clocks:
+            clocks.pause()
+        block_launches.append(handle.get_option(_lib.OPT_LAUNCH_COUNT) - launches0)
+        block_rank_ms.append(gather_floats(ev0.elapsed_time(ev1)))
+    block_ms = [max(b) for b in block_rank_ms]                       # max over ranks, per block
+    order = sorted(range(len(block_ms)), key=lambda i: block_ms[i])
+    mid = order[(len(order) - 1) // 2]                               # the median block (lower median: a block that ran)
+    ms_per_step = block_ms[mid] / args.steps
+    B_job = wl_global.B if strong else world * wl.B
+    value = B_job / (ms_per_step / 1000.0)
+    gpu_launches = int(block_launches[mid])
     # the world's sum as the kernels exchanged it, against a library all-reduce of the same costs (outside the timing)
     collective_check = None
     if world > 1:
@@ -393,6 +453,36 @@ def run_b200(args) -> None:
         collective_check = {"world_sum": fused_total, "nccl_f64_sum_of_the_same_costs": float(want.item()),
                             "rel_diff": abs(fused_total - float(want.item())) / abs(float(want.item()))}
         assert collective_check["rel_diff"] < 1e-5, collective_check
+
+    # ---- strong scaling: the sharded result IS the whole batch's (outside the timing) ------------------------------
+    shard_info = None
+    if strong:
+        rows_per_rank = [int(sum((wl_global.T[p].astype(np.int64) * (wl_global.S[p] + 1)))) for p in parts]
+        all_costs = torch.full((wl_global.B,), float("nan"), dtype=torch.float32, device=dev)
+        all_costs[torch.from_numpy(np.asarray(parts[rank])).to(dev)] = costs_host.to(dev)
+        gathered = [torch.empty_like(all_costs) for _ in range(world)]
+        dist.all_gather(gathered, all_costs)
+        merged = torch.stack(gathered).nan_to_num(nan=0.0).sum(dim=0).cpu()    # (every utterance is owned by one rank)
+        whole_equal = None
+        if rank == 0:
+            g = wl_global
+            acts_w = torch.empty((g.rows, g.V), dtype=torch.float32, device=dev)
+            _lib.check(lib.mrnnt_synth_uniform(acts_w.data_ptr(), g.elements, g.logits_seed, 0, stream.cuda_stream), "synth")
+            hw = mr.LossHandle(acts_w, torch.from_numpy(g.labels).to(dev), torch.from_numpy(g.T).to(dev),
+                               torch.from_numpy(g.S).to(dev), lengths_host=(g.T, g.S))
+            if g.alignment is not None:
+                hw.restrict_to_alignment(torch.from_numpy(g.alignment).to(dev), g.max_shift, g.blank)
+            whole = hw.cost_and_grad(g.blank, torch.empty_like(acts_w)).clone()
+            hw.close()
+            del acts_w
+            torch.cuda.empty_cache()
+            whole_equal = bool(torch.equal(whole, merged))
+            assert whole_equal, "sharded per-utterance costs differ from the whole batch on one GPU"
+        shard_info = {"partition": args.partition, "utterances_per_rank": [int(len(p)) for p in parts],
+                      "rows_per_rank": rows_per_rank,
+                      "imbalance_max_over_mean": max(rows_per_rank) / (sum(rows_per_rank) / world),
+                      "max_T_per_rank": [int(wl_global.T[p].max()) for p in parts],
+                      "costs_bit_identical_to_the_whole_batch_on_one_gpu": whole_equal}
 
     # ---- the same K steps through the asynchronous entry (mrnnt_enqueue: costs stay on the device, no host round trip
     #      per step, one synchronisation at the end): what a training loop that never looks at the costs sees ----
@@ -506,15 +596,19 @@ def run_b200(args) -> None:
         barrier()
         if clocks:
             clocks.pause()
-        e2e_ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-        ms = float(e2e_ms.item()) / e2e_steps
+        rank_ms = gather_floats(ev0.elapsed_time(ev1) / e2e_steps)
+        ms = max(rank_ms)
         assert np.allclose(costs_host.numpy(), costs_gpu, rtol=1e-6)
+        bytes_step = (h2d - acts_h.numel() * 4 + live_bytes) if live_rows_only else h2d
+        host_read = gather_floats(bytes_step)
         e2e_paths["live_rows" if live_rows_only else "whole_tensor"] = {
-            "value": world * wl.B / (ms / 1000.0), "unit": UNIT, "ms_per_step": ms, "steps": e2e_steps,
-            "h2d_bytes_per_step": (h2d - acts_h.numel() * 4 + live_bytes) if live_rows_only else h2d,
+            "value": B_job / (ms / 1000.0), "unit": UNIT, "ms_per_step": ms, "steps": e2e_steps,
+            "h2d_bytes_per_step": bytes_step,
             "d2h_bytes_per_step": d2h,
+            "ms_per_step_per_rank": rank_ms,
+            "host_read_GBps_all_ranks": sum(host_read) / (ms * 1e-3) / 1e9,
+            "gradients": "stay on the device (the reference's GPU contract, gpu_rnnt.h:229: costs to the host, gradients "
+                         "to the caller's device buffer): this leg is the upload of the logits plus the call",
             "path": ("pinned host -> LossHandle(...) -> mrnnt_upload_acts (a kernel reads the live rows from host memory "
                      "over PCIe) -> mrnnt_cost_and_grad -> costs on host") if live_rows_only else
                     "pinned host -> H2D copy of the whole tensor -> LossHandle(...) -> mrnnt_cost_and_grad -> costs on host"}
@@ -549,11 +643,23 @@ def run_b200(args) -> None:
                         "sample": f"{which}, best of {len(times)} runs of "
                                   f"CpuRNNTComputer<float>::cost_and_grad (-O2 -fopenmp), {best * 1000:.0f} ms"}
         g = grads[:rows_k].cpu().numpy()
-        parity = {"checker": f"oracle/{'_ref' if kind == 'reference' else 'liboracle'} f32 on the same inputs ({which})",
-                  "cost_max_rel": float(np.max(np.abs(costs_gpu[:k] - res.costs) / np.abs(res.costs))),
-                  "grad_max_abs_vs_f32_cpu": float(np.abs(g - res.grads).max()),
-                  "note": "the float CPU reference itself is only ~4e-4 from exact arithmetic on c2 "
-                          "(SURVEY D6); tests/test_gpu_fullsize.py checks against the double-precision oracle"}
+        # gradients: against the double-precision oracle (the float reference is its own rounding noise away from exact
+        # arithmetic, 3e-4 .. 3e-3 on these shapes) on a prefix of at most 1 GiB of logits (>= 1 utterance)
+        k64, rows64, labels64, align64 = _cpu_sample(wl, max_bytes=1 << 30)
+        o64 = oracle.run(acts_h.numpy().reshape(-1)[: rows64 * wl.V], labels64, wl.T[:k64], wl.S[:k64], wl.V, blank=wl.blank,
+                         alignment=align64, max_shift=wl.max_shift, precision="f64_from_f32", want_grads=True,
+                         num_threads=cores)
+        parity = {"checker": f"oracle/{'_ref' if kind == 'reference' else 'liboracle'} f32 on the same inputs ({which}) for the "
+                             f"costs; the double-precision oracle on the first {k64} utterances for the gradients",
+                  "cost_max_rel_vs_f32_reference": float(np.max(np.abs(costs_gpu[:k] - res.costs) / np.abs(res.costs))),
+                  "cost_max_rel_vs_f64_oracle": float(np.max(np.abs(costs_gpu[:k64] - o64.costs) / np.abs(o64.costs))),
+                  "grad_max_abs_vs_f64_oracle": float(np.abs(g[:rows64] - o64.grads).max()),
+                  "grad_max_abs_vs_f32_reference": float(np.abs(g - res.grads).max()),
+                  "f32_reference_vs_f64_oracle": float(np.abs(res.grads[:rows64] - o64.grads).max()),
+                  "tolerance": "costs 1e-5 relative, gradients 1e-5 absolute (north_star), asserted"}
+        assert parity["cost_max_rel_vs_f32_reference"] <= 1e-5, parity
+        assert parity["cost_max_rel_vs_f64_oracle"] <= 1e-5, parity
+        assert parity["grad_max_abs_vs_f64_oracle"] <= 1e-5, parity
 
     # ---- secondary: the reference's own CUDA path (unmodified tests/test_time.cu for sm_100a) on this GPU -----
     ref_cuda = None
@@ -578,39 +684,66 @@ def run_b200(args) -> None:
         return
 
     peak, peak_src = _peaks()
-    # K3 algorithmic bytes per launch: read the logits once + write the gradients once, less the zero rows the
-    # lattice kernel has already written when its zero fill is on (those are charged to K2 below)
-    zero_bytes_in_k2 = 4 * dead_rows * wl.V if zero_fill_warps > 0 else 0
-    k3_bytes = 2 * 4 * n - zero_bytes_in_k2
+    # K3's job, in bytes per launch: read the logits of the live rows once, write the gradient rows it owns once (all
+    # of them, less the zero rows the lattice kernel's fill has already written -- those are that kernel's)
+    live_rows = wl.rows - dead_rows
     zero_note = None
-    if wl.alignment is not None and zero_fill_warps == 0:
+    if zero_fill_warps > 0 and zero_fill_warps < 32:
+        k3_written = live_rows
+        zero_note = "the dead rows' zeros are written by the lattice kernel's fill warps while its recursions run"
+    elif zero_fill_warps >= 32 or (wl.alignment is not None and zero_fill_warps == 0):
         # tight alignment band: the zero rows are written by one extra warp in K1 and one in K3 out of ONE counter
-        # (DESIGN 3.2), the split is not known on the host: K3 is charged with none of them (a lower bound)
-        k3_bytes = 2 * 4 * n - 4 * dead_rows * wl.V
+        # (DESIGN 3.2); the split is not known on the host, K3 is charged with none of them (a lower bound)
+        k3_written = live_rows
         zero_note = "zero rows written by the fill warps of K1 and K3 from one counter; K3 charged with none of them"
+    else:
+        k3_written = wl.rows
+    k3_bytes = 4 * wl.V * (live_rows + k3_written)
     k3_gbs = k3_bytes / (k_ms[2] * 1e-3) / 1e9
-    k3_traffic = _traffic("k3_grad_tma_kernel")   # DRAM bytes per launch from the committed ncu capture (c2 only)
+    k3_traffic = _traffic("k3_grad_tma_kernel")   # DRAM bytes per launch from the committed ncu capture of this workload
     k3_dram_gbs = None if k3_traffic is None else k3_traffic / (k_ms[2] * 1e-3) / 1e9
     call_gbs = wl.algorithmic_bytes / (ms_per_step * 1e-3) / 1e9
+    call_traffic = None
+    tj = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tj):
+        with open(tj) as f:
+            e = json.load(f).get(WORKLOAD, {})
+        if all(kname in e for kname in ("k1_lse_tma_kernel", "k2_lattice_kernel", "k3_grad_tma_kernel")):
+            call_traffic = e["k1_lse_tma_kernel"] + e["k2_lattice_kernel"] + e["k3_grad_tma_kernel"]
+    # (the captures are of the whole named batch on one GPU: not comparable with a shard's step time)
+    call_dram_gbs = None if (call_traffic is None or strong) else call_traffic / (ms_per_step * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": _config(wl, {"collective": collective}),
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": SCALING,
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": _config(wl_global if strong else wl, {"collective": collective, "scaling": SCALING,
+                                                        "batch_total": B_job}),
+        "timing": {"blocks": len(block_ms), "steps_per_block": args.steps, "reported": "median block, max over ranks",
+                   "ms_per_step_blocks": [b / args.steps for b in block_ms],
+                   "ms_per_step_min_block": min(block_ms) / args.steps, "ms_per_step_max_block": max(block_ms) / args.steps,
+                   "ms_per_step_per_rank_median_block": [x / args.steps for x in block_rank_ms[mid]],
+                   "wall_ms_blocks": wall_ms},
+        "shards": shard_info,
         "collective_check": collective_check,
         "roofline": {"kernel": "k3_grad_tma_kernel", "bound": "hbm", "achieved": k3_gbs, "peak": peak, "unit": "GB/s",
                      "frac": k3_gbs / peak, "traffic": k3_traffic, "peak_source": peak_src,
                      "dram_achieved": k3_dram_gbs, "dram_frac": None if k3_dram_gbs is None else k3_dram_gbs / peak,
-                     "note": "achieved counts ALGORITHMIC bytes (SURVEY 8d: every logit read, every gradient written); the "
-                             "kernel never reads the logits of dead rows, so frac can exceed 1 -- dram_achieved = the "
-                             "DRAM bytes ncu counted per launch (traffic) / this run's launch duration is the "
-                             "kernel-quality figure",
+                     "note": "achieved = the bytes the kernel's job requires per launch (4 V (live rows read + gradient rows "
+                             "written by this kernel)) / this run's launch duration; traffic = DRAM bytes ncu counted per "
+                             "launch of this workload (profiles/traffic.json, isolated cold-cache run); dram_frac = traffic / "
+                             "this run's duration / peak.  Rank 0's shard under --scaling strong.",
                      "algorithmic_bytes_per_launch": k3_bytes, "ms_per_launch": float(k_ms[2]),
-                     "zero_rows_written_by_k2_bytes": zero_bytes_in_k2, "k2_zero_fill_warps": zero_fill_warps,
-                     "dead_rows": dead_rows, "zero_rows_note": zero_note},
+                     "live_rows": live_rows, "dead_rows": dead_rows, "gradient_rows_written_by_this_kernel": k3_written,
+                     "k2_zero_fill_warps": zero_fill_warps, "zero_rows_note": zero_note,
+                     "survey_8d_convention": {"bytes": 2 * 4 * n, "GBps": 2 * 4 * n / (k_ms[2] * 1e-3) / 1e9,
+                                              "note": "8 bytes per logit whether the row is ever read or not"}},
         "kernels_ms": {"k1_lse_gather": float(k_ms[0]), "k2_lattice": float(k_ms[1]), "k3_grad": float(k_ms[2]),
-                       "sum": float(k_ms.sum()), "k1_GBps_of_4N": 4 * n / (k_ms[0] * 1e-3) / 1e9},
-        "call_roofline": {"algorithmic_bytes": wl.algorithmic_bytes, "achieved_GBps": call_gbs,
-                          "frac_of_measured_peak": call_gbs / peak, "frac_of_8TBps_nominal": call_gbs / 8000.0,
+                       "sum": float(k_ms.sum()), "k1_GBps_of_live_logits": 4 * wl.V * live_rows / (k_ms[0] * 1e-3) / 1e9},
+        "call_roofline": {"algorithmic_bytes_survey_8d": wl.algorithmic_bytes, "achieved_GBps_survey_8d": call_gbs,
+                          "frac_of_measured_peak_survey_8d": call_gbs / peak, "frac_of_8TBps_nominal_survey_8d": call_gbs / 8000.0,
+                          "dram_traffic_bytes": call_traffic,
+                          "dram_GBps": call_dram_gbs,
+                          "dram_frac_of_measured_peak": None if call_dram_gbs is None else call_dram_gbs / peak,
                           "per_gpu": True},
         "e2e": e2e_best, "e2e_paths": e2e_paths,
         "async_enqueue": None if async_ms is None else {
@@ -620,8 +753,9 @@ def run_b200(args) -> None:
             "value": wl.B / (alloc_ms / 1000.0), "unit": UNIT, "ms_per_step": alloc_ms,
             "what": "new handle + cudaMalloc of the workspace + set-up kernels + cost_and_grad + cudaFree per call (host clock), "
                     "the way the reference's torch binding drives its manager"},
-        "gpu_launches": 3 * args.steps,
-        "clocks": clock_info, "wall_ms_timed_region": wall_ms,
+        "gpu_launches": gpu_launches,
+        "gpu_launches_note": "kernel launches counted by the engine (MRNNT_OPT_LAUNCH_COUNT) inside the reported block of K steps, rank 0",
+        "clocks": clock_info, "wall_ms_timed_region": wall_ms[mid],
         "cpu_baseline": cpu_baseline, "reference_cuda_same_gpu": ref_cuda, "parity": parity,
         "build": lib.mrnnt_build_info().decode(),
     }
@@ -655,7 +789,14 @@ def main() -> None:
                     help="N > 1: the sum of the costs over peer memory inside the gradient kernel, or NCCL on a side stream")
     ap.add_argument("--reserve-sms", type=int, default=0,
                     help="N > 1: SMs the gradient kernel leaves to the concurrent all-reduce")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
+                    help="weak: the named batch on every GPU; strong: ONE batch sharded over the GPUs by utterance")
+    ap.add_argument("--partition", choices=["lpt", "contiguous"], default="lpt",
+                    help="--scaling strong: longest-processing-time assignment of single utterances, or contiguous ranges")
+    ap.add_argument("--blocks", type=int, default=5, help="how often the K-step timed region is run (median reported)")
     args = ap.parse_args()
+    global SCALING
+    SCALING = args.scaling
     WORKLOAD = args.workload
     args.out_fd = _claim_stdout()
     if args.impl == "reference":

@@ -19,7 +19,12 @@
 namespace mrnnt {
 
 constexpr int kWarp = 32;
-constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLog2e = 1.4426950408889634f;  // float(log2 e): the constant of every x * log2(e) in the streaming kernels
+// log2 e = kLog2e + kLog2eLo to ~48 bits.  Only the lattice's transition weights use the full value for their own
+// logit; the per-row sums (K1) and the gradient (K3) use kLog2e alone, and the denominator carries the difference for
+// the row's maximum (lse_finish) -- see the note there.
+constexpr float kLog2eLo = 1.925963033500011e-8f;
+constexpr float kLog2eLoRel = 1.3349827e-8f;   // kLog2eLo / kLog2e
 constexpr double kLog2eD = 1.4426950408889634074;
 constexpr double kLn2D = 0.69314718055994530942;
 constexpr float kNegInfF = -__builtin_huge_valf();  // usable in host and device code alike
@@ -245,8 +250,8 @@ __device__ __forceinline__ void cell_renorm(float &m, int &e) {
 // polynomial (truncation 5e-9; the result carries about one float ulp of rounding).  `ok == false`, -inf, NaN
 // and anything below 2^-(2^22) give the zero weight.
 __device__ __forceinline__ void weight_from_logit(float x, float dh, float dl, bool ok, float &m, int &e) {
-    constexpr float kL1 = 1.44269502162933349609375f;  // float(log2 e)
-    constexpr float kL2 = 1.925963033500011e-8f;       // log2 e - kL1
+    constexpr float kL1 = kLog2e;    // float(log2 e)
+    constexpr float kL2 = kLog2eLo;  // log2 e - kL1
     constexpr float kMagic = 12582912.0f;              // 1.5 * 2^23: adding it rounds to the nearest integer
     const float ph = x * kL1;
     const float pl = fmaf(x, kL2, fmaf(x, kL1, -ph));
@@ -277,9 +282,13 @@ __device__ __forceinline__ void log2_parts(float v, int &ip, float &fp) {
     fp = log2f(f + f);
 }
 
-// From a row's max (times log2 e, rounded once and used for every term) and its sum of 2^(x log2e - ML): the
-// base-2 denominator -(ML + log2 sum) = -log2 sum_v exp(x[v]) as an unevaluated sum of two floats (error-free
-// additions; the only error is log2f's ~6e-8 on a value in [0,1)).
+// From a row's max (times kLog2e, rounded once and used for every term) and its sum of 2^(x kLog2e - ML): the base-2
+// denominator D = -log2 sum_v exp(x[v]) as an unevaluated sum of two floats (error-free additions; the only error is
+// log2f's ~6e-8 on a value in [0,1)), such that log2 p(v) = x[v] * (kLog2e + kLog2eLo) + D.
+// K1 forms its sum with kLog2e alone: sum_v 2^(x kLog2e - ML) = 2^-ML sum_v e^x 2^(-x kLog2eLo), and the last factor
+// is 2^(-max kLog2eLo) for every term that matters (|x - max| kLog2eLo < 1e-6 for the terms within e^-50 of the
+// largest).  Hence D = -(ML + log2 sum) - max * kLog2eLo; without the last term log2 p is off by max * 1.9e-8 per row,
+// which does not cancel between rows of different maxima (logits of magnitude 100: 2e-6 per row, T = 800 rows per path).
 struct Denominator {
     float hi, lo;
 };
@@ -291,7 +300,7 @@ __device__ __forceinline__ Denominator lse_finish(float ML, float sum) {
     two_sum(h, fp, h2, l2);
     Denominator d;
     d.hi = -h2;
-    d.lo = -(l1 + l2);
+    d.lo = -fmaf(ML, kLog2eLoRel, l1 + l2);  // (max * kLog2eLo = ML * kLog2eLo / kLog2e)
     return d;
 }
 

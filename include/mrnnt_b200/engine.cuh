@@ -806,7 +806,7 @@ class Engine {
     RNNTStatus launch_k2(int blank, cudaStream_t stream, const DeviceInfo &dev, bool need_beta) {
         K2Args a;
         a.T = T_dev_; a.S = S_dev_; a.labels = labels_; a.row_start = ws_.row_start; a.band = ws_.band;
-        a.lp = ws_.lp; a.wts = ws_.wts; a.alpha = ws_.alpha; a.beta = ws_.beta; a.coef = ws_.coef;
+        a.lp = ws_.lp; a.wts = ws_.wts; a.alpha = ws_.alpha; a.beta = ws_.beta; a.coef = ws_.coef; a.rowlab = ws_.rowlab;
         a.ll_fwd = ws_.ll_fwd; a.ll_bwd = ws_.ll_bwd; a.costs = ws_.costs;
         a.costs_mapped = need_beta ? nullptr : costs_mapped_;  // (with gradients: K3 mirrors the costs, see cost_mirror)
         a.T_max = shape_.T_max; a.S_max = shape_.S_max; a.V = V_; a.blank = blank;
@@ -939,7 +939,7 @@ class Engine {
         // (a dependent launch only right behind the lattice kernel: a backward pass called on its own has no such
         // predecessor to wait for, and an ordinary launch orders it behind whatever precedes it in the stream)
         if (launch_kernel(kern, grid, (NW + (zero_warp ? 2 : 1)) * kWarp, smem, stream, pdl_ && k3_follows_k2_,
-                          static_cast<const E *>(acts_), ws_.coef, static_cast<E *>(grads), shape_.rows, V_, blank, tl.G,
+                          static_cast<const E *>(acts_), ws_.coef, ws_.rowlab, static_cast<E *>(grads), shape_.rows, V_, blank, tl.G,
                           tl.stages, ws_.rowutt, scale, cost_mirror(), flags, zero, tl.smem_bytes,
                           ws_.k2_flags + stream_ctr_word(B_), peer_args(peer_in_k3_)) != cudaSuccess)
             return RNNT_STATUS_EXECUTION_FAILED;
@@ -949,7 +949,7 @@ class Engine {
     template <typename E>
     RNNTStatus launch_k3_typed(int blank, cudaStream_t stream, const DeviceInfo &dev, void *grads, const float *scale) {
         StreamTiling tl;
-        if (can_stream(acts_, grads, sizeof(float4), k3_warps_, kK3TileTarget, true, dev, &tl)) {
+        if (can_stream(acts_, grads, sizeof(float4) + sizeof(int), k3_warps_, kK3TileTarget, true, dev, &tl)) {
             if (scale != nullptr)
                 return tl.warps == 8    ? launch_k3_tma<E, 8, true>(blank, stream, dev, tl, grads, scale)
                        : tl.warps == 16 ? launch_k3_tma<E, 16, true>(blank, stream, dev, tl, grads, scale)
@@ -959,7 +959,7 @@ class Engine {
                                     : launch_k3_tma<E, 24, false>(blank, stream, dev, tl, grads, scale);
         }
         k3_grad_generic_kernel<E><<<generic_grid(dev), kGenericWarps * kWarp, 0, stream>>>(
-            static_cast<const E *>(acts_), ws_.coef, static_cast<E *>(grads), shape_.rows, V_, blank, ws_.rowutt, scale,
+            static_cast<const E *>(acts_), ws_.coef, ws_.rowlab, static_cast<E *>(grads), shape_.rows, V_, blank, ws_.rowutt, scale,
             cost_mirror(), peer_args(peer_in_k3_));
         return launched();
     }

@@ -33,11 +33,14 @@
 //       chain warps therefore contain no band arithmetic at all.
 //    B. part 0 runs the two systolic rows; the weights of a whole CHUNK of frames arrive in shared memory by
 //       one bulk async copy (TMA engine) per chunk, issued by an otherwise idle warp per direction.
-//    C. all parts fold alpha, beta, the likelihood and the denominators into three float coefficients per
-//       row, so that the gradient kernel is a pure stream:
-//         c0 = alpha(t-1,s) + beta(t,s)     - ll + denom      (x log2 e)
-//         cb = alpha(t-1,s) + beta(t+1,s)   - ll + denom
-//         cl = alpha(t-1,s) + beta(t+1,s+1) - ll + denom
+//    C. all parts fold alpha, beta, the likelihood and the denominators into one record per row, so that the
+//       gradient kernel is a pure stream: the high float dh of the row's denominator and, relative to it,
+//         r0 = log2( alpha(t-1,s) beta(t,s)     / Z ) + dl
+//         rb = log2( alpha(t-1,s) beta(t+1,s)   / Z ) + dl
+//         rl = log2( alpha(t-1,s) beta(t+1,s+1) / Z ) + dl
+//       so that g[v] = 2^((x[v] kLog2e + dh) + r0) - ...: the large part (dh ~ -max * log2 e, hundreds for logits of
+//       magnitude 100) meets the logit inside one fused multiply-add whose RESULT is small, and the r's are small
+//       numbers too -- a single float coefficient c = r + dh would carry half an ulp of |dh| into every gradient.
 #pragma once
 
 #include "common.cuh"
@@ -72,7 +75,9 @@ struct K2Args {
     Weight *wts;       // [rows] transition weights, written by phase A
     Cell *alpha;
     Cell *beta;
-    float4 *coef;
+    float4 *coef;      // [rows] (r0, rb, rl, dh) per row, see the head of this file; r0 == -inf: a zero gradient row
+    int *rowlab;       // [rows] the row's label for the gradient kernel: >= 0, -1 none (or blank: the blank branch wins),
+                       //        kRowDead: a row the plan calls dead (whoever zeroes those rows has done so or will)
     double *ll_fwd;
     double *ll_bwd;
     float *costs;
@@ -471,18 +476,17 @@ __device__ __forceinline__ void k2_chain_dispatch(const K2Args &a, int b, K2Dir 
 // Semantics of the lookups follow the reference accessors (gpu_rnnt_kernel.h:10-56): alpha(-1,0)=1,
 // alpha(-1,s>0)=0, beta(T,S)=1, beta(T,s<S)=0, beta(.,S+1)=0 (linear domain); everything else comes from
 // the stored grids, which hold zeros outside the lattice.
-//   log2( alpha * beta / Z * 2^D ) = (e_a + e_b - e_Z) + log2( m_a * m_b / m_Z ) + dh + dl
-// summed in float with one error-free addition for the two large parts (no double-precision instructions).
-__device__ __forceinline__ float k2_coef(const Cell &x, float ratio, int base_e, float dh, float dl) {
+//   log2( alpha * beta / Z ) = (e_a + e_b - e_Z) + log2( m_a * m_b / m_Z )
+// `lo`: what is added to it -- the low float of the row's denominator (see k2_coef_rows).
+__device__ __forceinline__ float k2_coef(const Cell &x, float ratio, int base_e, float lo) {
     if (x.m == 0.0f) return kNegInfF;
     // log2 of the mantissa product: exponent bits exactly, mantissa in [1,2) through MUFU.LG2 (absolute error
     // 2^-22.6 on a value in [0,1): 1e-7 relative on the gradient)
     const int bits = __float_as_int(ratio * x.m);
     const int ip = (bits >> 23) - 127;
-    float fp, s, err;
+    float fp;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(fp) : "f"(__int_as_float((bits & 0x007fffff) | 0x3f800000)));
-    two_sum(static_cast<float>(base_e + x.e + ip), dh, s, err);
-    return s + ((err + dl) + fp);
+    return static_cast<float>(base_e + x.e + ip) + (fp + lo);
 }
 
 __device__ __forceinline__ void k2_coef_rows(const K2Args &a, int b, int part, int parts, int tid = threadIdx.x,
@@ -495,6 +499,7 @@ __device__ __forceinline__ void k2_coef_rows(const K2Args &a, int b, int part, i
     const RawRow *lp = a.lp + R;
     const int *labels = a.labels + static_cast<size_t>(b) * a.label_stride;
     float4 *coef = a.coef + R;
+    int *rowlab = a.rowlab + R;
     const int *rowmeta = a.rowmeta + R;
     // every row of the utterance's block gets a coefficient record (K3 takes row liveness from it); in a padded
     // tensor that includes the rows behind T_b and the states behind S_b, which are dead
@@ -549,8 +554,8 @@ __device__ __forceinline__ void k2_coef_rows(const K2Args &a, int b, int part, i
             // zero fill of this kernel or the gradient kernel -- a row whose coefficient merely came out as zero
             // (logits of -inf) is the gradient kernel's to write.
             if (lb != kRowDead && (s >= Sb || lb == a.blank || lb < 0 || lb >= a.V)) lb = -1;  // blank branch wins (cpu_rnnt.h:224-232)
-            float4 c;
-            c.w = __int_as_float(lb);
+            float4 c;  // (r0, rb, rl, dh)
+            c.w = 0.0f;
             if (!inside || (feasible && av.m == 0.0f)) {
                 c.x = c.y = c.z = kNegInfF;
             } else if (!feasible) {
@@ -560,11 +565,18 @@ __device__ __forceinline__ void k2_coef_rows(const K2Args &a, int b, int part, i
             } else {
                 const float ratio = av.m * inv_mz;
                 const int base_e = av.e - Z.e;
-                c.x = k2_coef(b0[u], ratio, base_e, dn[u].x, dn[u].y);
-                c.y = k2_coef(v1, ratio, base_e, dn[u].x, dn[u].y);
-                c.z = k2_coef(v2, ratio, base_e, dn[u].x, dn[u].y);
+                // The gradient kernel multiplies the logit by kLog2e alone; the denominator's -max * kLog2eLo
+                // (lse_finish) stands for the missing x * kLog2eLo of the elements near the row's maximum -- the only
+                // ones whose gradient is not negligible -- so it is taken out again here (max * kLog2e ~ -dh: off by
+                // log2 sum <= 20, i.e. by < 3e-7 in the exponent).
+                const float lo = fmaf(dn[u].x, -kLog2eLoRel, dn[u].y);  // dl + max * kLog2eLo
+                c.x = k2_coef(b0[u], ratio, base_e, lo);
+                c.y = k2_coef(v1, ratio, base_e, lo);
+                c.z = k2_coef(v2, ratio, base_e, lo);
+                c.w = dn[u].x;
             }
             coef[i] = c;
+            rowlab[i] = lb;
         }
     }
 }
@@ -670,9 +682,11 @@ static __global__ void __launch_bounds__(kK2Threads) k2_lattice_kernel(K2Args a)
     const int nphase = kK2Threads - zw * kWarp;
     const int nblk = 2 * parts;  // blocks per phase: two per launched CTA
     MRNNT_K2_STAMP(0);
-    // the first request for a block of phase A needs nothing of K1's: its round trip overlaps the wait for K1
-    unsigned held = (parts > 1 && tid == 0) ? atomicAdd(a_next, 1u) : kK2NoTicket;
     pdl_wait();  // K1's records
+    // (Not before the wait: under programmatic dependent launch this CTA can be running while the PREVIOUS lattice
+    // launch has not yet cleared this set of hand-over words -- e.g. forward halves back to back with small kernels
+    // that all fit on the device together.  Behind the wait the predecessor chain has completed.)
+    const unsigned held = kK2NoTicket;
     if (blockIdx.x == 0) {
         if (tid == 0 && a.zero_clear != nullptr) *a.zero_clear = 0u;
         // the other set of hand-over words, for the next launch (its last user, the previous launch, is long gone)

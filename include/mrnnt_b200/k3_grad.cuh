@@ -5,10 +5,12 @@
 // global memory per element, up to two exp per element, int32 element index).  CPU twin:
 // cpu_rnnt.h:216-236.
 //
-//   g[row, v] = exp(x + c0)  - [v == blank] exp(x + cb)  - [v == label_s] exp(x + cl)
-// with the three per-row coefficients (already multiplied by log2 e) and the row's label prepared by
-// K2 (k2_lattice.cuh).  Rows whose c0 is -inf (alpha(t-1,s) outside the lattice) are never read:
-// zeros are stored (reference: gpu_rnnt_kernel.h:266-271 does this for the geometric part only).
+//   g[row, v] = 2^(t + r0) - [v == blank] 2^(t + rb) - [v == label_s] 2^(t + rl),   t = x[v] * kLog2e + dh
+// with the per-row record (r0, rb, rl, dh) and the row's label prepared by K2 (k2_lattice.cuh): dh is the high float
+// of the row's base-2 log-softmax denominator, so t = log2 p(v) is formed by ONE fused multiply-add whose result is
+// small (whatever the magnitude of the logits), and the r's are the small lattice terms.  Rows whose r0 is -inf
+// (alpha(t-1,s) outside the lattice) are never read: zeros are stored (reference: gpu_rnnt_kernel.h:266-271 does
+// this for the geometric part only).
 // SCALED variants multiply utterance b's rows by scale[b] on the way out: the chain rule of the reference's
 // autograd glue (pytorch_binding/monotonic_rnnt_op.py:97-118, a separate read+write pass over the gradients
 // there) at no extra memory traffic.
@@ -26,7 +28,7 @@
 
 namespace mrnnt {
 
-__device__ __forceinline__ float grad_elem(float x, float c) { return ex2_approx(fmaf(x, kLog2e, c)); }
+__device__ __forceinline__ float grad_log2p(float x, float dh) { return fmaf(x, kLog2e, dh); }
 
 // Optional hand-over of the B costs to the host (a synchronous call's staging buffer in host-mapped pinned memory,
 // engine.cuh): done here, by the first CTA of the LAST kernel of the call, so that the PCIe write overlaps the whole
@@ -42,14 +44,14 @@ __device__ __forceinline__ void mirror_costs(const CostMirror &m, int nthreads) 
         for (int i = threadIdx.x; i < m.B; i += nthreads) m.mapped[i] = m.costs[i];
 }
 
-// subtract the blank / label term from component k of a vector of NE gradients (k is warp-divergent, so the
-// component is picked with selects instead of a dynamically indexed register array)
+// subtract the blank / label term from component k of a vector of NE gradients, t = the components' log2 p (k is
+// warp-divergent, so the component is picked with selects instead of a dynamically indexed register array)
 template <int NE>
-__device__ __forceinline__ void patch_component(float (&g)[NE], const float (&x)[NE], int k, float c) {
-    float xv = x[0];
+__device__ __forceinline__ void patch_component(float (&g)[NE], const float (&t)[NE], int k, float r) {
+    float tv = t[0];
 #pragma unroll
-    for (int i = 1; i < NE; ++i) xv = (k == i) ? x[i] : xv;
-    const float d = grad_elem(xv, c);
+    for (int i = 1; i < NE; ++i) tv = (k == i) ? t[i] : tv;
+    const float d = ex2_approx(tv + r);
 #pragma unroll
     for (int i = 0; i < NE; ++i) g[i] -= (k == i) ? d : 0.0f;
 }
@@ -59,9 +61,10 @@ __device__ __forceinline__ void patch_component(float (&g)[NE], const float (&x)
 // ---------------------------------------------------------------------------------------------
 template <typename E>
 static __global__ void __launch_bounds__(kGenericWarps * kWarp)
-    k3_grad_generic_kernel(const E *__restrict__ acts, const float4 *__restrict__ coef, E *__restrict__ grads,
-                           int64_t rows, int V, int blank, const int *__restrict__ rowutt,
-                           const float *__restrict__ scale, CostMirror mirror, PeerReduce peer) {
+    k3_grad_generic_kernel(const E *__restrict__ acts, const float4 *__restrict__ coef,
+                           const int *__restrict__ rowlab, E *__restrict__ grads, int64_t rows, int V, int blank,
+                           const int *__restrict__ rowutt, const float *__restrict__ scale, CostMirror mirror,
+                           PeerReduce peer) {
     mirror_costs(mirror, blockDim.x);
     const bool peer_warp = blockIdx.x == 0 && threadIdx.x < kWarp;  // (peer_reduce.cuh)
     if (peer_warp) peer_publish(peer);
@@ -76,13 +79,13 @@ static __global__ void __launch_bounds__(kGenericWarps * kWarp)
             continue;
         }
         const E *x = acts + row * V;
-        const int lab = __float_as_int(c.w);
+        const int lab = __ldg(rowlab + row);
         const float sc = scale != nullptr ? __ldg(scale + __ldg(rowutt + row)) : 1.0f;
         for (int v = lane; v < V; v += kWarp) {
-            const float xv = Elem<E>::to_float(x[v]);
-            float gv = grad_elem(xv, c.x);
-            if (v == blank) gv -= grad_elem(xv, c.y);
-            else if (v == lab) gv -= grad_elem(xv, c.z);
+            const float t = grad_log2p(Elem<E>::to_float(x[v]), c.w);
+            float gv = ex2_approx(t + c.x);
+            if (v == blank) gv -= ex2_approx(t + c.y);
+            else if (v == lab) gv -= ex2_approx(t + c.z);
             g[v] = Elem<E>::from_float(gv * sc);
         }
     }
@@ -92,7 +95,7 @@ static __global__ void __launch_bounds__(kGenericWarps * kWarp)
 // ---------------------------------------------------------------------------------------------
 // TMA-staged variant.  Requirements: rows are whole 16-byte vectors, acts and grads 16-byte aligned.
 // Shared memory: [stages][G*V] elements | full[stages] | empty[stages] | scale[stages][32] floats | coef[stages][32] float4
-// | tile[stages] ints
+// | label[stages][32] ints | tile[stages] ints
 // ---------------------------------------------------------------------------------------------
 // flags
 constexpr int kK3WriteDead = 1;  // write the zero rows (off: somebody else zeroes the rows the plan calls dead)
@@ -113,8 +116,9 @@ inline size_t k3_smem_bytes(size_t ring_bytes, bool zero_warp) {
 
 template <typename E, int NW, bool SCALED>
 static __global__ void __launch_bounds__((NW + 2) * kWarp, 1)
-    k3_grad_tma_kernel(const E *__restrict__ acts, const float4 *__restrict__ coef, E *__restrict__ grads,
-                       int64_t rows, int V, int blank, int G, int stages, const int *__restrict__ rowutt,
+    k3_grad_tma_kernel(const E *__restrict__ acts, const float4 *__restrict__ coef, const int *__restrict__ rowlab,
+                       E *__restrict__ grads, int64_t rows, int V, int blank, int G, int stages,
+                       const int *__restrict__ rowutt,
                        const float *__restrict__ scale, CostMirror mirror, int flags, ZeroFill zero, size_t ring_bytes,
                        unsigned *__restrict__ dyn, PeerReduce peer) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -126,7 +130,8 @@ static __global__ void __launch_bounds__((NW + 2) * kWarp, 1)
     float *scale_sh = reinterpret_cast<float *>(empty + stages);
     float4 *coef_sh = reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(empty + stages) +
                                                  static_cast<size_t>(stages) * 32 * sizeof(float));
-    int *tile_sh = reinterpret_cast<int *>(coef_sh + static_cast<size_t>(stages) * 32);  // [stages] tile held by the slot
+    int *lab_sh = reinterpret_cast<int *>(coef_sh + static_cast<size_t>(stages) * 32);
+    int *tile_sh = lab_sh + static_cast<size_t>(stages) * 32;  // [stages] tile held by the slot
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -165,10 +170,11 @@ static __global__ void __launch_bounds__((NW + 2) * kWarp, 1)
         const uint64_t policy = l2_policy_evict_first();
         int stage = 0;
         uint32_t phase = 0;
-        auto fill_slot = [&](int64_t k, const float4 &c, float sc, uint32_t mask) {
+        auto fill_slot = [&](int64_t k, const float4 &c, int lb, float sc, uint32_t mask) {
             const int64_t row0 = (dynamic ? k : blockIdx.x + k * gridDim.x) * G;  // (dynamic: k is the tile itself)
             mbar_wait(empty + stage, phase ^ 1u);
             coef_sh[stage * 32 + lane] = c;
+            lab_sh[stage * 32 + lane] = lb;
             if (SCALED) scale_sh[stage * 32 + lane] = sc;
             if (lane == 0) tile_sh[stage] = static_cast<int>(k);
             __syncwarp();
@@ -203,17 +209,23 @@ static __global__ void __launch_bounds__((NW + 2) * kWarp, 1)
                 const int64_t row = tile * G + lane;
                 return (SCALED && tile < ntiles && lane < G && row < rows) ? __ldg(scale + __ldg(rowutt + row)) : 1.0f;
             };
+            auto load_lab = [&](int64_t tile) {
+                const int64_t row = tile * G + lane;
+                return (tile < ntiles && lane < G && row < rows) ? __ldg(rowlab + row) : kRowDead;
+            };
             int64_t t0 = blockIdx.x, t1 = static_cast<int64_t>(blockIdx.x) + gridDim.x;
             float4 c0 = load_coef(t0), c1 = load_coef(t1);
             float s0 = load_scale(t0), s1 = load_scale(t1);
+            int l0 = load_lab(t0), l1 = load_lab(t1);
             while (t0 < ntiles) {
                 const int64_t t2 = next_tile();
                 const float4 c2 = load_coef(t2);
                 const float s2 = load_scale(t2);
+                const int l2 = load_lab(t2);
                 const uint32_t mask = __ballot_sync(0xffffffffu, !(c0.x == kNegInfF));
-                if (write_dead || mask != 0u) fill_slot(t0, c0, s0, mask);
-                t0 = t1; c0 = c1; s0 = s1;
-                t1 = t2; c1 = c2; s1 = s2;
+                if (write_dead || mask != 0u) fill_slot(t0, c0, l0, s0, mask);
+                t0 = t1; c0 = c1; s0 = s1; l0 = l1;
+                t1 = t2; c1 = c2; s1 = s2; l1 = l2;
             }
             for (int i = 0; i < stages; ++i) {  // one terminator per slot, as in the compact mode
                 mbar_wait(empty + stage, phase ^ 1u);
@@ -236,16 +248,24 @@ static __global__ void __launch_bounds__((NW + 2) * kWarp, 1)
                 const int64_t row = (blockIdx.x + k * gridDim.x) * G + lane;
                 return (SCALED && k < nloc && lane < G && row < rows) ? __ldg(scale + __ldg(rowutt + row)) : 1.0f;
             };
+            auto load_lab = [&](int64_t k) {
+                const int64_t row = (blockIdx.x + k * gridDim.x) * G + lane;
+                return (k < nloc && lane < G && row < rows) ? __ldg(rowlab + row) : kRowDead;
+            };
             float4 c_next = load_coef(0), c_next2 = load_coef(1);
             float s_next = load_scale(0), s_next2 = load_scale(1);
+            int l_next = load_lab(0), l_next2 = load_lab(1);
             for (int64_t k = 0; k < nloc; ++k) {
                 const float4 c = c_next;
                 const float sc = s_next;
+                const int lb = l_next;
                 c_next = c_next2;  // two tiles ahead: the latency hides behind two tiles' waits
                 s_next = s_next2;
+                l_next = l_next2;
                 c_next2 = load_coef(k + 2);
                 s_next2 = load_scale(k + 2);
-                fill_slot(k, c, sc, __ballot_sync(0xffffffffu, !(c.x == kNegInfF)));
+                l_next2 = load_lab(k + 2);
+                fill_slot(k, c, lb, sc, __ballot_sync(0xffffffffu, !(c.x == kNegInfF)));
             }
         } else {
             // coefficients for 32/G tiles per load (lane l: tile k0 + l/G, row l%G), two such batches ahead: with
@@ -265,15 +285,23 @@ static __global__ void __launch_bounds__((NW + 2) * kWarp, 1)
                 const int64_t row = batch_row(k0);
                 return (SCALED && row >= 0) ? __ldg(scale + __ldg(rowutt + row)) : 1.0f;
             };
+            auto load_lab = [&](int64_t k0) {
+                const int64_t row = batch_row(k0);
+                return row >= 0 ? __ldg(rowlab + row) : kRowDead;
+            };
             float4 cb0 = load_coef(0), cb1 = load_coef(TPB);
             float sb0 = load_scale(0), sb1 = load_scale(TPB);
+            int lb0 = load_lab(0), lb1 = load_lab(TPB);
             for (int64_t k0 = 0; k0 < nloc; k0 += TPB) {
                 const float4 cb = cb0;
                 const float sb = sb0;
+                const int lbb = lb0;
                 cb0 = cb1;
                 sb0 = sb1;
+                lb0 = lb1;
                 cb1 = load_coef(k0 + 2 * TPB);
                 sb1 = load_scale(k0 + 2 * TPB);
+                lb1 = load_lab(k0 + 2 * TPB);
                 const uint32_t ball = __ballot_sync(0xffffffffu, !(cb.x == kNegInfF));
                 for (int j = 0; j < TPB && k0 + j < nloc; ++j) {
                     const uint32_t mask = (ball >> (j * G)) & gmask;
@@ -285,8 +313,9 @@ static __global__ void __launch_bounds__((NW + 2) * kWarp, 1)
                     c.z = __shfl_sync(0xffffffffu, cb.z, src);
                     c.w = __shfl_sync(0xffffffffu, cb.w, src);
                     const float sc = SCALED ? __shfl_sync(0xffffffffu, sb, src) : 1.0f;
+                    const int lb = __shfl_sync(0xffffffffu, lbb, src);
                     if (lane >= G) c.x = kNegInfF;
-                    fill_slot(k0 + j, c, sc, mask);
+                    fill_slot(k0 + j, c, lb, sc, mask);
                 }
             }
             // one terminator per slot: every consumer warp meets one within its next `stages` slot uses
@@ -317,30 +346,38 @@ static __global__ void __launch_bounds__((NW + 2) * kWarp, 1)
             if (k < 0) break;
             const int64_t row = (dynamic ? k : blockIdx.x + k * gridDim.x) * G + r;
             if (row < rows) {
-                const float4 c = coef_sh[stage * 32 + r];
+                const float4 c = coef_sh[stage * 32 + r];  // (r0, rb, rl, dh)
+                const int lab = lab_sh[stage * 32 + r];    // -1 when the row has no (non-blank) label
                 uint4 *gv = reinterpret_cast<uint4 *>(grads + row * V);
                 if (c.x == kNegInfF) {
                     // a zero row; without write_dead somebody else zeroes the rows the plan calls dead (marked in the
                     // label slot; the lattice kernel's fill or a zero-fill warp, zero_fill.cuh), and only a row
                     // INSIDE the lattice that came out as zero (masked logits) is written here
                     const uint4 z = make_uint4(0u, 0u, 0u, 0u);  // +0.0 in either element type
-                    if (write_dead || __float_as_int(c.w) != kRowDead)
+                    if (write_dead || lab != kRowDead)
                         for (int j = lane; j < NV; j += kWarp) st_stream_u4(gv + j, z);
                 } else {
                     const uint4 *xv = reinterpret_cast<const uint4 *>(tiles + stage * tile_elems +
                                                                       static_cast<size_t>(r) * V);
-                    const int lab = __float_as_int(c.w);  // -1 when the row has no (non-blank) label
                     const int jb = blank / NE, kb = blank - jb * NE;
                     const int jl = lab >= 0 ? lab / NE : -1, kl = lab - jl * NE;
                     const float sc = SCALED ? scale_sh[stage * 32 + r] : 1.0f;
+                    const float2 l2 = make_float2(kLog2e, kLog2e), dh2 = make_float2(c.w, c.w), r2 = make_float2(c.x, c.x);
 #pragma unroll 2
                     for (int j = lane; j < NV; j += kWarp) {
-                        float x[NE], g[NE];
+                        float x[NE], t[NE], g[NE];
                         Elem<E>::unpack(xv[j], x);
 #pragma unroll
-                        for (int i = 0; i < NE; ++i) g[i] = grad_elem(x[i], c.x);
-                        if (j == jb) patch_component<NE>(g, x, kb, c.y);
-                        if (j == jl) patch_component<NE>(g, x, kl, c.z);
+                        for (int i = 0; i < NE; i += 2) {  // log2 p of two elements at a time (FFMA2 / FADD2)
+                            const float2 tt = __ffma2_rn(make_float2(x[i], x[i + 1]), l2, dh2);
+                            const float2 ee = __fadd2_rn(tt, r2);
+                            t[i] = tt.x;
+                            t[i + 1] = tt.y;
+                            g[i] = ex2_approx(ee.x);
+                            g[i + 1] = ex2_approx(ee.y);
+                        }
+                        if (j == jb) patch_component<NE>(g, t, kb, c.y);
+                        if (j == jl) patch_component<NE>(g, t, kl, c.z);
                         if (SCALED) {
 #pragma unroll
                             for (int i = 0; i < NE; ++i) g[i] *= sc;

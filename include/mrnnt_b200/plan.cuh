@@ -44,7 +44,8 @@ struct Workspace {
     Weight *wts = nullptr;         // [rows]  transition weights (m * 2^e pairs, band folded in), K2 phase A
     Cell *alpha = nullptr;         // [rows]  full T x (S+1) grid per utterance (m * 2^e), zero outside the band
     Cell *beta = nullptr;          // [rows]
-    float4 *coef = nullptr;        // [rows]  per-row gradient coefficients, see k2_lattice.cuh
+    float4 *coef = nullptr;        // [rows]  per-row gradient record (r0, rb, rl, dh), see k2_lattice.cuh
+    int *rowlab = nullptr;         // [rows]  the row's label as the gradient kernel needs it (-1 none, kRowDead dead)
     double *ll_fwd = nullptr;      // [B]     alpha(T-1, S)
     double *ll_bwd = nullptr;      // [B]     beta(0, 0)  (diagnostic, as in the reference)
     float *costs = nullptr;        // [B]     -ll_fwd
@@ -55,7 +56,7 @@ struct Workspace {
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Bytes needed for `shape`.  A function of (B, T[], S[]) only, like the reference
-// (gpu_workspace_manager.h:242-247); the value differs (60 B/row + O(B*T_max) instead of 12 B/row).
+// (gpu_workspace_manager.h:242-247); the value differs (76 B/row + O(B*T_max) instead of 12 B/row).
 // words of Workspace::k2_flags: two SETS of kK2FlagWords per utterance that take turns from launch to launch (a lattice
 // launch uses set `epoch & 1` and clears the other one for its successor: nothing in a launch ever has to reset a word
 // that a late CTA of the same launch might still touch), then (256 bytes clear of the flags that waiting CTAs poll)
@@ -80,6 +81,7 @@ inline size_t workspace_bytes(const Shape &sh) {
     n += align_up(rows * sizeof(Weight), 256);
     n += 2 * align_up(rows * sizeof(Cell), 256);
     n += align_up(rows * sizeof(float4), 256);
+    n += align_up(rows * sizeof(int), 256);
     n += 2 * align_up(B * sizeof(double), 256);
     n += align_up(B * sizeof(float), 256);
     n += align_up(k2_flag_words(sh.B) * sizeof(unsigned), 256);
@@ -105,6 +107,7 @@ inline Workspace carve_workspace(void *base, const Shape &sh) {
     w.alpha = reinterpret_cast<Cell *>(take(rows * sizeof(Cell)));
     w.beta = reinterpret_cast<Cell *>(take(rows * sizeof(Cell)));
     w.coef = reinterpret_cast<float4 *>(take(rows * sizeof(float4)));
+    w.rowlab = reinterpret_cast<int *>(take(rows * sizeof(int)));
     w.ll_fwd = reinterpret_cast<double *>(take(B * sizeof(double)));
     w.ll_bwd = reinterpret_cast<double *>(take(B * sizeof(double)));
     w.costs = reinterpret_cast<float *>(take(B * sizeof(float)));

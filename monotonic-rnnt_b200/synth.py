@@ -101,6 +101,14 @@ def workload(name: str, B: Optional[int] = None) -> Workload:
         T = np.full(B, 300, np.int32); S = np.full(B, 60, np.int32); V = 2000
         labels = labels_for(B, 60, V)
         return Workload("c5", B, V, T, S, labels, _alignment(T, S, labels, seed=7), max_shift=5)
+    if name == "c2v1025":  # c2 with a vocabulary that is not a multiple of 4: rows are not whole 16-byte vectors
+        B = B or 32
+        T = np.full(B, 150, np.int32); S = np.full(B, 40, np.int32); V = 1025
+        return Workload("c2v1025", B, V, T, S, labels_for(B, 40, V))
+    if name == "c4v5001":  # c4 likewise (real vocabularies: 1025, 5001, ...)
+        B = B or 8
+        T = np.full(B, 800, np.int32); S = np.full(B, 120, np.int32); V = 5001
+        return Workload("c4v5001", B, V, T, S, labels_for(B, 120, V))
     if name == "dense":   # tools only: the size of c2 with (almost) no dead rows, to separate streaming efficiency
         B = B or 32       # from the effect of skipping rows
         T = np.full(B, 1500, np.int32); S = np.full(B, 3, np.int32); V = 1000

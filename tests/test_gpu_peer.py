@@ -5,8 +5,6 @@ allocations (monotonic_rnnt_b200.peer.PeerBoards.local).  The CUDA-IPC mapping b
 `bench.py --gpus N` (it checks the exchanged sum against an NCCL all-reduce of the same costs) and by
 test_two_processes below where the box has two GPUs.
 """
-import time
-
 import numpy as np
 import pytest
 import torch
@@ -104,15 +102,46 @@ def test_two_ranks_on_one_device(dev):
         torch.cuda.synchronize()
         with torch.cuda.stream(s1):
             h1.enqueue_forward(c1.blank, want_grads=False)   # publishes, then waits for rank 0 in a one-warp kernel
-        # (two lattice kernels must not share the device: each sizes its grid for CTAs that are all resident.  By now
-        # rank 1's is over and only its one waiting warp is left; the wait gives up after 2 s.)
-        time.sleep(0.05)
+        # (no pause: the two ranks' lattice kernels may share the device -- no CTA of either waits for a CTA that has
+        # not been dispatched, tests/test_gpu_concurrent.py)
         h0.enqueue(c0.blank, g0)                              # publishes at the start of K3, collects at its end
         torch.cuda.synchronize()
         assert abs(float(t0.item()) - want) <= 1e-5 * abs(want)
         assert float(t0.item()) == float(t1.item())
     h0.close()
     h1.close()
+    b0.close()
+    b1.close()
+
+
+def test_peer_that_never_shows_up_fails_for_good(dev):
+    """world = 2, but rank 1 never runs: rank 0's collect gives up after its time-out (set to 50 ms here; 60 s by
+    default), leaves NaN, and from then on the handle refuses to take part -- it must not publish epochs its peer has
+    not collected (the slot invariant is gone once a rank has moved on alone)."""
+    import monotonic_rnnt_b200 as mr
+    from monotonic_rnnt_b200 import _lib
+    c0 = fixtures.random_case("peer_to", 7, B=4, V=1000, T_range=(20, 40), S_range=(3, 10), dist="uniform")
+    b0, b1 = mr.peer.PeerBoards.local(2, dev)
+    total = torch.zeros(1).pin_memory()
+    h0, a0 = _handle(c0, dev)
+    h0.set_peer_reduce(b0, total)
+    h0.set_peer_timeout_ms(50)
+    g0 = torch.empty_like(a0)
+    with pytest.raises(_lib.RNNTError) as e:
+        h0.cost_and_grad(c0.blank, g0)
+    assert e.value.status == 3                       # RNNT_STATUS_EXECUTION_FAILED
+    assert np.isnan(float(total.item()))
+    assert h0.peer_failed()
+    # the gradients of the call itself are complete: only the exchange failed
+    ref = oracle.run(c0.acts, c0.labels, c0.T, c0.S, c0.V, blank=c0.blank, precision="f64_from_f32")
+    assert np.abs(g0.cpu().numpy() - ref.grads).max() <= 1e-5
+    with pytest.raises(_lib.RNNTError):              # final: no further exchange through this handle
+        h0.cost_and_grad(c0.blank, g0)
+    # without the exchange the handle works again
+    h0.set_peer_reduce(None, None)
+    costs = h0.cost_and_grad(c0.blank, g0)
+    np.testing.assert_allclose(costs.numpy(), ref.costs, rtol=1e-5)
+    h0.close()
     b0.close()
     b1.close()
 

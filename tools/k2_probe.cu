@@ -56,6 +56,7 @@ int main(int argc, char **argv) {
     cudaMemcpy(dlp, lp.data(), lp.size() * 16, cudaMemcpyHostToDevice);
     g_lp_host = lp.data(); g_lp_dev = dlp; g_lp_bytes = lp.size() * 16;
     a.T = dT; a.S = dS; a.labels = dl; a.row_start = drs; a.band = dband + 32; a.lp = dlp + slack; a.wts = dw;
+    int *drl; cudaMalloc(&drl, rows * 4); a.rowlab = drl;
     a.alpha = dal; a.beta = dbe; a.coef = dco; a.ll_fwd = dll; a.ll_bwd = dll + B; a.costs = dc; a.costs_mapped = nullptr; a.flags = dfl;
     a.T_max = T; a.S_max = S; a.V = 1000; a.blank = 0;
     a.chunk_frames = k2_chunk_frames(W);
