@@ -16,6 +16,7 @@
 #include <cstdint>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 #include <vector>
 
 #include "../status.h"
@@ -526,6 +527,7 @@ class Engine {
     // on.  All ranks must make the same sequence of such calls.  world == 0 turns it off.
     RNNTStatus set_peer_reduce(int rank, int world, void *const *boards, float *total_out) {
         peer_ = PeerReduce{};
+        peer_failed_ = false;  // (the failure belongs to the boards that are being let go of)
         if (world == 0) return RNNT_STATUS_SUCCESS;
         if (world < 0 || world > kPeerMaxWorld || rank < 0 || rank >= world || boards == nullptr) return RNNT_STATUS_INVALID_VALUE;
         for (int r = 0; r < world; ++r) {
@@ -678,6 +680,8 @@ class Engine {
                     bool whole_tiles, const DeviceInfo &dev, StreamTiling *tl) const {
         if (force_generic_) return false;
         if ((reinterpret_cast<uintptr_t>(p0) & 15) || (reinterpret_cast<uintptr_t>(p1) & 15)) return false;
+        // rows that are not whole 16-byte vectors stream too (aligned windows, k1_lse.cuh), for float32 logits
+        if (bf16_ && (static_cast<size_t>(V_) * elem_bytes()) % 16 != 0) return false;
         const int order[3] = {preferred_warps, 16, 8};
         for (int w : order) {
             if (stream_tiling(V_, elem_bytes(), extra_per_row, w, tile_target, whole_tiles, tl) &&
@@ -693,9 +697,9 @@ class Engine {
         return static_cast<int>(want < cap ? (want < 1 ? 1 : want) : cap);
     }
 
-    template <typename E, int NW, int C, bool COMPACT>
+    template <typename E, int NW, int C, bool COMPACT, bool UNALIGNED = false>
     RNNTStatus launch_k1_variant(int blank, cudaStream_t stream, const DeviceInfo &dev, const StreamTiling &tl) {
-        auto kern = k1_lse_tma_kernel<E, NW, C, COMPACT>;
+        auto kern = k1_lse_tma_kernel<E, NW, C, COMPACT, UNALIGNED>;
         // (the kernel's zero-fill warp: one more warp, 8 KB more shared memory; the gradient kernel continues the fill)
         ZeroFill zero{};
         const bool zero_warp = COMPACT && shared_fill_ctr_ != nullptr;
@@ -706,7 +710,7 @@ class Engine {
         if (smem > static_cast<size_t>(dev.max_smem_optin) || !ensure_dynamic_smem(kern, smem)) return RNNT_STATUS_EXECUTION_FAILED;
         kern<<<dev.sm_count, (NW + (zero_warp ? 2 : 1)) * kWarp, smem, stream>>>(
             static_cast<const E *>(acts_), labels_, ws_.rowmeta, ws_.lp, shape_.rows, V_, blank, tl.G, tl.stages, zero,
-            tl.smem_bytes);
+            tl.smem_bytes, tl.slot_bytes);
         return launched();
     }
 
@@ -724,6 +728,7 @@ class Engine {
     // rate on long inputs.  tools/kernel_times.py --dyn 0,1: c2 K3 205 -> 191 us, bfloat16 c2 unchanged, c3 1290 ->
     // 1368 us, c4 4469 -> 4588 us, c5 (alignment band, most tiles dead: one request per dead tile) 521 -> 664 us.
     // Hence: dense inputs of up to kDynamicTilesPerCta tiles per CTA.
+    static constexpr int kK1NineVectors = 9;
     static constexpr int64_t kDynamicTilesPerCta = 400;
     bool dynamic_tiles(const StreamTiling &tl) const {
         const int64_t ntiles = (shape_.rows + tl.G - 1) / tl.G;
@@ -735,6 +740,11 @@ class Engine {
 
     template <typename E, int NW, int C>
     RNNTStatus launch_k1_tma(int blank, cudaStream_t stream, const DeviceInfo &dev, const StreamTiling &tl) {
+        if (tl.unaligned) {
+            // rows that are not whole 16-byte vectors (float32 only; k1_lse.cuh: StreamWindow): one variant, the compact one
+            if constexpr (std::is_same<E, float>::value) return launch_k1_variant<E, NW, C, true, true>(blank, stream, dev, tl);
+            else return RNNT_STATUS_EXECUTION_FAILED;  // (can_stream never chooses it for bfloat16)
+        }
         return k1_compact(tl) ? launch_k1_variant<E, NW, C, true>(blank, stream, dev, tl)
                               : launch_k1_variant<E, NW, C, false>(blank, stream, dev, tl);
     }
@@ -743,8 +753,13 @@ class Engine {
     template <typename E, int NW>
     RNNTStatus launch_k1_nw(int blank, cudaStream_t stream, const DeviceInfo &dev, const StreamTiling &tl) {
         constexpr int NE = Elem<E>::kPerVec;
-        const int NV = V_ / NE;
+        const int NV = row_vectors<E>();
         if (NV <= (32 / NE) * kWarp) return launch_k1_tma<E, NW, 32 / NE>(blank, stream, dev, tl);
+        // rows just above 1024 logits that do not start on a 16-byte boundary (V = 1025: 258 covering vectors): one more
+        // vector per lane in registers instead of the 64-register variant with 16 warps
+        if constexpr (std::is_same<E, float>::value) {
+            if (tl.unaligned && NV <= kK1NineVectors * kWarp) return launch_k1_variant<E, NW, kK1NineVectors, true, true>(blank, stream, dev, tl);
+        }
         if constexpr (NW < 24) {  // (launch_k1_typed never asks for 24 warps with 64 registers of row per lane)
             if (NV <= (64 / NE) * kWarp) return launch_k1_tma<E, NW, 64 / NE>(blank, stream, dev, tl);
         }
@@ -756,8 +771,9 @@ class Engine {
         StreamTiling tl;
         // rows held in 64 registers per lane are too many for 25 warps on one SM
         constexpr int NE = Elem<E>::kPerVec;
-        const int NV = V_ / NE;
-        const bool wide_regs = NV > (32 / NE) * kWarp && NV <= (64 / NE) * kWarp;
+        const int NV = row_vectors<E>();
+        const bool nine = !bf16_ && V_ % NE != 0 && NV <= kK1NineVectors * kWarp;  // (launch_k1_nw)
+        const bool wide_regs = !nine && NV > (32 / NE) * kWarp && NV <= (64 / NE) * kWarp;
         const int want = (k1_warps_ == 24 && wide_regs) ? 16 : k1_warps_;
         const size_t input_bytes = static_cast<size_t>(shape_.rows) * V_ * elem_bytes();
         const int tile_target = input_bytes < kK1SmallInputBytes ? kK1TileTargetSmall : kK1TileTarget;
@@ -874,10 +890,12 @@ class Engine {
         return z;
     }
 
-    // bulk-copy granularity: whole 16-byte vectors per row, aligned base
+    // the fill stores 4-byte words at the ragged ends of a run of rows and bulk copies in between: an aligned base,
+    // rows of whole words
     bool zero_fill_possible() const {
         const size_t row_bytes = static_cast<size_t>(V_) * elem_bytes();
-        return row_bytes % 16 == 0 && reinterpret_cast<uintptr_t>(zero_dst_) % 16 == 0 && row_bytes < (1ull << 31);
+        return row_bytes % 4 == 0 && row_bytes >= 64 && reinterpret_cast<uintptr_t>(zero_dst_) % 16 == 0 &&
+               row_bytes < (1ull << 31);
     }
 
     // The zero fill as one more warp of the gradient kernel instead (k3_grad.cuh) -- and, in a one-shot call, of the
@@ -922,7 +940,17 @@ class Engine {
     template <typename E, int NW, bool SCALED>
     RNNTStatus launch_k3_tma(int blank, cudaStream_t stream, const DeviceInfo &dev, const StreamTiling &tl, void *grads,
                              const float *scale) {
-        auto kern = k3_grad_tma_kernel<E, NW, SCALED>;
+        if (tl.unaligned) {
+            if constexpr (std::is_same<E, float>::value) return launch_k3_tma_variant<E, NW, SCALED, true>(blank, stream, dev, tl, grads, scale);
+            else return RNNT_STATUS_EXECUTION_FAILED;
+        }
+        return launch_k3_tma_variant<E, NW, SCALED, false>(blank, stream, dev, tl, grads, scale);
+    }
+
+    template <typename E, int NW, bool SCALED, bool UNALIGNED>
+    RNNTStatus launch_k3_tma_variant(int blank, cudaStream_t stream, const DeviceInfo &dev, const StreamTiling &tl,
+                                     void *grads, const float *scale) {
+        auto kern = k3_grad_tma_kernel<E, NW, SCALED, UNALIGNED>;
         // the kernel's own zero-fill warp (one more warp, 8 KB more shared memory)
         ZeroFill zero{};
         const bool zero_warp = k3_zero_warp_ && !k3_write_dead_;
@@ -941,7 +969,7 @@ class Engine {
         if (launch_kernel(kern, grid, (NW + (zero_warp ? 2 : 1)) * kWarp, smem, stream, pdl_ && k3_follows_k2_,
                           static_cast<const E *>(acts_), ws_.coef, ws_.rowlab, static_cast<E *>(grads), shape_.rows, V_, blank, tl.G,
                           tl.stages, ws_.rowutt, scale, cost_mirror(), flags, zero, tl.smem_bytes,
-                          ws_.k2_flags + stream_ctr_word(B_), peer_args(peer_in_k3_)) != cudaSuccess)
+                          ws_.k2_flags + stream_ctr_word(B_), peer_args(peer_in_k3_), tl.slot_bytes) != cudaSuccess)
             return RNNT_STATUS_EXECUTION_FAILED;
         return launched();
     }
@@ -970,6 +998,13 @@ class Engine {
     }
 
     size_t elem_bytes() const { return bf16_ ? 2 : 4; }
+
+    // 16-byte vectors a row of logits spans at most (rows that do not start on a 16-byte boundary: one more)
+    template <typename E>
+    int row_vectors() const {
+        constexpr int NE = Elem<E>::kPerVec;
+        return V_ % NE == 0 ? V_ / NE : (V_ + NE - 1) / NE + 1;
+    }
 
     // the exchange of this call (a new epoch), or none
     PeerReduce peer_args(bool active) {

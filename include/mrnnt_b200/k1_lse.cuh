@@ -82,23 +82,44 @@ struct RowSum {
     float ML, sum;
 };
 
-// One row resident in shared memory (16-byte aligned, NV >= 1 vectors of 16 bytes = NV * Elem<E>::kPerVec logits).
+// A row whose bytes do not start / end on a 16-byte boundary (V % kPerVec != 0: UNALIGNED) is read through the
+// aligned vectors that cover it: `head` leading elements of vector 0 and everything from element `tail` on in the
+// last vector belong to the neighbouring rows (or are slack) and are replaced by -inf -- no effect on the max, exactly
+// zero in the sum.  Only the lanes that hold one of the two edge vectors do anything.
+template <int NE>
+__device__ __forceinline__ void mask_row_edges(float (&f)[NE], int j, int last, int head, int tail) {
+    if (j == 0) {
+#pragma unroll
+        for (int i = 0; i < NE; ++i) f[i] = i < head ? kNegInfF : f[i];
+    }
+    if (j == last) {
+#pragma unroll
+        for (int i = 0; i < NE; ++i) f[i] = i >= tail ? kNegInfF : f[i];
+    }
+}
+
+// One row resident in shared memory: NV >= 1 aligned vectors of 16 bytes = NV * Elem<E>::kPerVec logits (UNALIGNED:
+// the vectors that COVER the row, see mask_row_edges; head in [0, kPerVec), tail in [1, kPerVec]).
 // C > 0: the lane's <= C vectors live in registers, unpacked (NV <= 32*C); C == 0: two passes over shared
 // memory, any NV.  Vector slots beyond the row: whole slots (c*32 >= NV, warp-uniform) are skipped; in the one
 // partly filled slot the surplus lanes load the row's last vector again -- harmless for the max, masked in the sum.
-template <typename E, int C>
-__device__ __forceinline__ RowSum row_sums(const uint4 *__restrict__ xv, int NV, int lane) {
+template <typename E, int C, bool UNALIGNED = false>
+__device__ __forceinline__ RowSum row_sums(const uint4 *__restrict__ xv, int NV, int lane, int head = 0,
+                                           int tail = Elem<E>::kPerVec) {
     constexpr int NE = Elem<E>::kPerVec;
     float2 s[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
     float ML;
+    const bool edges = UNALIGNED && (head != 0 || tail != NE);  // (warp-uniform)
     if constexpr (C > 0) {
         float f[C][NE];
         Elem<E>::unpack(xv[min(lane, NV - 1)], f[0]);
+        if (edges) mask_row_edges<NE>(f[0], min(lane, NV - 1), NV - 1, head, tail);
         float m = vec_max<NE>(f[0]);
 #pragma unroll
         for (int c = 1; c < C; ++c) {
             if (c * kWarp < NV) {
                 Elem<E>::unpack(xv[min(lane + c * kWarp, NV - 1)], f[c]);
+                if (edges) mask_row_edges<NE>(f[c], min(lane + c * kWarp, NV - 1), NV - 1, head, tail);
                 m = fmaxf(m, vec_max<NE>(f[c]));
             }
         }
@@ -118,6 +139,7 @@ __device__ __forceinline__ RowSum row_sums(const uint4 *__restrict__ xv, int NV,
         for (int j = lane; j < NV; j += kWarp) {
             float f[NE];
             Elem<E>::unpack(xv[j], f);
+            if (edges) mask_row_edges<NE>(f, j, NV - 1, head, tail);
             m = fmaxf(m, vec_max<NE>(f));
         }
         ML = warp_max_redux(m) * kLog2e;
@@ -126,6 +148,7 @@ __device__ __forceinline__ RowSum row_sums(const uint4 *__restrict__ xv, int NV,
         for (int j = lane; j < NV; j += kWarp) {
             float f[NE];
             Elem<E>::unpack(xv[j], f);
+            if (edges) mask_row_edges<NE>(f, j, NV - 1, head, tail);
             exp_acc<NE>(f, neg, s);
         }
     }
@@ -248,8 +271,39 @@ struct StreamTiling {
     int G = 0;       // rows per tile: a power of two in 1..32
     int stages = 0;  // ring depth
     int warps = 0;   // consumer warps (8 or 16)
+    size_t slot_bytes = 0;  // data bytes of one ring slot: G rows, plus -- when rows are not whole 16-byte vectors -- the
+                            // slack around the aligned window that covers the tile (stream_window)
+    bool unaligned = false; // V * sizeof(element) is not a multiple of 16
     size_t smem_bytes = 0;
 };
+
+// Rows that are not whole 16-byte vectors (V % 4 != 0 for float): a bulk copy wants 16-byte aligned addresses and sizes,
+// so what is copied for a run of rows [b0, b1) (bytes of the whole array) is the aligned window that covers it, and a ring
+// slot mirrors global memory from the aligned address at or below its tile's first byte: slot byte k <-> global byte
+// A0 + k, A0 = tile_first_byte & ~15.  The consumers read (and the gradient kernel writes) a row through the aligned
+// vectors that cover it and mask the few elements at the two ends that are not the row's (mask_row_edges).
+struct StreamWindow {
+    size_t slot_off;  // offset of the window in the slot
+    size_t g_off;     // offset of the window in the array
+    uint32_t bytes;   // multiple of 16
+    uint32_t tail;    // bytes of the run beyond the window, at the very end of the array (< 16; copied by hand)
+};
+__device__ __forceinline__ StreamWindow stream_window(size_t tile_b0, size_t b0, size_t b1, size_t total_bytes) {
+    const size_t a0 = tile_b0 & ~static_cast<size_t>(15);
+    const size_t w0 = b0 & ~static_cast<size_t>(15);
+    size_t w1 = (b1 + 15) & ~static_cast<size_t>(15);
+    StreamWindow w;
+    w.tail = 0;
+    if (w1 > total_bytes) {  // only the array's last row can get here: never read behind the caller's buffer
+        w1 = total_bytes & ~static_cast<size_t>(15);
+        w.tail = static_cast<uint32_t>(b1 - (w1 > b0 ? w1 : b0));
+        if (w1 < w0) w1 = w0;
+    }
+    w.slot_off = w0 - a0;
+    w.g_off = w0;
+    w.bytes = static_cast<uint32_t>(w1 - w0);
+    return w;
+}
 
 constexpr int kStreamMaxStages = 12;
 constexpr size_t kStreamSmemBudget = 200 * 1024;  // of the 227 KB a CTA may use
@@ -275,10 +329,14 @@ constexpr int kK3TileTarget = 32 * 1024;
 inline bool stream_tiling(int V, size_t elem_bytes, size_t extra_per_row, int warps, int tile_target,
                           bool whole_tiles_per_warp_set, StreamTiling *out) {
     const size_t row_bytes = static_cast<size_t>(V) * elem_bytes;
-    if (V <= 0 || (row_bytes % 16) != 0 || (warps != 8 && warps != 16 && warps != 24)) return false;
+    if (V <= 0 || (warps != 8 && warps != 16 && warps != 24)) return false;
+    const bool unaligned = (row_bytes % 16) != 0;
+    if (unaligned && row_bytes < 64) return false;  // (windows of neighbouring runs must not overlap; tiny rows: generic kernels)
     int G = 1;
     while (G < 32 && static_cast<size_t>(2 * G) * row_bytes <= static_cast<size_t>(tile_target)) G *= 2;
-    const size_t slot = static_cast<size_t>(G) * row_bytes + 32 * (sizeof(int) + extra_per_row) + 16;
+    // unaligned rows: the aligned window around a tile is up to 15 bytes longer at either end
+    const size_t data = unaligned ? (static_cast<size_t>(G) * row_bytes + 15) / 16 * 16 + 32 : static_cast<size_t>(G) * row_bytes;
+    const size_t slot = data + 32 * (sizeof(int) + extra_per_row) + 16;
     int stages = static_cast<int>(kStreamSmemBudget / slot);
     if (stages > kStreamMaxStages) stages = kStreamMaxStages;
     // warp w's uses repeat with period lcm(NW, G) rows = NW / gcd(NW, G) tiles (24 warps on 16-row tiles: 3)
@@ -295,6 +353,8 @@ inline bool stream_tiling(int V, size_t elem_bytes, size_t extra_per_row, int wa
     out->G = G;
     out->stages = stages;
     out->warps = warps;
+    out->slot_bytes = data;
+    out->unaligned = unaligned;
     out->smem_bytes = static_cast<size_t>(stages) * slot + 128;
     return true;
 }
@@ -314,6 +374,71 @@ __device__ __forceinline__ void issue_live_runs(uint32_t mask, E *tile, const E 
     }
 }
 
+// The same for rows that are not whole 16-byte vectors: per run the aligned window that covers it (stream_window).
+// Called by one lane, which also arrives on the barrier with the byte count it is about to issue (two passes over the
+// runs: the count first).  `slot` mirrors the array from (row0 * row_bytes) & ~15 on.
+template <typename E>
+__device__ __forceinline__ void issue_live_runs_unaligned(uint32_t mask, unsigned char *slot, const E *acts, int64_t row0,
+                                                          int V, int64_t rows, uint64_t *bar, uint64_t policy) {
+    const size_t rb = static_cast<size_t>(V) * sizeof(E);
+    const size_t total = static_cast<size_t>(rows) * rb;
+    const size_t tile_b0 = static_cast<size_t>(row0) * rb;
+    const unsigned char *g = reinterpret_cast<const unsigned char *>(acts);
+    uint32_t tx = 0;
+    for (uint32_t m = mask; m;) {
+        const int r0 = __ffs(m) - 1;
+        const uint32_t inv = ~(m >> r0);
+        const int len = inv ? (__ffs(inv) - 1) : 32;
+        tx += stream_window(tile_b0, tile_b0 + r0 * rb, tile_b0 + (r0 + len) * rb, total).bytes;
+        m = (len >= 32) ? 0u : (m & ~(((1u << len) - 1u) << r0));
+    }
+    for (uint32_t m = mask; m;) {
+        const int r0 = __ffs(m) - 1;
+        const uint32_t inv = ~(m >> r0);
+        const int len = inv ? (__ffs(inv) - 1) : 32;
+        const size_t b1 = tile_b0 + (r0 + len) * rb;
+        const StreamWindow w = stream_window(tile_b0, tile_b0 + r0 * rb, b1, total);
+        if (w.tail != 0) {  // the array's last bytes, behind the last whole 16-byte vector: by hand, element by element
+            const size_t a0 = tile_b0 & ~static_cast<size_t>(15);
+            for (size_t b = b1 - w.tail; b < b1; b += sizeof(E))
+                *reinterpret_cast<E *>(slot + (b - a0)) = *reinterpret_cast<const E *>(g + b);
+        }
+        m = (len >= 32) ? 0u : (m & ~(((1u << len) - 1u) << r0));
+    }
+    mbar_arrive_expect_tx(bar, tx);  // (release: the hand-copied tail is in place for whoever sees the barrier complete)
+    for (uint32_t m = mask; m;) {
+        const int r0 = __ffs(m) - 1;
+        const uint32_t inv = ~(m >> r0);
+        const int len = inv ? (__ffs(inv) - 1) : 32;
+        const StreamWindow w = stream_window(tile_b0, tile_b0 + r0 * rb, tile_b0 + (r0 + len) * rb, total);
+        if (w.bytes != 0) bulk_g2s_hint(slot + w.slot_off, g + w.g_off, w.bytes, bar, policy);
+        m = (len >= 32) ? 0u : (m & ~(((1u << len) - 1u) << r0));
+    }
+}
+
+// Where a row of an unaligned array lies in its tile's slot (see StreamWindow).
+struct RowWindow {
+    size_t vec_off;  // byte offset in the slot of the first aligned vector that covers the row
+    size_t row_off;  // byte offset in the slot of the row's first element
+    int head;        // elements of that vector before the row
+    int nvec;        // aligned vectors that cover the row
+    int tail;        // elements of the last vector that belong to the row (1..kPerVec)
+};
+template <typename E>
+__device__ __forceinline__ RowWindow row_window(int64_t tile_row0, int r, int V) {
+    constexpr int NE = Elem<E>::kPerVec;
+    const size_t rb = static_cast<size_t>(V) * sizeof(E);
+    const size_t tile_b0 = static_cast<size_t>(tile_row0) * rb;
+    const size_t off = tile_b0 + static_cast<size_t>(r) * rb - (tile_b0 & ~static_cast<size_t>(15));
+    RowWindow w;
+    w.row_off = off;
+    w.vec_off = off & ~static_cast<size_t>(15);
+    w.head = static_cast<int>((off & 15) / sizeof(E));
+    w.nvec = (w.head + V + NE - 1) / NE;
+    w.tail = w.head + V - (w.nvec - 1) * NE;
+    return w;
+}
+
 // COMPACT: tiles without a live row take no ring slot (the slots carry their tile's index and the consumers walk
 // the slots, not the tiles; the producer ends the sequence with one terminator per slot).  Worth it when many
 // tiles are dead -- alignment-restricted lattices, padded inputs -- and costs ~2 % on dense inputs (the end of the
@@ -325,15 +450,15 @@ inline size_t k1_smem_bytes(size_t ring_bytes, bool zero_warp) {
     return zero_warp ? (ring_bytes + 127) / 128 * 128 + kZeroFillBytes + 16 : ring_bytes;
 }
 
-template <typename E, int NW, int C, bool COMPACT>
+// UNALIGNED: rows are not whole 16-byte vectors (StreamWindow above); slot_bytes = StreamTiling::slot_bytes.
+template <typename E, int NW, int C, bool COMPACT, bool UNALIGNED = false>
 static __global__ void __launch_bounds__((NW + (COMPACT ? 2 : 1)) * kWarp, 1)
     k1_lse_tma_kernel(const E *__restrict__ acts, const int *__restrict__ labels,
                       const int *__restrict__ rowmeta, RawRow *__restrict__ lp, int64_t rows, int V, int blank,
-                      int G, int stages, ZeroFill zero, size_t ring_bytes) {
+                      int G, int stages, ZeroFill zero, size_t ring_bytes, size_t slot_bytes) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const size_t tile_elems = static_cast<size_t>(G) * V;
-    E *tiles = reinterpret_cast<E *>(smem_raw);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + static_cast<size_t>(stages) * tile_elems * sizeof(E));
+    unsigned char *tiles = smem_raw;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + static_cast<size_t>(stages) * slot_bytes);
     uint64_t *empty = full + stages;
     // per slot and row: (rowmeta, which of this CTA's tiles the slot holds; -1: no more tiles) -- one 8-byte load
     int2 *meta_sh = reinterpret_cast<int2 *>(empty + stages);
@@ -398,9 +523,14 @@ static __global__ void __launch_bounds__((NW + (COMPACT ? 2 : 1)) * kWarp, 1)
                 meta_sh[stage * 32 + lane] = make_int2(lane < G ? m : kRowDead, static_cast<int>(k));
                 __syncwarp();
                 if (lane == 0) {
-                    mbar_arrive_expect_tx(full + stage, static_cast<uint32_t>(__popc(mask)) * static_cast<uint32_t>(V) *
-                                                            static_cast<uint32_t>(sizeof(E)));
-                    issue_live_runs<E>(mask, tiles + stage * tile_elems, acts + row0 * V, V, full + stage, policy);
+                    if constexpr (UNALIGNED) {
+                        issue_live_runs_unaligned<E>(mask, tiles + stage * slot_bytes, acts, row0, V, rows, full + stage, policy);
+                    } else {
+                        mbar_arrive_expect_tx(full + stage, static_cast<uint32_t>(__popc(mask)) * static_cast<uint32_t>(V) *
+                                                                static_cast<uint32_t>(sizeof(E)));
+                        issue_live_runs<E>(mask, reinterpret_cast<E *>(tiles + stage * slot_bytes), acts + row0 * V, V,
+                                           full + stage, policy);
+                    }
                 }
                 if (++stage == stages) {
                     stage = 0;
@@ -441,10 +571,19 @@ static __global__ void __launch_bounds__((NW + (COMPACT ? 2 : 1)) * kWarp, 1)
             MRNNT_K1_ADD(warp, 2, 1);
             const int meta = mk.x;
             if (row < rows && meta != kRowDead) {
-                const E *xrow = tiles + stage * tile_elems + static_cast<size_t>(r) * V;
+                const unsigned char *slot = tiles + stage * slot_bytes;
                 int lab = -1;
                 if (lane == 0 && meta >= 0) lab = __ldg(labels + meta);  // latency hides under the row math
-                const RowSum den = row_sums<E, C>(reinterpret_cast<const uint4 *>(xrow), NV, lane);
+                const E *xrow;
+                RowSum den;
+                if constexpr (UNALIGNED) {
+                    const RowWindow w = row_window<E>(row - r, r, V);
+                    xrow = reinterpret_cast<const E *>(slot + w.row_off);
+                    den = row_sums<E, C, true>(reinterpret_cast<const uint4 *>(slot + w.vec_off), w.nvec, lane, w.head, w.tail);
+                } else {
+                    xrow = reinterpret_cast<const E *>(slot) + static_cast<size_t>(r) * V;
+                    den = row_sums<E, C>(reinterpret_cast<const uint4 *>(xrow), NV, lane);
+                }
                 if (lane == 0) {
                     const bool has = lab >= 0 && lab < V;
                     k1_store_row(lp, row, den, Elem<E>::to_float(xrow[blank]),

@@ -34,13 +34,16 @@
 //    B. part 0 runs the two systolic rows; the weights of a whole CHUNK of frames arrive in shared memory by
 //       one bulk async copy (TMA engine) per chunk, issued by an otherwise idle warp per direction.
 //    C. all parts fold alpha, beta, the likelihood and the denominators into one record per row, so that the
-//       gradient kernel is a pure stream: the high float dh of the row's denominator and, relative to it,
-//         r0 = log2( alpha(t-1,s) beta(t,s)     / Z ) + dl
-//         rb = log2( alpha(t-1,s) beta(t+1,s)   / Z ) + dl
-//         rl = log2( alpha(t-1,s) beta(t+1,s+1) / Z ) + dl
-//       so that g[v] = 2^((x[v] kLog2e + dh) + r0) - ...: the large part (dh ~ -max * log2 e, hundreds for logits of
-//       magnitude 100) meets the logit inside one fused multiply-add whose RESULT is small, and the r's are small
-//       numbers too -- a single float coefficient c = r + dh would carry half an ulp of |dh| into every gradient.
+//       gradient kernel is a pure stream.  With r0 = log2( alpha(t-1,s) beta(t,s) / Z ) (the row's occupancy, <= 0) and
+//       D = dh + dl the row's base-2 log-softmax denominator:
+//         (H, L) = dh + (r0 + dl) as an error-free pair:   g[v] = 2^((x[v] kLog2e + H) + L) - ...
+//         qb = log2( alpha(t-1,s) p_blank(t,s) beta(t+1,s)   / Z )   what is subtracted at v == blank:    2^qb
+//         ql = log2( alpha(t-1,s) p_label(t,s) beta(t+1,s+1) / Z )   what is subtracted at v == label_s:  2^ql
+//       The large parts (H ~ -max * log2 e: hundreds for logits of magnitude 100) meet the logit inside one fused
+//       multiply-add whose RESULT is small.  qb and ql are formed HERE, from the row's blank / label logit in two-float
+//       arithmetic: where a path is forced through an improbable transition (p = 2^-400, posterior ~ 1) the lattice
+//       term is +400 and log2 p is -400, and rounding them separately before they cancel costs an ulp of 400 in the
+//       exponent, 4e-5 in the gradient.
 #pragma once
 
 #include "common.cuh"
@@ -75,7 +78,7 @@ struct K2Args {
     Weight *wts;       // [rows] transition weights, written by phase A
     Cell *alpha;
     Cell *beta;
-    float4 *coef;      // [rows] (r0, rb, rl, dh) per row, see the head of this file; r0 == -inf: a zero gradient row
+    float4 *coef;      // [rows] (H, qb, ql, L) per row, see the head of this file; H == -inf: a zero gradient row
     int *rowlab;       // [rows] the row's label for the gradient kernel: >= 0, -1 none (or blank: the blank branch wins),
                        //        kRowDead: a row the plan calls dead (whoever zeroes those rows has done so or will)
     double *ll_fwd;
@@ -476,17 +479,40 @@ __device__ __forceinline__ void k2_chain_dispatch(const K2Args &a, int b, K2Dir 
 // Semantics of the lookups follow the reference accessors (gpu_rnnt_kernel.h:10-56): alpha(-1,0)=1,
 // alpha(-1,s>0)=0, beta(T,S)=1, beta(T,s<S)=0, beta(.,S+1)=0 (linear domain); everything else comes from
 // the stored grids, which hold zeros outside the lattice.
-//   log2( alpha * beta / Z ) = (e_a + e_b - e_Z) + log2( m_a * m_b / m_Z )
-// `lo`: what is added to it -- the low float of the row's denominator (see k2_coef_rows).
-__device__ __forceinline__ float k2_coef(const Cell &x, float ratio, int base_e, float lo) {
-    if (x.m == 0.0f) return kNegInfF;
-    // log2 of the mantissa product: exponent bits exactly, mantissa in [1,2) through MUFU.LG2 (absolute error
-    // 2^-22.6 on a value in [0,1): 1e-7 relative on the gradient)
+//   log2( alpha * beta / Z ) = (e_a + e_b - e_Z) + log2( m_a * m_b / m_Z ): the integer part exactly, and the
+// fraction in [0,1) through MUFU.LG2 on a mantissa in [1,2) (absolute error 2^-22.6: 1e-7 relative on the gradient).
+// false: the cell is zero.
+__device__ __forceinline__ bool k2_log2_ratio(const Cell &x, float ratio, int base_e, float &ipart, float &fpart) {
+    if (x.m == 0.0f) return false;
     const int bits = __float_as_int(ratio * x.m);
-    const int ip = (bits >> 23) - 127;
-    float fp;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(fp) : "f"(__int_as_float((bits & 0x007fffff) | 0x3f800000)));
-    return static_cast<float>(base_e + x.e + ip) + (fp + lo);
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(fpart) : "f"(__int_as_float((bits & 0x007fffff) | 0x3f800000)));
+    ipart = static_cast<float>(base_e + x.e + (bits >> 23) - 127);
+    return true;
+}
+// The occupancy term of a row as the pair (H, L) = dh + (log2(alpha beta / Z) + lo), H + L exact to ~48 bits.
+__device__ __forceinline__ void k2_coef_main(const Cell &x, float ratio, int base_e, float dh, float lo, float &H, float &L) {
+    float ip, fp;
+    if (!k2_log2_ratio(x, ratio, base_e, ip, fp)) {
+        H = kNegInfF;
+        L = 0.0f;
+        return;
+    }
+    float s, e1;
+    two_sum(ip, dh, s, e1);
+    const float rest = (e1 + lo) + fp;
+    two_sum(s, rest, H, L);
+}
+// log2 of a transition's posterior: log2(alpha beta' / Z) + x * log2(e) + dh + dl, every large part added error-free
+// (as in weight_from_logit); the result is <= 0 up to rounding.
+__device__ __forceinline__ float k2_coef_patch(const Cell &x, float ratio, int base_e, float logit, float dh, float dl) {
+    float ip, fp;
+    if (!k2_log2_ratio(x, ratio, base_e, ip, fp) || !(logit > kNegInfF)) return kNegInfF;
+    const float ph = logit * kLog2e;
+    const float pl = fmaf(logit, kLog2eLo, fmaf(logit, kLog2e, -ph));
+    float s, e1, h, e2;
+    two_sum(ph, dh, s, e1);   // log2 p, high part
+    two_sum(ip, s, h, e2);    // + the lattice term's integer part: what is left is small
+    return h + (((e2 + e1) + (pl + dl)) + fp);
 }
 
 __device__ __forceinline__ void k2_coef_rows(const K2Args &a, int b, int part, int parts, int tid = threadIdx.x,
@@ -520,7 +546,7 @@ __device__ __forceinline__ void k2_coef_rows(const K2Args &a, int b, int part, i
     constexpr int U = 4;  // rows per thread per batch: 5*U independent loads in flight before any use
     for (int base = i_begin + tid; base < i_end; base += U * nthreads) {
         Cell al[U], b0[U], b1[U], b2[U];
-        float2 dn[U];
+        RawRow rw[U];
         int lab[U], tt[U], ss[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -534,8 +560,9 @@ __device__ __forceinline__ void k2_coef_rows(const K2Args &a, int b, int part, i
             b0[u] = beta[min(i, n_valid - 1)];
             b1[u] = beta[min(i + ld, n_valid - 1)];
             b2[u] = beta[min(i + ld + 1, n_valid - 1)];
-            // (dh, dl): garbage for dead rows, but only used when alpha(t-1,s) != 0, i.e. when the row is live
-            dn[u] = *reinterpret_cast<const float2 *>(&lp[min(i, n_valid - 1)].dh);
+            // K1's record with the denominator pair: garbage for dead rows, but only used when alpha(t-1,s) != 0, i.e.
+            // when the row is live
+            rw[u] = lp[min(i, n_valid - 1)];
             lab[u] = (Sb > 0) ? labels[min(s, Sb - 1)] : -1;
             if (rowmeta[i] == kRowDead) lab[u] = kRowDead;
         }
@@ -554,7 +581,7 @@ __device__ __forceinline__ void k2_coef_rows(const K2Args &a, int b, int part, i
             // zero fill of this kernel or the gradient kernel -- a row whose coefficient merely came out as zero
             // (logits of -inf) is the gradient kernel's to write.
             if (lb != kRowDead && (s >= Sb || lb == a.blank || lb < 0 || lb >= a.V)) lb = -1;  // blank branch wins (cpu_rnnt.h:224-232)
-            float4 c;  // (r0, rb, rl, dh)
+            float4 c;  // (H, qb, ql, L)
             c.w = 0.0f;
             if (!inside || (feasible && av.m == 0.0f)) {
                 c.x = c.y = c.z = kNegInfF;
@@ -569,11 +596,10 @@ __device__ __forceinline__ void k2_coef_rows(const K2Args &a, int b, int part, i
                 // (lse_finish) stands for the missing x * kLog2eLo of the elements near the row's maximum -- the only
                 // ones whose gradient is not negligible -- so it is taken out again here (max * kLog2e ~ -dh: off by
                 // log2 sum <= 20, i.e. by < 3e-7 in the exponent).
-                const float lo = fmaf(dn[u].x, -kLog2eLoRel, dn[u].y);  // dl + max * kLog2eLo
-                c.x = k2_coef(b0[u], ratio, base_e, lo);
-                c.y = k2_coef(v1, ratio, base_e, lo);
-                c.z = k2_coef(v2, ratio, base_e, lo);
-                c.w = dn[u].x;
+                const float lo = fmaf(rw[u].dh, -kLog2eLoRel, rw[u].dl);  // dl + max * kLog2eLo
+                k2_coef_main(b0[u], ratio, base_e, rw[u].dh, lo, c.x, c.w);
+                c.y = k2_coef_patch(v1, ratio, base_e, rw[u].xb, rw[u].dh, rw[u].dl);
+                c.z = lb >= 0 ? k2_coef_patch(v2, ratio, base_e, rw[u].xl, rw[u].dh, rw[u].dl) : kNegInfF;
             }
             coef[i] = c;
             rowlab[i] = lb;

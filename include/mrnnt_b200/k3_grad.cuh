@@ -5,12 +5,12 @@
 // global memory per element, up to two exp per element, int32 element index).  CPU twin:
 // cpu_rnnt.h:216-236.
 //
-//   g[row, v] = 2^(t + r0) - [v == blank] 2^(t + rb) - [v == label_s] 2^(t + rl),   t = x[v] * kLog2e + dh
-// with the per-row record (r0, rb, rl, dh) and the row's label prepared by K2 (k2_lattice.cuh): dh is the high float
-// of the row's base-2 log-softmax denominator, so t = log2 p(v) is formed by ONE fused multiply-add whose result is
-// small (whatever the magnitude of the logits), and the r's are the small lattice terms.  Rows whose r0 is -inf
-// (alpha(t-1,s) outside the lattice) are never read: zeros are stored (reference: gpu_rnnt_kernel.h:266-271 does
-// this for the geometric part only).
+//   g[row, v] = 2^((x[v] * kLog2e + H) + L) - [v == blank] 2^qb - [v == label_s] 2^ql
+// with the per-row record (H, qb, ql, L) and the row's label prepared by K2 (k2_lattice.cuh): H + L = the row's base-2
+// log-softmax denominator plus the log2 of the row's occupancy, so the exponent is formed by ONE fused multiply-add
+// whose result is small (whatever the magnitude of the logits) plus a small correction, and the two subtracted terms
+// are complete.  Rows whose H is -inf (alpha(t-1,s) outside the lattice) are never read: zeros are stored
+// (reference: gpu_rnnt_kernel.h:266-271 does this for the geometric part only).
 // SCALED variants multiply utterance b's rows by scale[b] on the way out: the chain rule of the reference's
 // autograd glue (pytorch_binding/monotonic_rnnt_op.py:97-118, a separate read+write pass over the gradients
 // there) at no extra memory traffic.
@@ -28,8 +28,6 @@
 
 namespace mrnnt {
 
-__device__ __forceinline__ float grad_log2p(float x, float dh) { return fmaf(x, kLog2e, dh); }
-
 // Optional hand-over of the B costs to the host (a synchronous call's staging buffer in host-mapped pinned memory,
 // engine.cuh): done here, by the first CTA of the LAST kernel of the call, so that the PCIe write overlaps the whole
 // gradient pass instead of sitting between the lattice kernel and this one.
@@ -44,14 +42,10 @@ __device__ __forceinline__ void mirror_costs(const CostMirror &m, int nthreads) 
         for (int i = threadIdx.x; i < m.B; i += nthreads) m.mapped[i] = m.costs[i];
 }
 
-// subtract the blank / label term from component k of a vector of NE gradients, t = the components' log2 p (k is
-// warp-divergent, so the component is picked with selects instead of a dynamically indexed register array)
+// subtract d from component k of a vector of NE gradients (k is warp-divergent, so the component is picked with
+// selects instead of a dynamically indexed register array)
 template <int NE>
-__device__ __forceinline__ void patch_component(float (&g)[NE], const float (&t)[NE], int k, float r) {
-    float tv = t[0];
-#pragma unroll
-    for (int i = 1; i < NE; ++i) tv = (k == i) ? t[i] : tv;
-    const float d = ex2_approx(tv + r);
+__device__ __forceinline__ void patch_component(float (&g)[NE], int k, float d) {
 #pragma unroll
     for (int i = 0; i < NE; ++i) g[i] -= (k == i) ? d : 0.0f;
 }
@@ -82,10 +76,9 @@ static __global__ void __launch_bounds__(kGenericWarps * kWarp)
         const int lab = __ldg(rowlab + row);
         const float sc = scale != nullptr ? __ldg(scale + __ldg(rowutt + row)) : 1.0f;
         for (int v = lane; v < V; v += kWarp) {
-            const float t = grad_log2p(Elem<E>::to_float(x[v]), c.w);
-            float gv = ex2_approx(t + c.x);
-            if (v == blank) gv -= ex2_approx(t + c.y);
-            else if (v == lab) gv -= ex2_approx(t + c.z);
+            float gv = ex2_approx(fmaf(Elem<E>::to_float(x[v]), kLog2e, c.x) + c.w);
+            if (v == blank) gv -= ex2_approx(c.y);
+            else if (v == lab) gv -= ex2_approx(c.z);
             g[v] = Elem<E>::from_float(gv * sc);
         }
     }
@@ -114,18 +107,34 @@ inline size_t k3_smem_bytes(size_t ring_bytes, bool zero_warp) {
     return zero_warp ? (ring_bytes + 127) / 128 * 128 + kZeroFillBytes : ring_bytes;
 }
 
-template <typename E, int NW, bool SCALED>
+// One gradient row through the aligned 16-byte vectors that cover it (UNALIGNED rows, k1_lse.cuh: RowWindow): whole
+// vectors inside the row are stored as such, the up to two edge vectors element by element -- their other elements
+// belong to the neighbouring rows.
+template <typename E, int NE>
+__device__ __forceinline__ void store_row_vector(uint4 *gv, int j, const float (&g)[NE], int last, int head, int tail) {
+    const int lo = j == 0 ? head : 0, hi = j == last ? tail : NE;
+    if (lo == 0 && hi == NE) {
+        st_stream_u4(gv + j, Elem<E>::pack(g));
+    } else {
+        E *ge = reinterpret_cast<E *>(gv + j);
+#pragma unroll
+        for (int i = 0; i < NE; ++i)
+            if (i >= lo && i < hi) ge[i] = Elem<E>::from_float(g[i]);
+    }
+}
+
+// UNALIGNED: rows are not whole 16-byte vectors (k1_lse.cuh: StreamWindow); slot_bytes = StreamTiling::slot_bytes.
+template <typename E, int NW, bool SCALED, bool UNALIGNED = false>
 static __global__ void __launch_bounds__((NW + 2) * kWarp, 1)
     k3_grad_tma_kernel(const E *__restrict__ acts, const float4 *__restrict__ coef, const int *__restrict__ rowlab,
                        E *__restrict__ grads, int64_t rows, int V, int blank, int G, int stages,
                        const int *__restrict__ rowutt,
                        const float *__restrict__ scale, CostMirror mirror, int flags, ZeroFill zero, size_t ring_bytes,
-                       unsigned *__restrict__ dyn, PeerReduce peer) {
+                       unsigned *__restrict__ dyn, PeerReduce peer, size_t slot_bytes) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NE = Elem<E>::kPerVec;
-    const size_t tile_elems = static_cast<size_t>(G) * V;
-    E *tiles = reinterpret_cast<E *>(smem_raw);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + static_cast<size_t>(stages) * tile_elems * sizeof(E));
+    unsigned char *tiles = smem_raw;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + static_cast<size_t>(stages) * slot_bytes);
     uint64_t *empty = full + stages;
     float *scale_sh = reinterpret_cast<float *>(empty + stages);
     float4 *coef_sh = reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(empty + stages) +
@@ -179,9 +188,14 @@ static __global__ void __launch_bounds__((NW + 2) * kWarp, 1)
             if (lane == 0) tile_sh[stage] = static_cast<int>(k);
             __syncwarp();
             if (lane == 0) {
-                mbar_arrive_expect_tx(full + stage, static_cast<uint32_t>(__popc(mask)) * static_cast<uint32_t>(V) *
-                                                        static_cast<uint32_t>(sizeof(E)));
-                issue_live_runs<E>(mask, tiles + stage * tile_elems, acts + row0 * V, V, full + stage, policy);
+                if constexpr (UNALIGNED) {
+                    issue_live_runs_unaligned<E>(mask, tiles + stage * slot_bytes, acts, row0, V, rows, full + stage, policy);
+                } else {
+                    mbar_arrive_expect_tx(full + stage, static_cast<uint32_t>(__popc(mask)) * static_cast<uint32_t>(V) *
+                                                            static_cast<uint32_t>(sizeof(E)));
+                    issue_live_runs<E>(mask, reinterpret_cast<E *>(tiles + stage * slot_bytes), acts + row0 * V, V,
+                                       full + stage, policy);
+                }
             }
             if (++stage == stages) {
                 stage = 0;
@@ -346,43 +360,64 @@ static __global__ void __launch_bounds__((NW + 2) * kWarp, 1)
             if (k < 0) break;
             const int64_t row = (dynamic ? k : blockIdx.x + k * gridDim.x) * G + r;
             if (row < rows) {
-                const float4 c = coef_sh[stage * 32 + r];  // (r0, rb, rl, dh)
+                const float4 c = coef_sh[stage * 32 + r];  // (H, qb, ql, L)
                 const int lab = lab_sh[stage * 32 + r];    // -1 when the row has no (non-blank) label
-                uint4 *gv = reinterpret_cast<uint4 *>(grads + row * V);
+                // the aligned vectors that cover the row, in the slot and -- the same ones -- in the gradient array
+                const unsigned char *slot = tiles + stage * slot_bytes;
+                const uint4 *xv;
+                uint4 *gv;
+                int nvec = NV, head = 0, tail = NE;
+                if constexpr (UNALIGNED) {
+                    const RowWindow w = row_window<E>(row - r, r, V);
+                    xv = reinterpret_cast<const uint4 *>(slot + w.vec_off);
+                    gv = reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(grads) +
+                                                   ((static_cast<size_t>(row) * V * sizeof(E)) & ~static_cast<size_t>(15)));
+                    nvec = w.nvec;
+                    head = w.head;
+                    tail = w.tail;
+                } else {
+                    xv = reinterpret_cast<const uint4 *>(slot) + static_cast<size_t>(r) * NV;
+                    gv = reinterpret_cast<uint4 *>(grads + row * V);
+                }
                 if (c.x == kNegInfF) {
                     // a zero row; without write_dead somebody else zeroes the rows the plan calls dead (marked in the
                     // label slot; the lattice kernel's fill or a zero-fill warp, zero_fill.cuh), and only a row
                     // INSIDE the lattice that came out as zero (masked logits) is written here
-                    const uint4 z = make_uint4(0u, 0u, 0u, 0u);  // +0.0 in either element type
-                    if (write_dead || lab != kRowDead)
-                        for (int j = lane; j < NV; j += kWarp) st_stream_u4(gv + j, z);
+                    if (write_dead || lab != kRowDead) {
+                        if constexpr (UNALIGNED) {
+                            const float z[NE] = {};
+                            for (int j = lane; j < nvec; j += kWarp) store_row_vector<E, NE>(gv, j, z, nvec - 1, head, tail);
+                        } else {
+                            const uint4 z = make_uint4(0u, 0u, 0u, 0u);  // +0.0 in either element type
+                            for (int j = lane; j < NV; j += kWarp) st_stream_u4(gv + j, z);
+                        }
+                    }
                 } else {
-                    const uint4 *xv = reinterpret_cast<const uint4 *>(tiles + stage * tile_elems +
-                                                                      static_cast<size_t>(r) * V);
-                    const int jb = blank / NE, kb = blank - jb * NE;
-                    const int jl = lab >= 0 ? lab / NE : -1, kl = lab - jl * NE;
+                    // (element e of the row is component (e + head) % NE of vector (e + head) / NE)
+                    const int eb = blank + head, el = lab + head;
+                    const int jb = eb / NE, kb = eb - jb * NE;
+                    const int jl = lab >= 0 ? el / NE : -1, kl = el - jl * NE;
                     const float sc = SCALED ? scale_sh[stage * 32 + r] : 1.0f;
-                    const float2 l2 = make_float2(kLog2e, kLog2e), dh2 = make_float2(c.w, c.w), r2 = make_float2(c.x, c.x);
+                    const float2 l2 = make_float2(kLog2e, kLog2e), h2 = make_float2(c.x, c.x), lo2 = make_float2(c.w, c.w);
+                    const float db = ex2_approx(c.y), dl = ex2_approx(c.z);  // what the blank / the label element loses
 #pragma unroll 2
-                    for (int j = lane; j < NV; j += kWarp) {
-                        float x[NE], t[NE], g[NE];
+                    for (int j = lane; j < nvec; j += kWarp) {
+                        float x[NE], g[NE];
                         Elem<E>::unpack(xv[j], x);
 #pragma unroll
-                        for (int i = 0; i < NE; i += 2) {  // log2 p of two elements at a time (FFMA2 / FADD2)
-                            const float2 tt = __ffma2_rn(make_float2(x[i], x[i + 1]), l2, dh2);
-                            const float2 ee = __fadd2_rn(tt, r2);
-                            t[i] = tt.x;
-                            t[i + 1] = tt.y;
+                        for (int i = 0; i < NE; i += 2) {  // two elements at a time (FFMA2 / FADD2)
+                            const float2 ee = __fadd2_rn(__ffma2_rn(make_float2(x[i], x[i + 1]), l2, h2), lo2);
                             g[i] = ex2_approx(ee.x);
                             g[i + 1] = ex2_approx(ee.y);
                         }
-                        if (j == jb) patch_component<NE>(g, t, kb, c.y);
-                        if (j == jl) patch_component<NE>(g, t, kl, c.z);
+                        if (j == jb) patch_component<NE>(g, kb, db);
+                        if (j == jl) patch_component<NE>(g, kl, dl);
                         if (SCALED) {
 #pragma unroll
                             for (int i = 0; i < NE; ++i) g[i] *= sc;
                         }
-                        st_stream_u4(gv + j, Elem<E>::pack(g));
+                        if constexpr (UNALIGNED) store_row_vector<E, NE>(gv, j, g, nvec - 1, head, tail);
+                        else st_stream_u4(gv + j, Elem<E>::pack(g));
                     }
                 }
             }

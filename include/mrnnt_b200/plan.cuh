@@ -44,7 +44,7 @@ struct Workspace {
     Weight *wts = nullptr;         // [rows]  transition weights (m * 2^e pairs, band folded in), K2 phase A
     Cell *alpha = nullptr;         // [rows]  full T x (S+1) grid per utterance (m * 2^e), zero outside the band
     Cell *beta = nullptr;          // [rows]
-    float4 *coef = nullptr;        // [rows]  per-row gradient record (r0, rb, rl, dh), see k2_lattice.cuh
+    float4 *coef = nullptr;        // [rows]  per-row gradient record (H, qb, ql, L), see k2_lattice.cuh
     int *rowlab = nullptr;         // [rows]  the row's label as the gradient kernel needs it (-1 none, kRowDead dead)
     double *ll_fwd = nullptr;      // [B]     alpha(T-1, S)
     double *ll_bwd = nullptr;      // [B]     beta(0, 0)  (diagnostic, as in the reference)

@@ -19,7 +19,7 @@ struct ZeroFill {
     unsigned char *dst;   // the gradient buffer
     const int *rowmeta;   // [rows]
     int64_t rows;         // rows of the whole batch
-    unsigned row_bytes;   // V * sizeof(element), a multiple of 16
+    unsigned row_bytes;   // V * sizeof(element), a multiple of 4
     unsigned *ctr;        // the hand-out counter (OWNED: {units handed out, warps finished}, zero between launches)
 };
 
@@ -95,6 +95,15 @@ __device__ __forceinline__ void zero_dead_rows_impl(const ZeroFill &a, int fw, i
             const int len = inv ? __ffs(inv) - 1 : kWarp;
             unsigned char *p = a.dst + static_cast<size_t>(u0 * kWarp + lane) * a.row_bytes;
             size_t left = static_cast<size_t>(len) * a.row_bytes;
+            // rows that are not whole 16-byte vectors (row_bytes % 16 != 0, a multiple of 4): the up to 12 bytes before
+            // the run's first and behind its last 16-byte boundary go out as ordinary 4-byte stores, the rest in bulk
+            const size_t head = min(static_cast<size_t>((16u - (reinterpret_cast<uintptr_t>(p) & 15u)) & 15u), left);
+            for (size_t b = 0; b < head; b += 4) *reinterpret_cast<unsigned *>(p + b) = 0u;
+            p += head;
+            left -= head;
+            const size_t tail = left & 15u;
+            left -= tail;
+            for (size_t b = 0; b < tail; b += 4) *reinterpret_cast<unsigned *>(p + left + b) = 0u;
             while (left > 0) {
                 const uint32_t nbytes = left < static_cast<size_t>(kZeroFillBytes) ? static_cast<uint32_t>(left) : kZeroFillBytes;
                 bulk_s2g(p, zbuf, nbytes);

