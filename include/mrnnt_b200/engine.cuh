@@ -728,7 +728,6 @@ class Engine {
     // rate on long inputs.  tools/kernel_times.py --dyn 0,1: c2 K3 205 -> 191 us, bfloat16 c2 unchanged, c3 1290 ->
     // 1368 us, c4 4469 -> 4588 us, c5 (alignment band, most tiles dead: one request per dead tile) 521 -> 664 us.
     // Hence: dense inputs of up to kDynamicTilesPerCta tiles per CTA.
-    static constexpr int kK1NineVectors = 9;
     static constexpr int64_t kDynamicTilesPerCta = 400;
     bool dynamic_tiles(const StreamTiling &tl) const {
         const int64_t ntiles = (shape_.rows + tl.G - 1) / tl.G;
@@ -755,11 +754,7 @@ class Engine {
         constexpr int NE = Elem<E>::kPerVec;
         const int NV = row_vectors<E>();
         if (NV <= (32 / NE) * kWarp) return launch_k1_tma<E, NW, 32 / NE>(blank, stream, dev, tl);
-        // rows just above 1024 logits that do not start on a 16-byte boundary (V = 1025: 258 covering vectors): one more
-        // vector per lane in registers instead of the 64-register variant with 16 warps
-        if constexpr (std::is_same<E, float>::value) {
-            if (tl.unaligned && NV <= kK1NineVectors * kWarp) return launch_k1_variant<E, NW, kK1NineVectors, true, true>(blank, stream, dev, tl);
-        }
+
         if constexpr (NW < 24) {  // (launch_k1_typed never asks for 24 warps with 64 registers of row per lane)
             if (NV <= (64 / NE) * kWarp) return launch_k1_tma<E, NW, 64 / NE>(blank, stream, dev, tl);
         }
@@ -772,8 +767,7 @@ class Engine {
         // rows held in 64 registers per lane are too many for 25 warps on one SM
         constexpr int NE = Elem<E>::kPerVec;
         const int NV = row_vectors<E>();
-        const bool nine = !bf16_ && V_ % NE != 0 && NV <= kK1NineVectors * kWarp;  // (launch_k1_nw)
-        const bool wide_regs = !nine && NV > (32 / NE) * kWarp && NV <= (64 / NE) * kWarp;
+        const bool wide_regs = NV > (32 / NE) * kWarp && NV <= (64 / NE) * kWarp;
         const int want = (k1_warps_ == 24 && wide_regs) ? 16 : k1_warps_;
         const size_t input_bytes = static_cast<size_t>(shape_.rows) * V_ * elem_bytes();
         const int tile_target = input_bytes < kK1SmallInputBytes ? kK1TileTargetSmall : kK1TileTarget;
@@ -999,11 +993,11 @@ class Engine {
 
     size_t elem_bytes() const { return bf16_ ? 2 : 4; }
 
-    // 16-byte vectors a row of logits spans at most (rows that do not start on a 16-byte boundary: one more)
+    // 16-byte vectors that lie wholly inside a row of logits, at most (what the consumer warps keep in registers: the up
+    // to two edge vectors of a row that does not start / end on a 16-byte boundary are handled apart, k1_lse.cuh: RowEdges)
     template <typename E>
     int row_vectors() const {
-        constexpr int NE = Elem<E>::kPerVec;
-        return V_ % NE == 0 ? V_ / NE : (V_ + NE - 1) / NE + 1;
+        return V_ / Elem<E>::kPerVec;
     }
 
     // the exchange of this call (a new epoch), or none

@@ -82,44 +82,58 @@ struct RowSum {
     float ML, sum;
 };
 
-// A row whose bytes do not start / end on a 16-byte boundary (V % kPerVec != 0: UNALIGNED) is read through the
-// aligned vectors that cover it: `head` leading elements of vector 0 and everything from element `tail` on in the
-// last vector belong to the neighbouring rows (or are slack) and are replaced by -inf -- no effect on the max, exactly
-// zero in the sum.  Only the lanes that hold one of the two edge vectors do anything.
-template <int NE>
-__device__ __forceinline__ void mask_row_edges(float (&f)[NE], int j, int last, int head, int tail) {
-    if (j == 0) {
-#pragma unroll
-        for (int i = 0; i < NE; ++i) f[i] = i < head ? kNegInfF : f[i];
-    }
-    if (j == last) {
-#pragma unroll
-        for (int i = 0; i < NE; ++i) f[i] = i >= tail ? kNegInfF : f[i];
-    }
+// A row whose bytes do not start / end on a 16-byte boundary (V % kPerVec != 0: UNALIGNED) is split into its INTERIOR --
+// the aligned 16-byte vectors that lie wholly inside it, which go through exactly the code of an aligned row -- and up to
+// 2 * (kPerVec - 1) EDGE elements before and behind the interior, which lanes 0, 1, ... take one each (a scalar load;
+// -inf for the lanes that have none: no effect on the max, exactly zero in the sum).  The streaming kernels are bound by
+// their consumers' instruction stream at V ~ 1000, so the geometry is 32-bit arithmetic and the edge costs a dozen
+// instructions per row.  (Masking inside the vector loop costs eight predicated instructions on EVERY vector.)
+struct RowSplit {
+    unsigned off;    // byte offset of the row's first element in its tile's slot (the slot mirrors global memory from the
+                     // 16-byte boundary at or below the tile's first byte, see StreamWindow)
+    unsigned vec0;   // index (in 16-byte vectors from the slot's start) of the first interior vector
+    int ninterior;   // interior vectors
+    int nhead;       // edge elements before the interior: the row's elements [0, nhead)
+    int ntail;       // edge elements behind it: the row's elements [V - ntail, V)
+};
+template <typename E>
+__device__ __forceinline__ RowSplit row_split(int64_t tile_row0, int r, int V) {
+    const unsigned rb = static_cast<unsigned>(V) * static_cast<unsigned>(sizeof(E));
+    // (tile_row0 * rb) mod 16 from the two factors mod 16; the row's offset in the slot stays below 32 rows' bytes
+    const unsigned t16 = ((static_cast<unsigned>(tile_row0) & 15u) * (rb & 15u)) & 15u;
+    RowSplit w;
+    w.off = t16 + static_cast<unsigned>(r) * rb;
+    w.vec0 = (w.off + 15u) >> 4;
+    const unsigned end = w.off + rb;
+    w.ninterior = static_cast<int>((end >> 4) - w.vec0);
+    w.nhead = static_cast<int>((w.vec0 * 16u - w.off) / sizeof(E));
+    w.ntail = static_cast<int>((end & 15u) / sizeof(E));
+    return w;
+}
+// which element of the row this lane takes as its edge element (-1: none)
+__device__ __forceinline__ int edge_element(const RowSplit &w, int V, int lane) {
+    const int e = lane < w.nhead ? lane : V - w.ntail + (lane - w.nhead);
+    return lane < w.nhead + w.ntail ? e : -1;
 }
 
-// One row resident in shared memory: NV >= 1 aligned vectors of 16 bytes = NV * Elem<E>::kPerVec logits (UNALIGNED:
-// the vectors that COVER the row, see mask_row_edges; head in [0, kPerVec), tail in [1, kPerVec]).
+// One row resident in shared memory: NV >= 1 aligned vectors of 16 bytes = NV * Elem<E>::kPerVec logits, all of them
+// the row's own (an unaligned row: its interior; `edge` is then the lane's edge element, -inf where it has none).
 // C > 0: the lane's <= C vectors live in registers, unpacked (NV <= 32*C); C == 0: two passes over shared
 // memory, any NV.  Vector slots beyond the row: whole slots (c*32 >= NV, warp-uniform) are skipped; in the one
 // partly filled slot the surplus lanes load the row's last vector again -- harmless for the max, masked in the sum.
-template <typename E, int C, bool UNALIGNED = false>
-__device__ __forceinline__ RowSum row_sums(const uint4 *__restrict__ xv, int NV, int lane, int head = 0,
-                                           int tail = Elem<E>::kPerVec) {
+template <typename E, int C, bool EDGE = false>
+__device__ __forceinline__ RowSum row_sums(const uint4 *__restrict__ xv, int NV, int lane, float edge = kNegInfF) {
     constexpr int NE = Elem<E>::kPerVec;
     float2 s[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
     float ML;
-    const bool edges = UNALIGNED && (head != 0 || tail != NE);  // (warp-uniform)
     if constexpr (C > 0) {
         float f[C][NE];
         Elem<E>::unpack(xv[min(lane, NV - 1)], f[0]);
-        if (edges) mask_row_edges<NE>(f[0], min(lane, NV - 1), NV - 1, head, tail);
-        float m = vec_max<NE>(f[0]);
+        float m = EDGE ? fmaxf(edge, vec_max<NE>(f[0])) : vec_max<NE>(f[0]);
 #pragma unroll
         for (int c = 1; c < C; ++c) {
             if (c * kWarp < NV) {
                 Elem<E>::unpack(xv[min(lane + c * kWarp, NV - 1)], f[c]);
-                if (edges) mask_row_edges<NE>(f[c], min(lane + c * kWarp, NV - 1), NV - 1, head, tail);
                 m = fmaxf(m, vec_max<NE>(f[c]));
             }
         }
@@ -133,13 +147,13 @@ __device__ __forceinline__ RowSum row_sums(const uint4 *__restrict__ xv, int NV,
                 exp_acc_masked<NE>(f[c], neg, lane + c * kWarp < NV, s);
             }
         }
+        if constexpr (EDGE) s[0].x += ex2_approx(fmaf(edge, kLog2e, neg));  // (2^-inf = 0 for a lane without an edge element)
     } else {
-        float m = kNegInfF;
+        float m = edge;
 #pragma unroll 4
         for (int j = lane; j < NV; j += kWarp) {
             float f[NE];
             Elem<E>::unpack(xv[j], f);
-            if (edges) mask_row_edges<NE>(f, j, NV - 1, head, tail);
             m = fmaxf(m, vec_max<NE>(f));
         }
         ML = warp_max_redux(m) * kLog2e;
@@ -148,9 +162,9 @@ __device__ __forceinline__ RowSum row_sums(const uint4 *__restrict__ xv, int NV,
         for (int j = lane; j < NV; j += kWarp) {
             float f[NE];
             Elem<E>::unpack(xv[j], f);
-            if (edges) mask_row_edges<NE>(f, j, NV - 1, head, tail);
             exp_acc<NE>(f, neg, s);
         }
+        if constexpr (EDGE) s[0].x += ex2_approx(fmaf(edge, kLog2e, neg));
     }
     RowSum r;
     r.ML = ML;
@@ -332,24 +346,44 @@ inline bool stream_tiling(int V, size_t elem_bytes, size_t extra_per_row, int wa
     if (V <= 0 || (warps != 8 && warps != 16 && warps != 24)) return false;
     const bool unaligned = (row_bytes % 16) != 0;
     if (unaligned && row_bytes < 64) return false;  // (windows of neighbouring runs must not overlap; tiny rows: generic kernels)
+    // ring depth for tiles of G rows: what fits the budget, rounded down to the period of a warp's tile pattern (warp w's
+    // uses repeat with period lcm(NW, G) rows = NW / gcd(NW, G) tiles; 24 warps on 16-row tiles: 3); 0: no safe ring
+    auto depth_for = [&](int G, size_t *data_bytes) -> int {
+        // unaligned rows: the aligned window around a tile is up to 15 bytes longer at either end
+        const size_t data = unaligned ? (static_cast<size_t>(G) * row_bytes + 15) / 16 * 16 + 32 : static_cast<size_t>(G) * row_bytes;
+        const size_t slot = data + 32 * (sizeof(int) + extra_per_row) + 16;
+        int stages = static_cast<int>(kStreamSmemBudget / slot);
+        if (stages > kStreamMaxStages) stages = kStreamMaxStages;
+        int g = warps, h = G;
+        while (h != 0) {
+            const int t = g % h;
+            g = h;
+            h = t;
+        }
+        if (whole_tiles_per_warp_set && warps > G && warps % G != 0) return 0;
+        const int stride = warps > G ? warps / g : 1;
+        stages = stages / stride * stride;
+        *data_bytes = data;
+        return stages < 3 ? 0 : stages;
+    };
     int G = 1;
     while (G < 32 && static_cast<size_t>(2 * G) * row_bytes <= static_cast<size_t>(tile_target)) G *= 2;
-    // unaligned rows: the aligned window around a tile is up to 15 bytes longer at either end
-    const size_t data = unaligned ? (static_cast<size_t>(G) * row_bytes + 15) / 16 * 16 + 32 : static_cast<size_t>(G) * row_bytes;
-    const size_t slot = data + 32 * (sizeof(int) + extra_per_row) + 16;
-    int stages = static_cast<int>(kStreamSmemBudget / slot);
-    if (stages > kStreamMaxStages) stages = kStreamMaxStages;
-    // warp w's uses repeat with period lcm(NW, G) rows = NW / gcd(NW, G) tiles (24 warps on 16-row tiles: 3)
-    int g = warps, h = G;
-    while (h != 0) {
-        const int t = g % h;
-        g = h;
-        h = t;
+    size_t data = 0;
+    int stages = depth_for(G, &data);
+    // A vocabulary just above a power of two (V = 1025: 4100-byte rows) would halve the tile (the cost of a slot hand-over
+    // is per tile, not per byte: 16 KB tiles stream ~40 % slower than 32 KB ones): take the next size up when it is within
+    // a quarter of the target and the ring stays as deep as the consumer warps need (two tiles' worth of rows ahead).
+    if (G < 32 && static_cast<size_t>(2 * G) * row_bytes <= static_cast<size_t>(tile_target) + static_cast<size_t>(tile_target) / 4) {
+        size_t data2 = 0;
+        const int stages2 = depth_for(2 * G, &data2);
+        if (stages2 >= 6 || (stages2 >= 3 && stages2 >= stages)) {
+            G *= 2;
+            stages = stages2;
+            data = data2;
+        }
     }
-    if (whole_tiles_per_warp_set && warps > G && warps % G != 0) return false;
-    const int stride = warps > G ? warps / g : 1;
-    stages = stages / stride * stride;
-    if (stages < 3) return false;
+    if (stages == 0) return false;
+    const size_t slot = data + 32 * (sizeof(int) + extra_per_row) + 16;
     out->G = G;
     out->stages = stages;
     out->warps = warps;
@@ -375,68 +409,40 @@ __device__ __forceinline__ void issue_live_runs(uint32_t mask, E *tile, const E 
 }
 
 // The same for rows that are not whole 16-byte vectors: per run the aligned window that covers it (stream_window).
-// Called by one lane, which also arrives on the barrier with the byte count it is about to issue (two passes over the
-// runs: the count first).  `slot` mirrors the array from (row0 * row_bytes) & ~15 on.
+// Called by the WHOLE producer warp (the address arithmetic of a window is a few dozen 64-bit instructions; done by one
+// lane for every run of a tile it was what the ring waited for): lane r computes and issues the run that starts at row
+// r of the tile, lane 0 first posts the byte count of all of them.  `slot` mirrors the array from (row0 * row_bytes) & ~15 on.
 template <typename E>
 __device__ __forceinline__ void issue_live_runs_unaligned(uint32_t mask, unsigned char *slot, const E *acts, int64_t row0,
-                                                          int V, int64_t rows, uint64_t *bar, uint64_t policy) {
+                                                          int V, int64_t rows, uint64_t *bar, uint64_t policy, int lane) {
     const size_t rb = static_cast<size_t>(V) * sizeof(E);
     const size_t total = static_cast<size_t>(rows) * rb;
     const size_t tile_b0 = static_cast<size_t>(row0) * rb;
     const unsigned char *g = reinterpret_cast<const unsigned char *>(acts);
-    uint32_t tx = 0;
-    for (uint32_t m = mask; m;) {
-        const int r0 = __ffs(m) - 1;
-        const uint32_t inv = ~(m >> r0);
+    // this lane's row starts a run of live rows?
+    const bool starts = ((mask >> lane) & 1u) != 0u && (lane == 0 || ((mask >> (lane - 1)) & 1u) == 0u);
+    StreamWindow w;
+    w.bytes = 0;
+    w.tail = 0;
+    size_t b1 = 0;
+    if (starts) {
+        const uint32_t inv = ~(mask >> lane);  // (zeros shifted in: inv != 0 unless lane == 0 and all 32 rows are live)
         const int len = inv ? (__ffs(inv) - 1) : 32;
-        tx += stream_window(tile_b0, tile_b0 + r0 * rb, tile_b0 + (r0 + len) * rb, total).bytes;
-        m = (len >= 32) ? 0u : (m & ~(((1u << len) - 1u) << r0));
-    }
-    for (uint32_t m = mask; m;) {
-        const int r0 = __ffs(m) - 1;
-        const uint32_t inv = ~(m >> r0);
-        const int len = inv ? (__ffs(inv) - 1) : 32;
-        const size_t b1 = tile_b0 + (r0 + len) * rb;
-        const StreamWindow w = stream_window(tile_b0, tile_b0 + r0 * rb, b1, total);
+        b1 = tile_b0 + (lane + len) * rb;
+        w = stream_window(tile_b0, tile_b0 + lane * rb, b1, total);
         if (w.tail != 0) {  // the array's last bytes, behind the last whole 16-byte vector: by hand, element by element
             const size_t a0 = tile_b0 & ~static_cast<size_t>(15);
             for (size_t b = b1 - w.tail; b < b1; b += sizeof(E))
                 *reinterpret_cast<E *>(slot + (b - a0)) = *reinterpret_cast<const E *>(g + b);
         }
-        m = (len >= 32) ? 0u : (m & ~(((1u << len) - 1u) << r0));
     }
-    mbar_arrive_expect_tx(bar, tx);  // (release: the hand-copied tail is in place for whoever sees the barrier complete)
-    for (uint32_t m = mask; m;) {
-        const int r0 = __ffs(m) - 1;
-        const uint32_t inv = ~(m >> r0);
-        const int len = inv ? (__ffs(inv) - 1) : 32;
-        const StreamWindow w = stream_window(tile_b0, tile_b0 + r0 * rb, tile_b0 + (r0 + len) * rb, total);
-        if (w.bytes != 0) bulk_g2s_hint(slot + w.slot_off, g + w.g_off, w.bytes, bar, policy);
-        m = (len >= 32) ? 0u : (m & ~(((1u << len) - 1u) << r0));
-    }
-}
-
-// Where a row of an unaligned array lies in its tile's slot (see StreamWindow).
-struct RowWindow {
-    size_t vec_off;  // byte offset in the slot of the first aligned vector that covers the row
-    size_t row_off;  // byte offset in the slot of the row's first element
-    int head;        // elements of that vector before the row
-    int nvec;        // aligned vectors that cover the row
-    int tail;        // elements of the last vector that belong to the row (1..kPerVec)
-};
-template <typename E>
-__device__ __forceinline__ RowWindow row_window(int64_t tile_row0, int r, int V) {
-    constexpr int NE = Elem<E>::kPerVec;
-    const size_t rb = static_cast<size_t>(V) * sizeof(E);
-    const size_t tile_b0 = static_cast<size_t>(tile_row0) * rb;
-    const size_t off = tile_b0 + static_cast<size_t>(r) * rb - (tile_b0 & ~static_cast<size_t>(15));
-    RowWindow w;
-    w.row_off = off;
-    w.vec_off = off & ~static_cast<size_t>(15);
-    w.head = static_cast<int>((off & 15) / sizeof(E));
-    w.nvec = (w.head + V + NE - 1) / NE;
-    w.tail = w.head + V - (w.nvec - 1) * NE;
-    return w;
+    uint32_t tx = w.bytes;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tx += __shfl_xor_sync(0xffffffffu, tx, o);
+    __syncwarp();  // (the hand-copied tail is in place before the arrival that publishes the slot)
+    if (lane == 0) mbar_arrive_expect_tx(bar, tx);
+    __syncwarp();
+    if (w.bytes != 0) bulk_g2s_hint(slot + w.slot_off, g + w.g_off, w.bytes, bar, policy);
 }
 
 // COMPACT: tiles without a live row take no ring slot (the slots carry their tile's index and the consumers walk
@@ -522,15 +528,13 @@ static __global__ void __launch_bounds__((NW + (COMPACT ? 2 : 1)) * kWarp, 1)
                 MRNNT_K1_ADD(NW, 2, 1);
                 meta_sh[stage * 32 + lane] = make_int2(lane < G ? m : kRowDead, static_cast<int>(k));
                 __syncwarp();
-                if (lane == 0) {
-                    if constexpr (UNALIGNED) {
-                        issue_live_runs_unaligned<E>(mask, tiles + stage * slot_bytes, acts, row0, V, rows, full + stage, policy);
-                    } else {
-                        mbar_arrive_expect_tx(full + stage, static_cast<uint32_t>(__popc(mask)) * static_cast<uint32_t>(V) *
-                                                                static_cast<uint32_t>(sizeof(E)));
-                        issue_live_runs<E>(mask, reinterpret_cast<E *>(tiles + stage * slot_bytes), acts + row0 * V, V,
-                                           full + stage, policy);
-                    }
+                if constexpr (UNALIGNED) {
+                    issue_live_runs_unaligned<E>(mask, tiles + stage * slot_bytes, acts, row0, V, rows, full + stage, policy, lane);
+                } else if (lane == 0) {
+                    mbar_arrive_expect_tx(full + stage, static_cast<uint32_t>(__popc(mask)) * static_cast<uint32_t>(V) *
+                                                            static_cast<uint32_t>(sizeof(E)));
+                    issue_live_runs<E>(mask, reinterpret_cast<E *>(tiles + stage * slot_bytes), acts + row0 * V, V,
+                                       full + stage, policy);
                 }
                 if (++stage == stages) {
                     stage = 0;
@@ -577,9 +581,11 @@ static __global__ void __launch_bounds__((NW + (COMPACT ? 2 : 1)) * kWarp, 1)
                 const E *xrow;
                 RowSum den;
                 if constexpr (UNALIGNED) {
-                    const RowWindow w = row_window<E>(row - r, r, V);
-                    xrow = reinterpret_cast<const E *>(slot + w.row_off);
-                    den = row_sums<E, C, true>(reinterpret_cast<const uint4 *>(slot + w.vec_off), w.nvec, lane, w.head, w.tail);
+                    const RowSplit w = row_split<E>(row - r, r, V);
+                    xrow = reinterpret_cast<const E *>(slot + w.off);
+                    const int e = edge_element(w, V, lane);
+                    const float xe = e >= 0 ? Elem<E>::to_float(xrow[e]) : kNegInfF;
+                    den = row_sums<E, C, true>(reinterpret_cast<const uint4 *>(slot) + w.vec0, w.ninterior, lane, xe);
                 } else {
                     xrow = reinterpret_cast<const E *>(slot) + static_cast<size_t>(r) * V;
                     den = row_sums<E, C>(reinterpret_cast<const uint4 *>(xrow), NV, lane);

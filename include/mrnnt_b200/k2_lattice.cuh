@@ -224,6 +224,7 @@ __device__ __forceinline__ void k2_weight_rows(const K2Args &a, int b, int part,
     const int i_begin = static_cast<int>(static_cast<int64_t>(n) * part / parts);
     const int i_end = static_cast<int>(static_cast<int64_t>(n) * (part + 1) / parts);
     constexpr int U = 4;  // rows per thread per batch: every load first, then 2*U independent conversions
+    MRNNT_K2_STAMP(55);
     for (int base = i_begin + tid; base < i_end; base += U * nthreads) {
         RawRow raw[U];
         int2 lh[U], lq[U];
@@ -239,6 +240,10 @@ __device__ __forceinline__ void k2_weight_rows(const K2Args &a, int b, int part,
             // never written for dead rows: whatever is there is masked by the flags below
             raw[u] = lp[static_cast<int64_t>(t) * ld + ss[u]];
         }
+#ifdef MRNNT_K2_TRACE
+        if (raw[0].xb + raw[1].xb + raw[2].xb + raw[3].xb == 123.456f) return;  // (the stamp below waits for the loads)
+#endif
+        MRNNT_K2_STAMP(56);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             bool stay_ok, emit_ok;
@@ -255,6 +260,7 @@ __device__ __forceinline__ void k2_weight_rows(const K2Args &a, int b, int part,
             }
         }
     }
+    MRNNT_K2_STAMP(57);
 }
 
 // ---- phase B, one lane per direction: keep the chunk ring full --------------------------------------------
@@ -637,11 +643,12 @@ __device__ __forceinline__ void k2_await_ge(const unsigned *flag, unsigned value
 // grid B * parts: CTA index = b * parts + part.  No CTA ever waits for a CTA that may not have been dispatched yet, so
 // the kernel cannot deadlock whatever else shares the device (a second lattice launch on another stream, another
 // process under MPS, fewer SMs than the occupancy query saw):
-//   * the rows of phases A and C are handed out in blocks through per-utterance counters (`parts` only says how many
-//     CTAs were launched to share them).  Part 0 takes blocks too; once the counter has run out it waits for the blocks
-//     that were TAKEN -- by CTAs that are therefore running -- and does everything itself if no helper ever shows up;
+//   * the rows of phases A and C are cut into `parts` blocks; block p belongs to part p, which CLAIMS it (an atomic
+//     exchange on the block's word) before it touches it.  Part 0 does block 0 without asking -- nobody else ever takes
+//     it -- and then claims whatever has not been claimed yet and does that too: a helper that has not been dispatched
+//     by then is not waited for, it finds its block taken and leaves.  What part 0 does wait for (phase A only) are the
+//     blocks that WERE claimed by helpers -- CTAs that are therefore running;
 //   * a helper waits for its own utterance's part 0 only, a CTA with a lower index (CTAs are dispatched in index order).
-// Every CTA keeps one request for a block in flight while it works on the previous one.
 // The hand-over words come in two sets that take turns (plan.cuh: kK2FlagWords); this launch clears the other set.
 // Barrier among the warps that run the phases (all of them, or all but the zero-fill warps -- those take part in
 // nothing else: their stores wait on the memory system).
@@ -650,36 +657,26 @@ __device__ __forceinline__ void k2_phase_sync(int zero_warps) {
     else asm volatile("bar.sync 1, %0;" ::"r"((kK2Warps - zero_warps) * kWarp) : "memory");
 }
 
-// One block hand-out loop (phase A or C), whole phase-warp set.  `next`: the counter; `held` (thread `tid` 0 only): a
-// request made earlier, or kK2NoTicket.  fn(block, nblocks) does the rows.  Returns when the counter has run out.
-constexpr unsigned kK2NoTicket = 0xffffffffu;
+// Part 0, after its own block: claim the blocks 1 .. parts-1 that nobody has claimed and do them (fn(block)).  Returns the
+// number of blocks taken over.  `claim`: the phase's words, one per block.  Whole phase-warp set.
 template <typename Fn>
-__device__ __forceinline__ void k2_block_loop(unsigned *next, unsigned *done, unsigned held, int nblk, int tid, int zw,
-                                              unsigned *ticket_sh, Fn fn) {
-    unsigned nxt = held;
-    for (int it = 0;; ++it) {
-        if (tid == 0) {
-            if (nxt == kK2NoTicket) nxt = atomicAdd(next, 1u);
-            ticket_sh[it & 1] = nxt;
-            // (the answer is looked at one block later: its round trip hides behind this block's rows)
-            nxt = nxt < static_cast<unsigned>(nblk) ? atomicAdd(next, 1u) : nxt;
-        }
-        k2_phase_sync(zw);
-        const unsigned blk = ticket_sh[it & 1];
-        if (blk >= static_cast<unsigned>(nblk)) break;
-        fn(static_cast<int>(blk), nblk);
-        if (done != nullptr) {
-            __threadfence();
-            k2_phase_sync(zw);
-            if (tid == 0) atomicAdd(done, 1u);
+__device__ __forceinline__ int k2_take_over_unclaimed(unsigned *claim, int parts, int tid, int zw, unsigned *ticket_sh, Fn fn) {
+    if (tid >= 1 && tid < parts) ticket_sh[tid] = atomicExch(claim + tid, 1u);  // (all requests in flight together)
+    k2_phase_sync(zw);
+    int taken = 0;
+    for (int blk = 1; blk < parts; ++blk) {
+        if (ticket_sh[blk] == 0u) {  // (block-uniform)
+            fn(blk);
+            ++taken;
         }
     }
+    return taken;
 }
 
 template <int K>
 static __global__ void __launch_bounds__(kK2Threads) k2_lattice_kernel(K2Args a) {
     extern __shared__ __align__(128) unsigned char k2_smem[];
-    __shared__ unsigned ticket_sh[2];
+    __shared__ unsigned ticket_sh[kK2MaxParts];
     const int parts = a.parts;
     const int warp = threadIdx.x >> 5;
     const int zw = a.zero_warps;           // warps 0..zw-1 do the zero fill and nothing else
@@ -697,7 +694,7 @@ static __global__ void __launch_bounds__(kK2Threads) k2_lattice_kernel(K2Args a)
     const int part = blockIdx.x - b * parts;
     const int tid = threadIdx.x - zw * kWarp;  // thread index among the phase warps; tid 0 leads
     unsigned *fl = a.flags + (static_cast<size_t>(a.epoch & 1u) * a.B + b) * kK2FlagWords;
-    unsigned *a_next = fl, *a_done = fl + 1, *c_next = fl + 2, *done = fl + 3;
+    unsigned *a_claim = fl, *c_claim = fl + kK2MaxParts, *a_done = fl + 2 * kK2MaxParts, *done = a_done + 1;
     if (warp < zw) {
         // ---- zero fill: this warp's share of the batch's dead rows, nothing else (and nothing K1 wrote) ----
         if (warp == 0) MRNNT_K2_STAMP(53);
@@ -706,13 +703,11 @@ static __global__ void __launch_bounds__(kK2Threads) k2_lattice_kernel(K2Args a)
         return;
     }
     const int nphase = kK2Threads - zw * kWarp;
-    const int nblk = 2 * parts;  // blocks per phase: two per launched CTA
     MRNNT_K2_STAMP(0);
     pdl_wait();  // K1's records
-    // (Not before the wait: under programmatic dependent launch this CTA can be running while the PREVIOUS lattice
-    // launch has not yet cleared this set of hand-over words -- e.g. forward halves back to back with small kernels
-    // that all fit on the device together.  Behind the wait the predecessor chain has completed.)
-    const unsigned held = kK2NoTicket;
+    // (Nothing of the hand-over words is touched before this wait: under programmatic dependent launch this CTA can be
+    // running while the PREVIOUS lattice launch has not yet cleared this set -- e.g. forward halves back to back with
+    // small kernels that all fit on the device together.  Behind the wait the predecessor chain has completed.)
     if (blockIdx.x == 0) {
         if (tid == 0 && a.zero_clear != nullptr) *a.zero_clear = 0u;
         // the other set of hand-over words, for the next launch (its last user, the previous launch, is long gone)
@@ -721,17 +716,27 @@ static __global__ void __launch_bounds__(kK2Threads) k2_lattice_kernel(K2Args a)
     }
 
     // ---- phase A: transition weights ----
-    if (parts > 1) {
-        k2_block_loop(a_next, a_done, held, nblk, tid, zw, ticket_sh,
-                      [&](int blk, int n) { k2_weight_rows(a, b, blk, n, tid, nphase); });
+    if (part == 0) {
+        k2_weight_rows(a, b, 0, parts, tid, nphase);
     } else {
-        k2_weight_rows(a, b, 0, 1, tid, nphase);
+        if (tid == 0) ticket_sh[0] = atomicExch(a_claim + part, 1u);
+        k2_phase_sync(zw);
+        if (ticket_sh[0] == 0u) {
+            k2_weight_rows(a, b, part, parts, tid, nphase);
+            __threadfence();
+            k2_phase_sync(zw);
+            if (tid == 0) atomicAdd(a_done, 1u);
+        }
     }
 
-    unsigned held_c = kK2NoTicket;
+    unsigned c_mine = 1u;  // (tid 0 of a helper: what its claim of its phase-C block returned)
     if (part == 0) {
         // ---- phase B: the two recursions ----
         MRNNT_K2_STAMP(60);
+        int taken = 0;
+        if (parts > 1)
+            taken = k2_take_over_unclaimed(a_claim, parts, tid, zw, ticket_sh,
+                                           [&](int blk) { k2_weight_rows(a, b, blk, parts, tid, nphase); });
         const int ndir = a.need_beta ? 2 : 1;
         for (int d = 0; d < ndir; ++d) {
             K2Dir ring(k2_smem + d * dir_bytes, chunk_bytes, bufs);
@@ -745,8 +750,8 @@ static __global__ void __launch_bounds__(kK2Threads) k2_lattice_kernel(K2Args a)
         }
         if (tid == 0) {
             mbar_init_fence();
-            // every block of phase A has been taken (the counter ran out above); the takers are running CTAs
-            if (parts > 1) k2_await_ge(a_done, static_cast<unsigned>(nblk));
+            // the blocks that helpers claimed: those CTAs are running
+            if (parts > 1) k2_await_ge(a_done, static_cast<unsigned>(parts - 1 - taken));
         }
         k2_phase_sync(zw);  // (parts == 1: this is also what orders phase A before the bulk copies)
         MRNNT_K2_STAMP(61);
@@ -777,19 +782,22 @@ static __global__ void __launch_bounds__(kK2Threads) k2_lattice_kernel(K2Args a)
         MRNNT_K2_STAMP(51);
     } else {
         if (!a.need_beta) return;
-        // a helper asks for its first block of phase C while it waits for the recursions of its utterance's part 0
+        // a helper claims its block of phase C while it waits for the recursions of its utterance's part 0
         if (tid == 0) {
-            held_c = atomicAdd(c_next, 1u);
+            c_mine = atomicExch(c_claim + part, 1u);
             k2_await(done, a.epoch);
+            ticket_sh[1] = c_mine;  // (not word 0: a thread may still be looking at phase A's answer there)
         }
         k2_phase_sync(zw);
     }
     // ---- phase C: gradient coefficients ----
-    if (parts > 1) {
-        k2_block_loop(c_next, nullptr, held_c, nblk, tid, zw, ticket_sh,
-                      [&](int blk, int n) { k2_coef_rows(a, b, blk, n, tid, nphase); });
-    } else {
-        k2_coef_rows(a, b, 0, 1, tid, nphase);
+    if (part == 0) {
+        k2_coef_rows(a, b, 0, parts, tid, nphase);
+        if (parts > 1)
+            (void)k2_take_over_unclaimed(c_claim, parts, tid, zw, ticket_sh,
+                                         [&](int blk) { k2_coef_rows(a, b, blk, parts, tid, nphase); });
+    } else if (ticket_sh[1] == 0u) {
+        k2_coef_rows(a, b, part, parts, tid, nphase);
     }
     k2_phase_sync(zw);
     MRNNT_K2_STAMP(52);

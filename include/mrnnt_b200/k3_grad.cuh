@@ -107,22 +107,6 @@ inline size_t k3_smem_bytes(size_t ring_bytes, bool zero_warp) {
     return zero_warp ? (ring_bytes + 127) / 128 * 128 + kZeroFillBytes : ring_bytes;
 }
 
-// One gradient row through the aligned 16-byte vectors that cover it (UNALIGNED rows, k1_lse.cuh: RowWindow): whole
-// vectors inside the row are stored as such, the up to two edge vectors element by element -- their other elements
-// belong to the neighbouring rows.
-template <typename E, int NE>
-__device__ __forceinline__ void store_row_vector(uint4 *gv, int j, const float (&g)[NE], int last, int head, int tail) {
-    const int lo = j == 0 ? head : 0, hi = j == last ? tail : NE;
-    if (lo == 0 && hi == NE) {
-        st_stream_u4(gv + j, Elem<E>::pack(g));
-    } else {
-        E *ge = reinterpret_cast<E *>(gv + j);
-#pragma unroll
-        for (int i = 0; i < NE; ++i)
-            if (i >= lo && i < hi) ge[i] = Elem<E>::from_float(g[i]);
-    }
-}
-
 // UNALIGNED: rows are not whole 16-byte vectors (k1_lse.cuh: StreamWindow); slot_bytes = StreamTiling::slot_bytes.
 template <typename E, int NW, bool SCALED, bool UNALIGNED = false>
 static __global__ void __launch_bounds__((NW + 2) * kWarp, 1)
@@ -187,15 +171,13 @@ static __global__ void __launch_bounds__((NW + 2) * kWarp, 1)
             if (SCALED) scale_sh[stage * 32 + lane] = sc;
             if (lane == 0) tile_sh[stage] = static_cast<int>(k);
             __syncwarp();
-            if (lane == 0) {
-                if constexpr (UNALIGNED) {
-                    issue_live_runs_unaligned<E>(mask, tiles + stage * slot_bytes, acts, row0, V, rows, full + stage, policy);
-                } else {
-                    mbar_arrive_expect_tx(full + stage, static_cast<uint32_t>(__popc(mask)) * static_cast<uint32_t>(V) *
-                                                            static_cast<uint32_t>(sizeof(E)));
-                    issue_live_runs<E>(mask, reinterpret_cast<E *>(tiles + stage * slot_bytes), acts + row0 * V, V,
-                                       full + stage, policy);
-                }
+            if constexpr (UNALIGNED) {
+                issue_live_runs_unaligned<E>(mask, tiles + stage * slot_bytes, acts, row0, V, rows, full + stage, policy, lane);
+            } else if (lane == 0) {
+                mbar_arrive_expect_tx(full + stage, static_cast<uint32_t>(__popc(mask)) * static_cast<uint32_t>(V) *
+                                                        static_cast<uint32_t>(sizeof(E)));
+                issue_live_runs<E>(mask, reinterpret_cast<E *>(tiles + stage * slot_bytes), acts + row0 * V, V,
+                                   full + stage, policy);
             }
             if (++stage == stages) {
                 stage = 0;
@@ -362,44 +344,45 @@ static __global__ void __launch_bounds__((NW + 2) * kWarp, 1)
             if (row < rows) {
                 const float4 c = coef_sh[stage * 32 + r];  // (H, qb, ql, L)
                 const int lab = lab_sh[stage * 32 + r];    // -1 when the row has no (non-blank) label
-                // the aligned vectors that cover the row, in the slot and -- the same ones -- in the gradient array
+                // The row's vectors in the slot and in the gradient array.  A row that is not whole 16-byte vectors
+                // (UNALIGNED; k1_lse.cuh: RowSplit): its interior -- the aligned vectors wholly inside it, the same ones in
+                // the slot and in global memory -- plus up to 2 * (NE - 1) edge elements, one per lane 0, 1, ...
                 const unsigned char *slot = tiles + stage * slot_bytes;
                 const uint4 *xv;
                 uint4 *gv;
-                int nvec = NV, head = 0, tail = NE;
+                int nvec = NV, nhead = 0, e_edge = -1;
+                [[maybe_unused]] const E *xrow = nullptr;
+                E *grow = grads + row * V;
                 if constexpr (UNALIGNED) {
-                    const RowWindow w = row_window<E>(row - r, r, V);
-                    xv = reinterpret_cast<const uint4 *>(slot + w.vec_off);
-                    gv = reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(grads) +
-                                                   ((static_cast<size_t>(row) * V * sizeof(E)) & ~static_cast<size_t>(15)));
-                    nvec = w.nvec;
-                    head = w.head;
-                    tail = w.tail;
+                    const RowSplit w = row_split<E>(row - r, r, V);
+                    xrow = reinterpret_cast<const E *>(slot + w.off);
+                    xv = reinterpret_cast<const uint4 *>(slot) + w.vec0;
+                    gv = reinterpret_cast<uint4 *>(grow + w.nhead);
+                    nvec = w.ninterior;
+                    nhead = w.nhead;
+                    e_edge = edge_element(w, V, lane);
                 } else {
                     xv = reinterpret_cast<const uint4 *>(slot) + static_cast<size_t>(r) * NV;
-                    gv = reinterpret_cast<uint4 *>(grads + row * V);
+                    gv = reinterpret_cast<uint4 *>(grow);
                 }
                 if (c.x == kNegInfF) {
                     // a zero row; without write_dead somebody else zeroes the rows the plan calls dead (marked in the
                     // label slot; the lattice kernel's fill or a zero-fill warp, zero_fill.cuh), and only a row
                     // INSIDE the lattice that came out as zero (masked logits) is written here
                     if (write_dead || lab != kRowDead) {
-                        if constexpr (UNALIGNED) {
-                            const float z[NE] = {};
-                            for (int j = lane; j < nvec; j += kWarp) store_row_vector<E, NE>(gv, j, z, nvec - 1, head, tail);
-                        } else {
-                            const uint4 z = make_uint4(0u, 0u, 0u, 0u);  // +0.0 in either element type
-                            for (int j = lane; j < NV; j += kWarp) st_stream_u4(gv + j, z);
-                        }
+                        const uint4 z = make_uint4(0u, 0u, 0u, 0u);  // +0.0 in either element type
+                        for (int j = lane; j < nvec; j += kWarp) st_stream_u4(gv + j, z);
+                        if (UNALIGNED && e_edge >= 0) grow[e_edge] = Elem<E>::from_float(0.0f);
                     }
                 } else {
-                    // (element e of the row is component (e + head) % NE of vector (e + head) / NE)
-                    const int eb = blank + head, el = lab + head;
-                    const int jb = eb / NE, kb = eb - jb * NE;
-                    const int jl = lab >= 0 ? el / NE : -1, kl = el - jl * NE;
                     const float sc = SCALED ? scale_sh[stage * 32 + r] : 1.0f;
                     const float2 l2 = make_float2(kLog2e, kLog2e), h2 = make_float2(c.x, c.x), lo2 = make_float2(c.w, c.w);
-                    const float db = ex2_approx(c.y), dl = ex2_approx(c.z);  // what the blank / the label element loses
+                    // (element e of the row is component (e - nhead) % NE of interior vector (e - nhead) / NE; an edge
+                    // element is nobody's component: jb / jl stay -1 and the edge code below patches it)
+                    const int ib = blank - nhead, il = lab - nhead;
+                    const bool b_in = ib >= 0 && ib < nvec * NE, l_in = lab >= 0 && il >= 0 && il < nvec * NE;
+                    const int jb = b_in ? ib / NE : -1, kb = ib - jb * NE;
+                    const int jl = l_in ? il / NE : -1, kl = il - jl * NE;
 #pragma unroll 2
                     for (int j = lane; j < nvec; j += kWarp) {
                         float x[NE], g[NE];
@@ -410,14 +393,22 @@ static __global__ void __launch_bounds__((NW + 2) * kWarp, 1)
                             g[i] = ex2_approx(ee.x);
                             g[i + 1] = ex2_approx(ee.y);
                         }
-                        if (j == jb) patch_component<NE>(g, kb, db);
-                        if (j == jl) patch_component<NE>(g, kl, dl);
+                        // the (at most) two elements that lose something: behind real branches (the exponential inside
+                        // keeps the compiler from turning them into predicated subtractions on every vector)
+                        if (j == jb) patch_component<NE>(g, kb, ex2_approx(c.y));
+                        if (j == jl) patch_component<NE>(g, kl, ex2_approx(c.z));
                         if (SCALED) {
 #pragma unroll
                             for (int i = 0; i < NE; ++i) g[i] *= sc;
                         }
-                        if constexpr (UNALIGNED) store_row_vector<E, NE>(gv, j, g, nvec - 1, head, tail);
-                        else st_stream_u4(gv + j, Elem<E>::pack(g));
+                        st_stream_u4(gv + j, Elem<E>::pack(g));
+                    }
+                    if (UNALIGNED && e_edge >= 0) {
+                        float gval = ex2_approx(fmaf(Elem<E>::to_float(xrow[e_edge]), kLog2e, c.x) + c.w);
+                        if (e_edge == blank) gval -= ex2_approx(c.y);
+                        else if (e_edge == lab) gval -= ex2_approx(c.z);
+                        if (SCALED) gval *= sc;
+                        grow[e_edge] = Elem<E>::from_float(gval);
                     }
                 }
             }

@@ -62,7 +62,8 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 // that a late CTA of the same launch might still touch), then (256 bytes clear of the flags that waiting CTAs poll)
 // the counters of the zero fill (zero_fill.cuh): two of the OWNED protocol, then the two alternating ones of the
 // SHARED protocol
-constexpr int kK2FlagWords = 4;  // per utterance: {phase-A blocks handed out, phase-A blocks done, phase-C blocks handed out, recursion done}
+constexpr int kK2FlagWords = 24;  // per utterance: phase-A block claims [8], phase-C block claims [8], phase-A blocks done
+                                  // by helpers, recursion done (k2_lattice.cuh; 8 = kK2MaxParts)
 __host__ __device__ inline size_t k2_zero_ctr_word(int B) {
     return (2 * kK2FlagWords * static_cast<size_t>(B) + 63) / 64 * 64 + 64;
 }

@@ -101,6 +101,7 @@ int main(int argc, char **argv) {
             printf("(%lld, %lld) ", h[3 + 2 * c] - h[2 + 2 * c], (c + 1 < nch && c < 19 ? h[4 + 2 * c] : h[50]) - h[3 + 2 * c]);
         printf("\n  phase A (own share) %lld cyc, wait for the other parts %lld cyc, both passes done at %lld cyc, coefficient phase %lld cyc\n",
                h[60] - h[0], h[61] - h[60], h[51] - h[0], h[52] - h[51]);
+        printf("  phase A inside (last call of CTA 0): start %lld, loads landed %lld, done %lld cyc after the kernel's start\n", h[55] - h[0], h[56] - h[0], h[57] - h[0]);
         if (a.zero_warps > 0) printf("  zero fill of CTA 0's first warp: from %lld to %lld cyc\n", h[53] - h[0], h[54] - h[0]);
     }
     return 0;
