@@ -125,6 +125,27 @@ inline void release_cost_stage(const CostStage &st) {
     g_cost_stages.push_back(st);
 }
 
+// A side stream for the copy-engine part of an upload (Engine::upload_live_rows): forked off the caller's stream and
+// joined back into it with two events.  One per device and module; the enqueue sequence holds the mutex, so two handles
+// on two threads cannot interleave their records of the shared events.
+struct UploadLane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    bool ok = false;
+};
+static std::mutex g_upload_lane_mutex;
+inline UploadLane &upload_lane(int device) {  // (call with g_upload_lane_mutex held)
+    static UploadLane lanes[64];
+    UploadLane &l = lanes[device & 63];
+    if (!l.ok && l.stream == nullptr) {
+        l.ok = cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) == cudaSuccess &&
+               cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming) == cudaSuccess &&
+               cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming) == cudaSuccess;
+        if (!l.ok) (void)cudaGetLastError();
+    }
+    return l;
+}
+
 // T[] and S[] in one hop: a tiny kernel writes both into a host-mapped staging buffer (one launch + one
 // synchronisation of the legacy stream, ~8 us) instead of two blocking cudaMemcpy calls (~16 us).
 static __global__ void gather_lengths_kernel(const int *__restrict__ T, const int *__restrict__ S, int B,
@@ -417,18 +438,64 @@ class Engine {
         const size_t row_bytes = static_cast<size_t>(V_) * elem_bytes();
         const uintptr_t bits = reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | row_bytes;
         const int grid = dev.sm_count * 8;
+        // The all-live block in the middle of every utterance (plan.cuh: upload_middle_block; packed layout, no band)
+        // goes through the copy engine on a side stream WHILE the kernel brings the ragged frames around it: the copy
+        // engine moves 55.6 GB/s over PCIe against the 51.5 of SM-issued reads (tools/h2d_probe.cu), and the tail of the
+        // upload -- the block is most of an utterance -- runs at its rate.
+        int64_t mid_min_rows = 0;
+        std::unique_lock<std::mutex> lane_lock(g_upload_lane_mutex, std::defer_lock);
+        UploadLane *lane = nullptr;
+        if (upload_copy_min_bytes_ > 0 && alignment_ == nullptr && pad_T_ == 0 && static_cast<int>(T_h_.size()) == B_) {
+            int cur = 0;
+            if (cudaGetDevice(&cur) == cudaSuccess) {
+                lane_lock.lock();
+                lane = &upload_lane(cur);
+                if (!lane->ok) {
+                    lane = nullptr;
+                    lane_lock.unlock();
+                }
+            }
+        }
+        if (lane != nullptr) {
+            mid_min_rows = static_cast<int64_t>((upload_copy_min_bytes_ + row_bytes - 1) / row_bytes);
+            if (cudaEventRecord(lane->fork, stream) != cudaSuccess || cudaStreamWaitEvent(lane->stream, lane->fork, 0) != cudaSuccess)
+                return RNNT_STATUS_EXECUTION_FAILED;
+            int64_t R = 0;
+            bool any = false;
+            for (int b = 0; b < B_; ++b) {
+                const MiddleBlock m = upload_middle_block(T_h_[b], S_h_[b], mid_min_rows);
+                if (m.rows > 0) {
+                    const size_t off = static_cast<size_t>(R + m.first) * row_bytes;
+                    if (cudaMemcpyAsync(static_cast<unsigned char *>(dst) + off, static_cast<const unsigned char *>(host_acts) + off,
+                                        static_cast<size_t>(m.rows) * row_bytes, cudaMemcpyHostToDevice, lane->stream) != cudaSuccess)
+                        return RNNT_STATUS_MEMOPS_FAILED;
+                    any = true;
+                }
+                R += static_cast<int64_t>(T_h_[b]) * (S_h_[b] + 1);
+            }
+            if (!any) mid_min_rows = 0;
+            if (cudaEventRecord(lane->join, lane->stream) != cudaSuccess) return RNNT_STATUS_EXECUTION_FAILED;
+        }
         if ((bits & 15) == 0) {
             upload_live_rows_kernel<uint4><<<grid, kUploadThreads, 0, stream>>>(
-                static_cast<const uint4 *>(src), static_cast<uint4 *>(dst), ws_.rowmeta, shape_.rows, static_cast<int>(row_bytes / 16));
+                static_cast<const uint4 *>(src), static_cast<uint4 *>(dst), ws_.rowmeta, shape_.rows, static_cast<int>(row_bytes / 16),
+                mid_min_rows, ws_.rowutt, ws_.row_start, T_dev_, S_dev_);
         } else if ((bits & 3) == 0) {
             upload_live_rows_kernel<uint32_t><<<grid, kUploadThreads, 0, stream>>>(
-                static_cast<const uint32_t *>(src), static_cast<uint32_t *>(dst), ws_.rowmeta, shape_.rows, static_cast<int>(row_bytes / 4));
+                static_cast<const uint32_t *>(src), static_cast<uint32_t *>(dst), ws_.rowmeta, shape_.rows, static_cast<int>(row_bytes / 4),
+                mid_min_rows, ws_.rowutt, ws_.row_start, T_dev_, S_dev_);
         } else {
             upload_live_rows_kernel<uint16_t><<<grid, kUploadThreads, 0, stream>>>(
-                static_cast<const uint16_t *>(src), static_cast<uint16_t *>(dst), ws_.rowmeta, shape_.rows, static_cast<int>(row_bytes / 2));
+                static_cast<const uint16_t *>(src), static_cast<uint16_t *>(dst), ws_.rowmeta, shape_.rows, static_cast<int>(row_bytes / 2),
+                mid_min_rows, ws_.rowutt, ws_.row_start, T_dev_, S_dev_);
         }
-        return launched();
+        const RNNTStatus kst = launched();
+        if (lane != nullptr && cudaStreamWaitEvent(stream, lane->join, 0) != cudaSuccess) return RNNT_STATUS_EXECUTION_FAILED;
+        return kst;
     }
+    // The smallest all-live middle block (bytes) that goes through the copy engine next to the upload kernel (default
+    // 1 MiB); 0: the kernel brings every live row.
+    void set_upload_copy_engine(int min_bytes) { upload_copy_min_bytes_ = min_bytes < 0 ? kUploadMinCopyBytes : static_cast<size_t>(min_bytes); }
 
     const Shape &shape() const { return shape_; }
     const Workspace &workspace() const { return ws_; }
@@ -1048,6 +1115,8 @@ class Engine {
     int max_shift_ = 0;
     int align_blank_ = 0;
     bool force_generic_ = false;
+    static constexpr size_t kUploadMinCopyBytes = size_t(1) << 20;  // a middle block below 1 MiB stays with the kernel
+    size_t upload_copy_min_bytes_ = kUploadMinCopyBytes;            // 0: no copy-engine part at all
     int k1_warps_ = 24;
     int k1_compact_ = -1;  // -1: automatic (k1_compact()), 0 / 1: forced
     static constexpr int kDynamicFixedPct = 0;  // (0: two fixed tiles per CTA, everything else through the counter)

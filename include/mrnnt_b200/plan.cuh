@@ -284,16 +284,47 @@ static __global__ void __launch_bounds__(256) rowmeta_kernel(const int *__restri
 // c2, ~95 % under c5's alignment band -- are never read by any kernel, so they need not cross the bus.  UNIT is the
 // widest access the row size and the two base addresses allow (16 bytes wherever the streaming kernels apply).
 constexpr int kUploadThreads = 256;
+// The frames of an utterance all of whose states are live when no alignment band is set: row (t, s) is live iff
+// alpha(t-1, s) lies inside the lattice, s <= t and S - s <= T - t (cpu_workspace_manager.h:161-181), for every s in
+// [0, S] iff S <= t <= T - S.  One contiguous block of (T - 2 S + 1)(S + 1) packed rows per utterance: the copy engine
+// takes it (Engine::upload_live_rows), the kernel below the ragged frames before and behind it.  Host and device use
+// this one function, so the two never disagree about who brings a row.
+struct MiddleBlock {
+    int64_t first = 0;  // row index inside the utterance
+    int64_t rows = 0;   // 0: none worth a copy of its own
+};
+__host__ __device__ inline MiddleBlock upload_middle_block(int Tb, int Sb, int64_t min_rows) {
+    MiddleBlock m;
+    const int64_t frames = static_cast<int64_t>(Tb) - 2 * static_cast<int64_t>(Sb) + 1;
+    if (frames <= 0) return m;
+    const int64_t n = frames * (Sb + 1);
+    if (n < min_rows) return m;
+    m.first = static_cast<int64_t>(Sb) * (Sb + 1);
+    m.rows = n;
+    return m;
+}
+// mid_min_rows > 0: the middle blocks of at least that many rows are somebody else's (the copy engine's) to bring.
 template <typename UNIT>
 static __global__ void __launch_bounds__(kUploadThreads) upload_live_rows_kernel(const UNIT *__restrict__ src,
                                                                                  UNIT *__restrict__ dst,
                                                                                  const int *__restrict__ rowmeta,
-                                                                                 int64_t rows, int units_per_row) {
+                                                                                 int64_t rows, int units_per_row,
+                                                                                 int64_t mid_min_rows = 0,
+                                                                                 const int *__restrict__ rowutt = nullptr,
+                                                                                 const int64_t *__restrict__ row_start = nullptr,
+                                                                                 const int *__restrict__ T = nullptr,
+                                                                                 const int *__restrict__ S = nullptr) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(kUploadThreads) + threadIdx.x) >> 5;
     const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * kUploadThreads) >> 5;
     for (int64_t row = warp0; row < rows; row += nwarps) {
         if (__ldg(rowmeta + row) == kRowDead) continue;  // (warp-uniform)
+        if (mid_min_rows > 0) {
+            const int b = __ldg(rowutt + row);
+            const MiddleBlock m = upload_middle_block(__ldg(T + b), __ldg(S + b), mid_min_rows);
+            const int64_t r = row - __ldg(row_start + b);
+            if (r >= m.first && r < m.first + m.rows) continue;
+        }
         const UNIT *s = src + row * units_per_row;
         UNIT *d = dst + row * units_per_row;
         // eight loads in flight per lane (4 KB per warp at 16 bytes), ALL issued before the first store waits for one:

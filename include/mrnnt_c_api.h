@@ -165,7 +165,10 @@ enum {
     MRNNT_OPT_DYNAMIC_TILES = 10,/* the gradient kernel hands its tiles out through a counter instead of round-robin by
                                     CTA index: 1 / 0 forced, -1 automatic; 2..100: through the counter once that
                                     percentage of a CTA's round-robin share has been worked off                  */
-    MRNNT_OPT_LAUNCH_COUNT = 11  /* mrnnt_get_option only: kernel launches this handle has made so far (low 31 bits) */
+    MRNNT_OPT_LAUNCH_COUNT = 11, /* mrnnt_get_option only: kernel launches this handle has made so far (low 31 bits) */
+    MRNNT_OPT_UPLOAD_COPY_ENGINE = 12 /* mrnnt_upload_acts: the all-live block in the middle of an utterance (packed layout,
+                                    no alignment band) goes through the copy engine next to the upload kernel when it has
+                                    at least this many bytes; 0: the kernel brings every live row; -1: default (1 MiB)  */
 };
 RNNTStatus mrnnt_set_option(mrnnt_handle_t h, int option, int value);
 /* What the last call actually did: MRNNT_OPT_K2_ZERO_FILL -> 0, 1..4 or 32 as above; MRNNT_OPT_LAUNCH_COUNT.  Other

@@ -273,6 +273,9 @@ RNNTStatus mrnnt_set_option(mrnnt_handle_t h, int option, int value) {
         case MRNNT_OPT_DYNAMIC_TILES:
             h->manager.engine().set_dynamic_tiles(value);
             return RNNT_STATUS_SUCCESS;
+        case MRNNT_OPT_UPLOAD_COPY_ENGINE:
+            h->manager.engine().set_upload_copy_engine(value);
+            return RNNT_STATUS_SUCCESS;
         default:
             return RNNT_STATUS_INVALID_VALUE;
     }

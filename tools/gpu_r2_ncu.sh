@@ -11,5 +11,9 @@ for wl in ${1:-c2}; do
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k1_lse_tma|k2_lattice|k3_grad_tma' --launch-skip 9 \
       --launch-count 3 -o gpurun_out/r2_full_$wl python bench.py $ARGS > gpurun_out/r2_ncu_f_$wl.log 2>&1
   echo "ncu full $wl rc=$?"
+  # the summary is made on the box (gpurun_out/ travels back only below 64 MiB in all); the capture itself is kept for c2 only
+  python tools/ncu_summary.py gpurun_out/r2_full_$wl.ncu-rep > gpurun_out/r2_ncu_full_$wl.txt 2>&1
+  python tools/ncu_launch_summary.py gpurun_out/r2_launches_$wl.csv > gpurun_out/r2_ncu_launches_${wl}_summary.txt 2>&1
+  [ "$wl" = "c2" ] || rm -f gpurun_out/r2_full_$wl.ncu-rep
 done
 ls -la gpurun_out/ | grep r2_ | tail -20

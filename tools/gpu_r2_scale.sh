@@ -16,6 +16,11 @@ for part in lpt contiguous; do
   [ "$N" = "1" ] && break
 done
 timeout 600 $RUN bench.py --gpus $N --steps 100 --warmup 5 --no-cpu-baseline > gpurun_out/r2_c2_weak_n$N.json 2> gpurun_out/r2_c2_weak_n$N.err; echo "c2 weak rc=$?"
+# the other named shapes, the named batch on every GPU (weak): utt/s, GB/s and the roofline fraction per N
+for wl in c3 c5 c4; do
+  EXTRA=""; [ "$wl" = "c4" ] && [ "$N" != "1" ] && EXTRA="--no-e2e"   # (15.5 GB of pinned host memory per rank)
+  timeout 600 $RUN bench.py --gpus $N --workload $wl --steps 20 --warmup 5 --no-cpu-baseline $EXTRA > gpurun_out/r2_${wl}_weak_n$N.json 2> gpurun_out/r2_${wl}_weak_n$N.err; echo "$wl weak rc=$?"
+done
 if [ "$N" = "2" ]; then
   # the CUDA-IPC boards between two processes (skipped on one GPU), and the NCCL fallback of the step
   timeout 400 python -m pytest tests/test_gpu_peer.py -m gpu -q 2>&1 | tail -3
