@@ -35,5 +35,5 @@ for f in sorted(glob.glob('gpurun_out/r2_c*_n$N.json')):
         print(f, 'unreadable', e); continue
     print(f, 'value', round(d['value']), 'ms', round(d['ms_per_step'], 4), 'blocks', [round(x, 4) for x in d['timing']['ms_per_step_blocks']],
           'shards', (d.get('shards') or {}).get('imbalance_max_over_mean'), 'bit-equal', (d.get('shards') or {}).get('costs_bit_identical_to_the_whole_batch_on_one_gpu'),
-          'e2e', round(d['e2e']['value']), 'host GB/s', round(d['e2e'].get('host_read_GBps_all_ranks', 0), 1), 'coll', d['config']['collective'][:30])
+          'e2e', round((d.get('e2e') or {}).get('value', 0)), 'host GB/s', round((d.get('e2e') or {}).get('host_read_GBps_all_ranks', 0), 1), 'coll', d['config']['collective'][:30])
 PY

@@ -1,0 +1,8 @@
+set -x
+mkdir -p gpurun_out
+{
+./tools/fill_probe 150 40 32 1000
+./tools/fill_probe 400 80 32 1024
+./tools/fill_probe 400 80 8 1024
+} > gpurun_out/r2u_fill_probe.txt 2>&1
+cat gpurun_out/r2u_fill_probe.txt

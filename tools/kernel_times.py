@@ -19,8 +19,14 @@ from monotonic_rnnt_b200 import _lib  # noqa: E402
 
 
 def run(name: str, iters: int, combos, padded: bool = False, bf16: bool = False, compact: int = -1,
-        zeros=(-1,), dyn: int = -1) -> None:
+        zeros=(-1,), dyn: int = -1, shard: str = "", parts: int = 0) -> None:
     wl = mr.synth.workload(name)
+    if shard:   # rank r's utterances of the batch cut over N ranks (LPT, as bench.py --scaling strong does)
+        import dataclasses
+        r, n = (int(x) for x in shard.split("/"))
+        idx = mr.shard.partition_lpt(wl.T, wl.S, n)[r]
+        sh = mr.shard.make_shard_indexed(wl.T, wl.S, wl.labels, idx, alignment=wl.alignment)
+        wl = dataclasses.replace(wl, name=f"{wl.name}[{shard}]", B=len(idx), T=sh.T, S=sh.S, labels=sh.labels, alignment=sh.alignment)
     dev = torch.device("cuda", 0)
     lib = _lib.load()
     if padded:   # the joint network's own [B, T_max, S_max+1, V] tensor; the padding holds ordinary numbers too
@@ -44,6 +50,7 @@ def run(name: str, iters: int, combos, padded: bool = False, bf16: bool = False,
     h.set_option(_lib.OPT_TIMING, 1)
     h.set_option(_lib.OPT_K1_COMPACT, compact)
     h.set_option(_lib.OPT_DYNAMIC_TILES, dyn)
+    h.set_option(_lib.OPT_K2_PARTS, parts)
     costs = torch.empty(wl.B, dtype=torch.float32).pin_memory()
     n4 = wl.elements * (2 if bf16 else 4)
     for k1w, k3w, zf in [(a, b, z) for a, b in combos for z in zeros]:
@@ -87,8 +94,10 @@ if __name__ == "__main__":
     ap.add_argument("--padded", action="store_true", help="feed the padded [B,T,S+1,V] tensor instead of packed rows")
     ap.add_argument("--dyn", default="-1", help="comma list of MRNNT_OPT_DYNAMIC_TILES values (0 / 1, -1 automatic)")
     ap.add_argument("--zero", default="-1", help="comma list of MRNNT_OPT_K2_ZERO_FILL values to compare")
+    ap.add_argument("--shard", default="", help="r/N: rank r's utterances of the batch cut over N ranks")
+    ap.add_argument("--parts", type=int, default=0, help="MRNNT_OPT_K2_PARTS")
     a = ap.parse_args()
     combos = [tuple(int(x) for x in c.split(":")) for c in a.combos.split(",")]
     for name in a.workloads:
         for d in [int(x) for x in a.dyn.split(',')]:
-            run(name, a.iters, combos, a.padded, a.bf16, a.compact, [int(z) for z in a.zero.split(',')], d)
+            run(name, a.iters, combos, a.padded, a.bf16, a.compact, [int(z) for z in a.zero.split(',')], d, a.shard, a.parts)
