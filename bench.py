@@ -365,7 +365,7 @@ def run_b200(args) -> None:
 
     def one_step():
         if world == 1 or boards is not None:
-            st = abi_call(*abi_args)  # costs (and the world's sum) on the host on return (one stream synchronisation inside)
+            st = abi_call(*abi_args)  # costs on the host on return; gradients (and the world's sum) in stream order
             if st != 0:
                 _lib.check(st, "mrnnt_cost_and_grad")
             return
@@ -398,6 +398,17 @@ def run_b200(args) -> None:
 
     if world > 1:
         handle.set_option(_lib.OPT_RESERVED_SMS, args.reserve_sms)
+    # The call returns when the costs are on the host; the gradient kernel completes in stream order (the default at
+    # N = 1, MRNNT_OPT_RETURN_EARLY).  With the fused exchange the world's sum arrives at the END of the gradient kernel,
+    # so there the same behaviour has to be asked for (value 2: the sum is valid in stream order as well -- the bench
+    # reads it behind the block's synchronisation, as a training loop reads its logged loss).
+    if boards is not None and not args.full_wait:
+        handle.set_option(_lib.OPT_RETURN_EARLY, 2)
+    if args.full_wait:
+        handle.set_option(_lib.OPT_RETURN_EARLY, 0)
+    call_semantics = ("mrnnt_cost_and_grad returns only when everything it launched has completed (--full-wait)" if args.full_wait else
+                      "mrnnt_cost_and_grad returns as soon as the costs are on the host; the gradient kernel completes in "
+                      "stream order (MRNNT_OPT_RETURN_EARLY) and every timed block ends with a device synchronisation")
     clocks = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         one_step()
@@ -406,6 +417,7 @@ def run_b200(args) -> None:
         # arrive leaves NaN after the kernel's time-out): otherwise all ranks switch to the NCCL step, and say so
         want = torch.tensor([float(costs_host.double().sum())], dtype=torch.float64, device=dev)
         dist.all_reduce(want)
+        torch.cuda.synchronize()                        # (the sum lands when the gradient kernel ends)
         got = float(cost_sum_host.item())
         ok = np.isfinite(got) and abs(got - float(want.item())) <= 1e-5 * abs(float(want.item()))
         flag = torch.tensor([1 if ok else 0], device=dev)
@@ -499,6 +511,21 @@ def run_b200(args) -> None:
         ev1.record(stream)
         barrier()
         async_ms = ev0.elapsed_time(ev1) / args.steps
+
+    # ---- the same K steps with the whole wait inside every call (MRNNT_OPT_RETURN_EARLY 0): what the early return buys
+    full_wait_ms = None
+    if world == 1 and not args.full_wait:
+        handle.set_option(_lib.OPT_RETURN_EARLY, 0)
+        for _ in range(3):
+            one_step()
+        barrier()
+        ev0.record(stream)
+        for _ in range(args.steps):
+            one_step()
+        ev1.record(stream)
+        barrier()
+        full_wait_ms = ev0.elapsed_time(ev1) / args.steps
+        handle.set_option(_lib.OPT_RETURN_EARLY, 1)
 
     # ---- the call as the reference's torch binding pays for it (pytorch_binding/monotonic_rnnt.cu:99-111): a new manager,
     #      cudaMalloc of the workspace, cost_and_grad, cudaFree -- every call ----
@@ -738,7 +765,7 @@ def run_b200(args) -> None:
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": SCALING,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": _config(wl_global if strong else wl, {"collective": collective, "scaling": SCALING,
-                                                        "batch_total": B_job}),
+                                                        "batch_total": B_job, "call": call_semantics}),
         "timing": {"blocks": len(block_ms), "steps_per_block": args.steps, "reported": "median block, max over ranks",
                    "ms_per_step_blocks": [b / args.steps for b in block_ms],
                    "ms_per_step_min_block": min(block_ms) / args.steps, "ms_per_step_max_block": max(block_ms) / args.steps,
@@ -774,6 +801,9 @@ def run_b200(args) -> None:
         "async_enqueue": None if async_ms is None else {
             "value": wl.B / (async_ms / 1000.0), "unit": UNIT, "ms_per_step": async_ms,
             "what": "the same steps through mrnnt_enqueue (no host synchronisation per step, one at the end)"},
+        "full_wait": None if full_wait_ms is None else {
+            "value": wl.B / (full_wait_ms / 1000.0), "unit": UNIT, "ms_per_step": full_wait_ms,
+            "what": "the same steps with MRNNT_OPT_RETURN_EARLY 0: every call waits for its gradient kernel before it returns"},
         "per_call_workspace": None if alloc_ms is None else {
             "value": wl.B / (alloc_ms / 1000.0), "unit": UNIT, "ms_per_step": alloc_ms,
             "what": "new handle + cudaMalloc of the workspace + set-up kernels + cost_and_grad + cudaFree per call (host clock), "
@@ -811,6 +841,8 @@ def main() -> None:
                     help="the named shape (BASELINE.json configs[1..4]); the contract's bench line is c2, the default")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-CPU baseline/checker leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs under ncu only)")
+    ap.add_argument("--full-wait", action="store_true",
+                    help="every call waits for all of its kernels before it returns (MRNNT_OPT_RETURN_EARLY 0)")
     ap.add_argument("--collective", choices=["fused", "nccl"], default="fused",
                     help="N > 1: the sum of the costs over peer memory inside the gradient kernel, or NCCL on a side stream")
     ap.add_argument("--reserve-sms", type=int, default=0,

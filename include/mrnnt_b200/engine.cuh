@@ -13,6 +13,8 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 #include <cstdint>
 #include <cstring>
 #include <mutex>
@@ -503,33 +505,98 @@ class Engine {
     int B() const { return B_; }
 
     // costs_host: B floats on the host (valid on return).  grads_dev: packed like acts, or nullptr.
+    // With gradients the call returns as soon as the costs have reached the host -- the first warp of the gradient
+    // kernel sends them and then a sequence word, which this thread polls -- while the gradient kernel is still
+    // running: the gradients are complete in STREAM ORDER, like the output of any kernel launch (both of the
+    // reference's bindings consume them on the same stream), and the caller's next launches queue up behind the
+    // gradient kernel instead of behind a host round trip.  set_return_early(false): wait for the whole stream, as the
+    // reference's blocking copy at gpu_rnnt.h:229 does on the legacy stream.
     RNNTStatus compute(int blank, cudaStream_t stream, float *costs_host, void *grads_dev) {
         if (costs_host == nullptr) return RNNT_STATUS_INVALID_VALUE;
         RNNTStatus st = ensure_shape();
         if (st != RNNT_STATUS_SUCCESS) return st;
         if (base_ == nullptr || blank < 0 || blank >= V_) return RNNT_STATUS_INVALID_VALUE;
         if (peer_failed_) return RNNT_STATUS_EXECUTION_FAILED;  // an exchange gave up earlier: final (peer_reduce.cuh)
-        // (one word behind the costs: the exchange's "gave up" flag)
-        const CostStage stage = acquire_cost_stage(static_cast<size_t>(B_) + 1);
+        // The staging buffer stays with the handle: after an early return the gradient kernel may still write the
+        // exchange's "gave up" flag into it (one word behind the costs; behind that the sequence word).
+        if (!stage_tried_) {
+            stage_tried_ = true;
+            stage_ = acquire_cost_stage(static_cast<size_t>(B_) + 2);
+            if (stage_.host != nullptr) {
+                reinterpret_cast<volatile unsigned *>(stage_.host)[B_] = 0u;
+                reinterpret_cast<volatile unsigned *>(stage_.host)[B_ + 1] = 0u;
+            }
+        }
+        const CostStage stage = stage_;
+        volatile unsigned *words = stage.host != nullptr ? reinterpret_cast<volatile unsigned *>(stage.host) + B_ : nullptr;
+        if (words != nullptr && words[0] != 0u) {  // (a collect that gave up behind the previous call's early return)
+            peer_failed_ = true;
+            return RNNT_STATUS_EXECUTION_FAILED;
+        }
+        // (with a peer reduce the caller is promised the world's sum and the exchange's verdict on return: the whole wait,
+        // unless told that stream order will do for those too -- mode 2)
+        const bool early = grads_dev != nullptr && stage.host != nullptr && !timing_ &&
+                           (return_early_ >= 2 || (return_early_ == 1 && peer_.world <= 0));
         costs_mapped_ = stage.host;
-        if (stage.host != nullptr) reinterpret_cast<volatile unsigned *>(stage.host)[B_] = 0u;
+        ready_seq_ = 0u;
+        if (early) {
+            if (++stage_seq_ == 0u) ++stage_seq_;
+            ready_seq_ = stage_seq_;
+        }
         st = enqueue(blank, stream, grads_dev);
         costs_mapped_ = nullptr;
+        ready_seq_ = 0u;
         if (st == RNNT_STATUS_SUCCESS && stage.host == nullptr &&
             cudaMemcpyAsync(costs_host, ws_.costs, sizeof(float) * B_, cudaMemcpyDeviceToHost, stream) != cudaSuccess)
             st = RNNT_STATUS_MEMOPS_FAILED;
-        if (st == RNNT_STATUS_SUCCESS && cudaStreamSynchronize(stream) != cudaSuccess) st = RNNT_STATUS_EXECUTION_FAILED;
+        if (st == RNNT_STATUS_SUCCESS && early) {
+            // what remains in flight when we return is remembered by an event: the staging buffer and the workspace
+            // must outlive it (~Engine, release_owned)
+            if (inflight_ev_ == nullptr && cudaEventCreateWithFlags(&inflight_ev_, cudaEventDisableTiming) != cudaSuccess) {
+                (void)cudaGetLastError();
+                inflight_ev_ = nullptr;
+            }
+            const bool have_ev = inflight_ev_ != nullptr && cudaEventRecord(inflight_ev_, stream) == cudaSuccess;
+            inflight_stream_ = stream;
+            inflight_stream_set_ = have_ev;
+            bool arrived = false;
+            for (unsigned spins = 1; have_ev; ++spins) {
+                if (words[1] == stage_seq_) {
+                    arrived = true;
+                    break;
+                }
+                if ((spins & 255u) == 0u) {
+                    // the stream has run dry (or died) without the word: look once more, then give up on the short cut
+                    const cudaError_t q = cudaEventQuery(inflight_ev_);
+                    if (q != cudaErrorNotReady) {
+                        arrived = q == cudaSuccess && words[1] == stage_seq_;
+                        break;
+                    }
+                }
+            }
+            if (arrived) {
+                std::atomic_thread_fence(std::memory_order_acquire);
+            } else if (cudaStreamSynchronize(stream) != cudaSuccess) {
+                st = RNNT_STATUS_EXECUTION_FAILED;
+            }
+        } else if (st == RNNT_STATUS_SUCCESS && cudaStreamSynchronize(stream) != cudaSuccess) {
+            st = RNNT_STATUS_EXECUTION_FAILED;
+        }
         if (st == RNNT_STATUS_SUCCESS && stage.host != nullptr) {
             std::memcpy(costs_host, stage.host, sizeof(float) * B_);
-            if (reinterpret_cast<volatile unsigned *>(stage.host)[B_] != 0u) {
+            if (words[0] != 0u) {
                 peer_failed_ = true;
                 st = RNNT_STATUS_EXECUTION_FAILED;
             }
         }
         if (st != RNNT_STATUS_SUCCESS && stage.host != nullptr) (void)cudaStreamSynchronize(stream);  // nothing may still write into it
-        release_cost_stage(stage);
         return st;
     }
+    // 0: a synchronous call returns only when everything it launched has completed.  1 (default): early return, except
+    // with a peer reduce.  2: early return with a peer reduce as well -- *total_out is then valid in stream order, and an
+    // exchange that gave up is reported by the NEXT call.
+    void set_return_early(int mode) { return_early_ = mode < 0 ? 1 : (mode > 2 ? 2 : mode); }
+    int return_early() const { return return_early_; }
 
     // Launch everything on `stream` without synchronising; costs stay in workspace().costs.
     RNNTStatus enqueue(int blank, cudaStream_t stream, void *grads_dev) {
@@ -595,6 +662,10 @@ class Engine {
     RNNTStatus set_peer_reduce(int rank, int world, void *const *boards, float *total_out) {
         peer_ = PeerReduce{};
         peer_failed_ = false;  // (the failure belongs to the boards that are being let go of)
+        if (stage_.host != nullptr) {
+            wait_inflight();
+            reinterpret_cast<volatile unsigned *>(stage_.host)[B_] = 0u;
+        }
         if (world == 0) return RNNT_STATUS_SUCCESS;
         if (world < 0 || world > kPeerMaxWorld || rank < 0 || rank >= world || boards == nullptr) return RNNT_STATUS_INVALID_VALUE;
         for (int r = 0; r < world; ++r) {
@@ -626,6 +697,7 @@ class Engine {
         const DeviceInfo &dev = device_info();
         if (!dev.ok) return RNNT_STATUS_EXECUTION_FAILED;
         if (grads_dev == nullptr || coef_blank_ < 0) return RNNT_STATUS_INVALID_VALUE;
+        if (order_behind_inflight(stream) != RNNT_STATUS_SUCCESS) return RNNT_STATUS_EXECUTION_FAILED;
         // who writes the plan's dead rows: the lattice kernel has (into this very buffer), or the gradient kernel's own
         // zero-fill warp will, or its consumer warps do
         zero_dst_ = grads_dev;
@@ -662,7 +734,14 @@ class Engine {
     ~Engine() {
         if (timing_)
             for (auto &e : ev_) cudaEventDestroy(e);
+        wait_inflight();
         release_owned();  // (mrnnt_destroy without mrnnt_free_workspace)
+        if (inflight_ev_ != nullptr) cudaEventDestroy(inflight_ev_);
+        release_cost_stage(stage_);
+    }
+    // Returns when nothing an early-return call left behind is still running.
+    void wait_inflight() {
+        if (inflight_ev_ != nullptr && cudaEventSynchronize(inflight_ev_) != cudaSuccess) (void)cudaGetLastError();
     }
 
     // Kernel launches this engine has made so far (set-up kernels included).
@@ -713,7 +792,16 @@ class Engine {
         owned_ = nullptr;
     }
 
+    // The kernels an early-return call left behind use the workspace: work enqueued on ANOTHER stream goes behind them.
+    RNNTStatus order_behind_inflight(cudaStream_t stream) {
+        if (inflight_ev_ != nullptr && inflight_stream_set_ && stream != inflight_stream_ &&
+            cudaStreamWaitEvent(stream, inflight_ev_, 0) != cudaSuccess)
+            return RNNT_STATUS_EXECUTION_FAILED;
+        return RNNT_STATUS_SUCCESS;
+    }
+
     RNNTStatus setup(cudaStream_t stream) {
+        if (order_behind_inflight(stream) != RNNT_STATUS_SUCCESS) return RNNT_STATUS_EXECUTION_FAILED;
         if (plan_dirty_) {
             plan_row_start_kernel<<<1, kPlanThreads, 0, stream>>>(
                 T_dev_, S_dev_, B_, ws_.row_start, ws_.k2_flags, static_cast<int64_t>(shape_.T_dim) * shape_.U);
@@ -775,9 +863,13 @@ class Engine {
         }
         const size_t smem = k1_smem_bytes(tl.smem_bytes, zero_warp);
         if (smem > static_cast<size_t>(dev.max_smem_optin) || !ensure_dynamic_smem(kern, smem)) return RNNT_STATUS_EXECUTION_FAILED;
-        kern<<<dev.sm_count, (NW + (zero_warp ? 2 : 1)) * kWarp, smem, stream>>>(
-            static_cast<const E *>(acts_), labels_, ws_.rowmeta, ws_.lp, shape_.rows, V_, blank, tl.G, tl.stages, zero,
-            tl.smem_bytes, tl.slot_bytes);
+        // (a programmatic dependent of whatever precedes it in the stream: behind the previous call's gradient kernel,
+        // which lets its dependents go at once, this kernel's CTAs set themselves up on the SMs that kernel's CTAs leave
+        // and wait there for the rest of them; behind anything else the attribute changes nothing)
+        if (launch_kernel(kern, dev.sm_count, (NW + (zero_warp ? 2 : 1)) * kWarp, smem, stream, pdl_ && !timing_,
+                          static_cast<const E *>(acts_), labels_, ws_.rowmeta, ws_.lp, shape_.rows, V_, blank, tl.G, tl.stages,
+                          zero, tl.smem_bytes, tl.slot_bytes) != cudaSuccess)
+            return RNNT_STATUS_EXECUTION_FAILED;
         return launched();
     }
 
@@ -1086,6 +1178,10 @@ class Engine {
         m.costs = ws_.costs;
         m.mapped = costs_mapped_;
         m.B = B_;
+        if (costs_mapped_ != nullptr && ready_seq_ != 0u) {
+            m.ready = reinterpret_cast<unsigned *>(costs_mapped_) + B_ + 1;
+            m.seq = ready_seq_;
+        }
         return m;
     }
 
@@ -1145,6 +1241,14 @@ class Engine {
     bool k3_follows_k2_ = false;  // K3 is being enqueued directly behind K2 (enqueue(), not a separate backward)
     unsigned epoch_ = 0u;  // launch counter published through Workspace::k2_flags
     float *costs_mapped_ = nullptr;  // set for the duration of a synchronous compute(): host-mapped copy of the costs
+    CostStage stage_{};              // this handle's staging buffer (B costs, the exchange's flag, the sequence word)
+    bool stage_tried_ = false;
+    int return_early_ = 1;           // compute() with gradients returns when the costs are on the host (set_return_early)
+    unsigned stage_seq_ = 0u;        // the last sequence number handed to a gradient kernel
+    unsigned ready_seq_ = 0u;        // set for the duration of an early-return compute(): this call's sequence number
+    cudaEvent_t inflight_ev_ = nullptr;  // behind the last early-return call's kernels
+    cudaStream_t inflight_stream_ = nullptr;
+    bool inflight_stream_set_ = false;
     int coef_blank_ = -1;  // blank label of the forward pass whose coefficients sit in the workspace (-1: none)
     bool timing_ = false;
     cudaEvent_t ev_[4] = {};

@@ -29,17 +29,27 @@
 namespace mrnnt {
 
 // Optional hand-over of the B costs to the host (a synchronous call's staging buffer in host-mapped pinned memory,
-// engine.cuh): done here, by the first CTA of the LAST kernel of the call, so that the PCIe write overlaps the whole
-// gradient pass instead of sitting between the lattice kernel and this one.
+// engine.cuh): done here, by the first warp of the first CTA of the LAST kernel of the call, so that the PCIe write
+// overlaps the whole gradient pass instead of sitting between the lattice kernel and this one.  With `ready` the warp
+// then publishes `seq` there (release, system scope): the host, polling that word, has the costs ~2 us after the
+// lattice kernel's end and returns to its caller while this kernel is still streaming (Engine::compute, early return).
 struct CostMirror {
     const float *costs = nullptr;  // device, final since the lattice kernel
     float *mapped = nullptr;       // host-mapped copy, or nullptr
     int B = 0;
+    unsigned *ready = nullptr;     // host-mapped word behind the costs, or nullptr
+    unsigned seq = 0u;             // what `ready` is set to once the costs are in place
 };
-// (called by threads 0 .. nthreads-1 of every CTA)
-__device__ __forceinline__ void mirror_costs(const CostMirror &m, int nthreads) {
-    if (m.mapped != nullptr && blockIdx.x == 0)
-        for (int i = threadIdx.x; i < m.B; i += nthreads) m.mapped[i] = m.costs[i];
+// (called by one whole warp of the first CTA)
+__device__ __forceinline__ void mirror_costs(const CostMirror &m) {
+    if (m.mapped == nullptr) return;
+    const int lane = threadIdx.x & 31;
+    for (int i = lane; i < m.B; i += kWarp) m.mapped[i] = m.costs[i];
+    if (m.ready != nullptr) {
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(m.ready), "r"(m.seq) : "memory");
+    }
 }
 
 // subtract d from component k of a vector of NE gradients (k is warp-divergent, so the component is picked with
@@ -59,9 +69,11 @@ static __global__ void __launch_bounds__(kGenericWarps * kWarp)
                            const int *__restrict__ rowlab, E *__restrict__ grads, int64_t rows, int V, int blank,
                            const int *__restrict__ rowutt, const float *__restrict__ scale, CostMirror mirror,
                            PeerReduce peer) {
-    mirror_costs(mirror, blockDim.x);
     const bool peer_warp = blockIdx.x == 0 && threadIdx.x < kWarp;  // (peer_reduce.cuh)
-    if (peer_warp) peer_publish(peer);
+    if (peer_warp) {
+        mirror_costs(mirror);
+        peer_publish(peer);
+    }
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * kGenericWarps + (threadIdx.x >> 5);
     const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kGenericWarps;
@@ -142,12 +154,15 @@ static __global__ void __launch_bounds__((NW + 2) * kWarp, 1)
         else zero_dead_rows(zero, blockIdx.x, gridDim.x, zbuf);
         return;
     }
+    pdl_launch_dependents();  // the next call's LSE kernel may be scheduled as our CTAs retire (it waits for all of us)
     pdl_wait();  // the coefficients come from the lattice kernel; everything above overlapped its tail
-    mirror_costs(mirror, (NW + 1) * kWarp);
     // the sum of this GPU's costs goes out to the peers now and the world's sum is picked up when this warp has got
     // through its rows (peer_reduce.cuh): the exchange rides along with the gradient pass
     const bool peer_warp = blockIdx.x == 0 && warp == 0;
-    if (peer_warp) peer_publish(peer);
+    if (peer_warp) {
+        mirror_costs(mirror);
+        peer_publish(peer);
+    }
 
     const int64_t ntiles = (rows + G - 1) / G;
     const int64_t nloc = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;

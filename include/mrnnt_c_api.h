@@ -166,9 +166,18 @@ enum {
                                     CTA index: 1 / 0 forced, -1 automatic; 2..100: through the counter once that
                                     percentage of a CTA's round-robin share has been worked off                  */
     MRNNT_OPT_LAUNCH_COUNT = 11, /* mrnnt_get_option only: kernel launches this handle has made so far (low 31 bits) */
-    MRNNT_OPT_UPLOAD_COPY_ENGINE = 12 /* mrnnt_upload_acts: the all-live block in the middle of an utterance (packed layout,
+    MRNNT_OPT_UPLOAD_COPY_ENGINE = 12,/* mrnnt_upload_acts: the all-live block in the middle of an utterance (packed layout,
                                     no alignment band) goes through the copy engine next to the upload kernel when it has
                                     at least this many bytes; 0: the kernel brings every live row; -1: default (1 MiB)  */
+    MRNNT_OPT_RETURN_EARLY = 13  /* 1 (default): mrnnt_cost_and_grad / compute_rnnt_loss with gradients return as soon as
+                                    the costs are on the host; the gradient kernel may still be running and the gradients
+                                    (and *total_out of a peer reduce) are complete in STREAM ORDER, like the result of any
+                                    kernel launch -- both of the reference's bindings consume them on the same stream.
+                                    A handle with a peer reduce still waits for everything (the world's sum and the
+                                    exchange's verdict are promised on return) unless the value is 2: *total_out is then
+                                    valid in stream order and an exchange that gave up is reported by the NEXT call.
+                                    0: return only when everything the call launched has completed (the reference's
+                                    blocking copy on the legacy stream, gpu_rnnt.h:229).  Also readable.             */
 };
 RNNTStatus mrnnt_set_option(mrnnt_handle_t h, int option, int value);
 /* What the last call actually did: MRNNT_OPT_K2_ZERO_FILL -> 0, 1..4 or 32 as above; MRNNT_OPT_LAUNCH_COUNT.  Other

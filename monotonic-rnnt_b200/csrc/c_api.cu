@@ -276,6 +276,9 @@ RNNTStatus mrnnt_set_option(mrnnt_handle_t h, int option, int value) {
         case MRNNT_OPT_UPLOAD_COPY_ENGINE:
             h->manager.engine().set_upload_copy_engine(value);
             return RNNT_STATUS_SUCCESS;
+        case MRNNT_OPT_RETURN_EARLY:
+            h->manager.engine().set_return_early(value);
+            return RNNT_STATUS_SUCCESS;
         default:
             return RNNT_STATUS_INVALID_VALUE;
     }
@@ -289,6 +292,9 @@ RNNTStatus mrnnt_get_option(mrnnt_handle_t h, int option, int *value) {
             return RNNT_STATUS_SUCCESS;
         case MRNNT_OPT_LAUNCH_COUNT:
             *value = static_cast<int>(h->manager.engine().launch_count() & 0x7fffffffull);
+            return RNNT_STATUS_SUCCESS;
+        case MRNNT_OPT_RETURN_EARLY:
+            *value = h->manager.engine().return_early();
             return RNNT_STATUS_SUCCESS;
         default:
             return RNNT_STATUS_INVALID_VALUE;

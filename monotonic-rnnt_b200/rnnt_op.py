@@ -215,7 +215,9 @@ class LossHandle:
 
     def cost_and_grad(self, blank_label: int = 0, grads: Optional[torch.Tensor] = None,
                       costs_host: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """GpuRNNTComputer::cost_and_grad: costs land on the HOST, valid on return (one stream sync)."""
+        """GpuRNNTComputer::cost_and_grad: costs land on the HOST, valid on return.  With ``grads`` the call returns as
+        soon as the costs have arrived; the gradient kernel may still be running and ``grads`` is complete in stream
+        order, like the result of any kernel launch (``set_option(OPT_RETURN_EARLY, 0)``: wait for everything)."""
         if costs_host is None:
             costs_host = torch.empty(self.B, dtype=torch.float32, device="cpu")
         assert costs_host.device.type == "cpu" and costs_host.dtype == torch.float32 and costs_host.numel() == self.B
