@@ -703,9 +703,19 @@ class Engine {
         zero_dst_ = grads_dev;
         k3_zero_warp_ = dead_rows_zeroed_ != grads_dev && k3_zero_warp_wanted() && zero_fill_possible();
         k3_write_dead_ = dead_rows_zeroed_ != grads_dev && !k3_zero_warp_;
+        // the lattice kernel's fill stopped at a unit: this kernel's zero-fill warp takes the units behind it
+        k3_fill_unit_begin_ = 0;
+        if (dead_rows_zeroed_ == grads_dev && k2_fill_unit_end_ >= 0 && zero_fill_possible()) {
+            k3_zero_warp_ = true;
+            k3_fill_unit_begin_ = k2_fill_unit_end_;
+        }
+        k2_fill_unit_end_ = -1;
         dead_rows_zeroed_ = nullptr;  // (good for the one backward pass that follows directly)
         mark(2, stream);
-        if (k3_zero_warp_) last_k2_zero_warps_ = 32;
+        if (k3_zero_warp_ && k3_fill_unit_begin_ == 0) last_k2_zero_warps_ = 32;
+        last_k2_fill_share_ = 100;
+        if (k3_fill_unit_begin_ > 0)
+            last_k2_fill_share_ = static_cast<int>(k3_fill_unit_begin_ * 100 / ((shape_.rows + kWarp - 1) / kWarp));
         const RNNTStatus st = launch_k3(coef_blank_, stream, dev, grads_dev, scale_dev);
         mark(3, stream);
         return st;
@@ -754,7 +764,10 @@ class Engine {
     // SMs the gradient kernel leaves free for a concurrent collective (0: none).
     void set_reserved_sms(int n) { reserved_sms_ = n < 0 ? 0 : n; }
     int last_k2_zero_warps() const { return last_k2_zero_warps_; }
+    int last_k2_fill_share() const { return last_k2_fill_share_; }  // percent of the fill's units the lattice kernel took
     void set_k2_zero_fill(int warps) { k2_zero_warps_ = warps; }
+    // percent of the zero fill that stays in the lattice kernel (-1: automatic); see k2_fill_share()
+    void set_k2_fill_share(int pct) { k2_fill_share_ = pct; }
     // -1 automatic, 0 off, 1 on; 2..100: on, with that percentage of a CTA's share fixed before the counter takes over
     void set_dynamic_tiles(int mode) {
         dynamic_tiles_ = mode < 0 ? -1 : (mode != 0);
@@ -996,6 +1009,8 @@ class Engine {
         a.rowmeta = ws_.rowmeta;
         a.row_bytes = static_cast<unsigned>(static_cast<size_t>(V_) * elem_bytes());
         a.zero_warps = 0;
+        a.zero_unit_end = -1;
+        k2_fill_unit_end_ = -1;
         a.zero_clear = shared_fill_clear_;
         last_k2_zero_warps_ = 0;
         a.rows = shape_.rows;
@@ -1018,7 +1033,14 @@ class Engine {
                 a.zero_warps = zw;
                 last_k2_zero_warps_ = zw;
                 dead_rows_zeroed_ = zero_dst_;
+                // the front of the batch here, the rest by the gradient kernel's zero-fill warp (k2_fill_share)
+                const int share = k2_fill_share();
+                if (share < 100) {
+                    const int64_t nunits = (shape_.rows + kWarp - 1) / kWarp;
+                    k2_fill_unit_end_ = nunits * share / 100;
+                }
             }
+            a.zero_unit_end = k2_fill_unit_end_;
             return K == 1   ? launch_k2_warp<1>(a, stream, dev)
                    : K == 2 ? launch_k2_warp<2>(a, stream, dev)
                             : launch_k2_warp<4>(a, stream, dev);
@@ -1078,6 +1100,20 @@ class Engine {
         return chain_us >= 0.025 * stream_us;
     }
 
+    // How much of the zero fill the lattice kernel takes (percent of the batch's units of 32 rows, from the front, 1..100);
+    // the gradient kernel's zero-fill warp writes the rest next to its consumers, starting -- SM by SM, as the lattice
+    // kernel's CTAs leave -- before it waits for the lattice kernel.  The idea: the lattice kernel ends when its fill does
+    // (c2: ~50 us) although its recursions and coefficient phase are over after 26.  Measured (tools/share_sweep.py, the
+    // whole call in the stream): it LOSES wherever the gradient kernel is the long pole -- c2 321.7 us at 100 %, 327.8 at
+    // 90 %, 343.6 at 80 %, 365.5 at 60 %; c3 2113 -> 2146 at 70 %; a quarter of c3 565 -> 591 at 80 % -- one warp per SM
+    // next to 24 consumer warps writes its zeros far more slowly than the lattice kernel's idle SMs do, and the gradient
+    // kernel cannot end before it has.  Only an eighth of c3 (8 utterances of T <= 400: the recursions are 20 % of the call)
+    // gains, 311.3 -> 306.2 us at 35 %.  Hence 100 unless asked otherwise (MRNNT_OPT_K2_FILL_SHARE).
+    int k2_fill_share() const {
+        if (k2_fill_share_ >= 0) return k2_fill_share_ > 100 ? 100 : (k2_fill_share_ < 1 ? 1 : k2_fill_share_);
+        return 100;
+    }
+
     // (dead tiles are skipped under the same conditions as in K1, and only when nobody has to zero them here)
     int k3_flags(const StreamTiling &tl) const {
         int dyn = 0;
@@ -1111,6 +1147,12 @@ class Engine {
         if (zero_warp) {
             zero = zero_fill_args(grads, shared_fill_ctr_ != nullptr ? shared_fill_ctr_ : ws_.k2_flags + k2_zero_ctr_word(B_));
             if (shared_fill_ctr_ != nullptr) flags |= kK3ZeroShared;
+            if (k3_fill_unit_begin_ > 0) {
+                // (behind the lattice kernel's fill, which may still be running when this kernel's warps start: a
+                // counter pair of its own)
+                zero.unit_begin = k3_fill_unit_begin_;
+                zero.ctr = ws_.k2_flags + k2_zero_ctr_word(B_) + 4;
+            }
         }
         const size_t smem = k3_smem_bytes(tl.smem_bytes, zero_warp);
         if (smem > static_cast<size_t>(dev.max_smem_optin) || !ensure_dynamic_smem(kern, smem)) return RNNT_STATUS_EXECUTION_FAILED;
@@ -1234,6 +1276,10 @@ class Engine {
     unsigned shared_seq_ = 0u;
     int last_k2_zero_warps_ = 0;        // what the last lattice launch ran with
     int k2_zero_warps_ = -1;            // warps per lattice CTA for the zero fill: -1 automatic, 0 off
+    int last_k2_fill_share_ = 100;
+    int k2_fill_share_ = -1;            // percent of the fill's units the lattice kernel takes: -1 automatic
+    int64_t k2_fill_unit_end_ = -1;     // where the last lattice kernel's fill stops (-1: it takes everything)
+    int64_t k3_fill_unit_begin_ = 0;    // ... and where the gradient kernel's zero-fill warp therefore starts
     PeerReduce peer_{};           // set_peer_reduce(): world > 0 when on; epoch = the last one used
     unsigned long long peer_timeout_ns_ = kPeerDefaultTimeoutNs;
     bool peer_failed_ = false;    // a collect of this handle gave up: every later synchronous call fails

@@ -107,6 +107,8 @@ struct K2Args {
     const int *rowmeta;       // [rows]
     unsigned row_bytes;       // V * sizeof(element), a multiple of 16
     int zero_warps;           // 0: off
+    int64_t zero_unit_end;    // this kernel's fill covers the units (of 32 rows) before this one (< 0: all of them); the
+                              // gradient kernel's zero-fill warp takes the rest
     int64_t rows;             // rows of the whole batch (= row_start[B])
     int B;                    // utterances; flags[k2_zero_ctr_word(B)...]: the zero fill's two counters
     unsigned *zero_clear;     // SHARED zero fill: the counter of the NEXT call, cleared here (nullptr: none)
@@ -622,6 +624,8 @@ __device__ __forceinline__ void k2_zero_dead_rows(const K2Args &a, int fw, int n
     z.rows = a.rows;
     z.row_bytes = a.row_bytes;
     z.ctr = a.flags + k2_zero_ctr_word(a.B);
+    z.unit_begin = 0;
+    z.unit_end = a.zero_unit_end;
     zero_dead_rows(z, fw, nfw, zbuf);
 }
 

@@ -21,6 +21,9 @@ struct ZeroFill {
     int64_t rows;         // rows of the whole batch
     unsigned row_bytes;   // V * sizeof(element), a multiple of 4
     unsigned *ctr;        // the hand-out counter (OWNED: {units handed out, warps finished}, zero between launches)
+    int64_t unit_begin = 0;   // the units (of 32 rows) this fill is responsible for: [unit_begin, unit_end);
+    int64_t unit_end = -1;    // unit_end < 0: up to the last one.  (The lattice kernel's fill takes the front of the
+                              // batch, the gradient kernel's zero-fill warp the rest: Engine::k2_fill_share.)
 };
 
 __device__ __forceinline__ void bulk_s2g(void *gdst, const void *ssrc, uint32_t bytes) {
@@ -49,7 +52,9 @@ __device__ __forceinline__ void zero_dead_rows_impl(const ZeroFill &a, int fw, i
     const int64_t rows = a.rows;
     const int *meta = a.rowmeta;
     unsigned *ctr = a.ctr;
-    const int64_t nunits = (rows + kWarp - 1) / kWarp;
+    const int64_t all_units = (rows + kWarp - 1) / kWarp;
+    const int64_t nunits = a.unit_end < 0 || a.unit_end > all_units ? all_units : a.unit_end;  // (one past the last unit)
+    const int64_t ubase = a.unit_begin;
     constexpr unsigned kNoUnit = 0xffffffffu;
     bool stopped = false;
     auto grab = [&]() {  // (the value is only looked at two units later)
@@ -58,7 +63,8 @@ __device__ __forceinline__ void zero_dead_rows_impl(const ZeroFill &a, int fw, i
     };
     auto unit_of = [&](unsigned raw) {
         const unsigned v = __shfl_sync(0xffffffffu, raw, 0);
-        return (!OWNED && v == kNoUnit) ? nunits : static_cast<int64_t>(v) + (OWNED ? static_cast<int64_t>(kZeroFillDepth) * nfw : 0);
+        return (!OWNED && v == kNoUnit) ? nunits
+                                        : ubase + static_cast<int64_t>(v) + (OWNED ? static_cast<int64_t>(kZeroFillDepth) * nfw : 0);
     };
     auto load = [&](int64_t u) {
         const int64_t r = u * kWarp + lane;
@@ -73,7 +79,7 @@ __device__ __forceinline__ void zero_dead_rows_impl(const ZeroFill &a, int fw, i
     for (int i = 0; i < D; ++i) raw[i] = grab();
     if (OWNED) {
 #pragma unroll
-        for (int i = 0; i < D; ++i) u[i] = fw + static_cast<int64_t>(i) * nfw;
+        for (int i = 0; i < D; ++i) u[i] = ubase + fw + static_cast<int64_t>(i) * nfw;
     } else {
 #pragma unroll
         for (int i = 0; i < D; ++i) u[i] = unit_of(raw[i]);

@@ -169,6 +169,10 @@ enum {
     MRNNT_OPT_UPLOAD_COPY_ENGINE = 12,/* mrnnt_upload_acts: the all-live block in the middle of an utterance (packed layout,
                                     no alignment band) goes through the copy engine next to the upload kernel when it has
                                     at least this many bytes; 0: the kernel brings every live row; -1: default (1 MiB)  */
+    MRNNT_OPT_K2_FILL_SHARE = 14,/* percent (1..100) of the zero fill (units of 32 rows from the front of the batch) the
+                                    lattice kernel writes; the gradient kernel's zero-fill warp writes the rest; -1
+                                    automatic (100: measured, the split loses on every named shape).  mrnnt_get_option:
+                                    what the last call used                                                          */
     MRNNT_OPT_RETURN_EARLY = 13  /* 1 (default): mrnnt_cost_and_grad / compute_rnnt_loss with gradients return as soon as
                                     the costs are on the host; the gradient kernel may still be running and the gradients
                                     (and *total_out of a peer reduce) are complete in STREAM ORDER, like the result of any

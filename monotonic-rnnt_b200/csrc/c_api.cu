@@ -279,6 +279,9 @@ RNNTStatus mrnnt_set_option(mrnnt_handle_t h, int option, int value) {
         case MRNNT_OPT_RETURN_EARLY:
             h->manager.engine().set_return_early(value);
             return RNNT_STATUS_SUCCESS;
+        case MRNNT_OPT_K2_FILL_SHARE:
+            h->manager.engine().set_k2_fill_share(value);
+            return RNNT_STATUS_SUCCESS;
         default:
             return RNNT_STATUS_INVALID_VALUE;
     }
@@ -295,6 +298,9 @@ RNNTStatus mrnnt_get_option(mrnnt_handle_t h, int option, int *value) {
             return RNNT_STATUS_SUCCESS;
         case MRNNT_OPT_RETURN_EARLY:
             *value = h->manager.engine().return_early();
+            return RNNT_STATUS_SUCCESS;
+        case MRNNT_OPT_K2_FILL_SHARE:
+            *value = h->manager.engine().last_k2_fill_share();
             return RNNT_STATUS_SUCCESS;
         default:
             return RNNT_STATUS_INVALID_VALUE;

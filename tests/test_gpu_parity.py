@@ -387,6 +387,58 @@ def test_every_way_of_zeroing_the_dead_rows(gu, mode, restricted, dyn):
     h.close()
 
 
+@pytest.mark.parametrize("dyn", [0, 1], ids=["round_robin", "dynamic_tiles"])
+@pytest.mark.parametrize("share", [1, 37, 64, 99], ids=lambda x: f"k2_takes_{x}pct")
+@pytest.mark.parametrize("restricted", [False, True], ids=["free", "aligned"])
+def test_zero_fill_split_between_lattice_and_gradient_kernel(gu, share, restricted, dyn):
+    """MRNNT_OPT_K2_FILL_SHARE: the lattice kernel's fill writes the zero rows of the first `share` percent of the batch's
+    units of 32 rows, the gradient kernel's zero-fill warp those of the rest (a counter pair of its own: it starts while
+    the lattice kernel's fill may still be running).  Every element written, the bits of the unsplit fill, three calls
+    in a row (both counter pairs come back to zero), and the two halves of a training step on their own."""
+    import monotonic_rnnt_b200 as mr
+    from monotonic_rnnt_b200 import _lib
+    case = fixtures.random_case("fill_split", 777, B=7, V=1000, T_range=(25, 60), S_range=(4, 20), dist="uniform")
+    if restricted:
+        al = fixtures.random_alignment(np.random.default_rng(19), case.T, case.S, case.labels)
+        case = case.with_alignment(al, 2)
+    o64 = _oracle(case, "f64_from_f32")
+    dev = torch.device("cuda", 0)
+    acts = torch.from_numpy(case.acts).to(dev)
+    h = mr.LossHandle(acts, torch.from_numpy(case.labels).to(dev), torch.from_numpy(case.T).to(dev),
+                      torch.from_numpy(case.S).to(dev))
+    if restricted:
+        h.restrict_to_alignment(torch.from_numpy(case.alignment).to(dev), case.max_shift, case.blank)
+    h.set_option(_lib.OPT_K2_ZERO_FILL, 2)
+    h.set_option(_lib.OPT_DYNAMIC_TILES, dyn)
+    h.set_option(_lib.OPT_K2_FILL_SHARE, 100)
+    g0 = torch.full_like(acts, float("nan"))
+    c0 = h.cost_and_grad(case.blank, g0).numpy().copy()
+    assert h.get_option(_lib.OPT_K2_FILL_SHARE) == 100
+    assert not torch.isnan(g0).any()
+    assert np.abs(g0.cpu().numpy() - o64.grads).max() <= GRAD_ATOL
+    h.set_option(_lib.OPT_K2_FILL_SHARE, share)
+    for _ in range(3):
+        g = torch.full_like(acts, float("nan"))
+        costs = h.cost_and_grad(case.blank, g).numpy()
+        assert h.get_option(_lib.OPT_K2_ZERO_FILL) == 2
+        assert abs(h.get_option(_lib.OPT_K2_FILL_SHARE) - share) <= 1
+        np.testing.assert_array_equal(costs, c0)
+        assert torch.equal(g, g0)
+    # the two halves: the forward half is told the buffer, the backward half finishes the fill
+    g = torch.full_like(acts, float("nan"))
+    h.enqueue_forward(case.blank, want_grads=True, grads=g)
+    h.enqueue_backward(g)
+    torch.cuda.synchronize()
+    assert torch.equal(g, g0)
+    # ... and a backward half into ANOTHER buffer than the one the forward half was told: all rows are its own
+    g2 = torch.full_like(acts, float("nan"))
+    h.enqueue_forward(case.blank, want_grads=True, grads=g)
+    h.enqueue_backward(g2)
+    torch.cuda.synchronize()
+    assert torch.equal(g2, g0)
+    h.close()
+
+
 @pytest.mark.parametrize("pct", [60, 100], ids=["60pct_fixed", "all_fixed_but_the_remainder"])
 def test_fixed_share_before_the_tile_counter(gu, pct):
     """MRNNT_OPT_DYNAMIC_TILES = 2..100: that percentage of a CTA's round-robin share of the gradient kernel's tiles is

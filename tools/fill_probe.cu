@@ -50,6 +50,39 @@ __global__ void runlist_fill(unsigned char *dst, const long long *run_off, const
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+// the same run list, but the 8 KB pieces of the compacted byte space are dealt out round-robin to ALL threads of the
+// grid (piece p -> thread p mod nthreads): at any moment the whole GPU writes one compact window of the address space
+__global__ void runlist_interleaved(unsigned char *dst, const long long *run_off, const long long *run_len, const long long *pre,
+                                    int nruns, long long total, int piece_bytes) {
+    extern __shared__ __align__(128) unsigned char zb[];
+    for (int i = threadIdx.x * 16; i < kZeroFillBytes; i += blockDim.x * 16) *reinterpret_cast<uint4 *>(zb + i) = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    // thread order: lane-major across the grid, so that one warp instruction issues 32 adjacent pieces
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    const long long g = (long long)(threadIdx.x >> 5) * gridDim.x * 32 + (long long)blockIdx.x * 32 + (threadIdx.x & 31);
+    const long long pieces = (total + piece_bytes - 1) / piece_bytes;
+    int r = 0;
+    for (long long p = g; p < pieces; p += nthreads) {
+        long long b0 = p * piece_bytes;
+        const long long b1 = std::min<long long>(b0 + piece_bytes, total);
+        int lo = r, hi = nruns - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) / 2;
+            if (pre[mid] + run_len[mid] > b0) hi = mid; else lo = mid + 1;
+        }
+        r = lo;
+        while (b0 < b1) {
+            const long long e = std::min(b1, pre[r] + run_len[r]);
+            bulk_s2g(dst + run_off[r] + (b0 - pre[r]), zb, (uint32_t)(e - b0));
+            b0 = e;
+            if (b0 < b1) ++r;
+        }
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 template <class F> static float time_it(F f, int reps = 10) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     f(); CK(cudaDeviceSynchronize());
@@ -105,7 +138,26 @@ int main(int argc, char **argv) {
         printf("%d warps/CTA: counter %7.1f us (%6.0f GB/s)   counter on a contiguous block %7.1f us   run list, equal bytes %7.1f us (%6.0f GB/s)\n", w,
                a * 1e3, total / a * 1e-6, c * 1e3, r * 1e3, total / r * 1e-6);
     }
+    for (int w : {1, 2, 4}) {
+        for (int pb : {2048, 4096, 8192}) {
+            const float r = time_it([&] { runlist_interleaved<<<148, w * 32, kZeroFillBytes>>>(dst, doff, dlen, dpre, (int)off.size(), total, pb); });
+            printf("%d warps/CTA: run list, interleaved %4d B pieces %7.1f us (%6.0f GB/s)\n", w, pb, r * 1e3, total / r * 1e-6);
+        }
+    }
     CK(cudaDeviceSynchronize());
+    {   // check of the interleaved variant
+        CK(cudaMemset(dst, 0xff, rows * row_bytes));
+        runlist_interleaved<<<148, 64, kZeroFillBytes>>>(dst, doff, dlen, dpre, (int)off.size(), total, 8192);
+        CK(cudaDeviceSynchronize());
+        std::vector<unsigned> hr(V);
+        size_t bad2 = 0;
+        for (size_t i = 0; i < rows; i += 97) {
+            CK(cudaMemcpy(hr.data(), dst + i * row_bytes, row_bytes, cudaMemcpyDeviceToHost));
+            const unsigned want = meta[i] == kRowDead ? 0u : 0xffffffffu;
+            for (int v = 0; v < V; ++v) bad2 += hr[v] != want;
+        }
+        printf("interleaved check: %zu wrong words\n", bad2);
+    }
     // the zeros really are everywhere they belong (run list variant ran last)
     CK(cudaMemset(dst, 0xff, rows * row_bytes));
     runlist_fill<<<148, 64, kZeroFillBytes>>>(dst, doff, dlen, dpre, (int)off.size(), total);
