@@ -703,16 +703,13 @@ class Engine {
         zero_dst_ = grads_dev;
         k3_zero_warp_ = dead_rows_zeroed_ != grads_dev && k3_zero_warp_wanted() && zero_fill_possible();
         k3_write_dead_ = dead_rows_zeroed_ != grads_dev && !k3_zero_warp_;
-        // the lattice kernel's fill stopped at a unit: this kernel's zero-fill warp takes the units behind it
+        // the lattice kernel's fill stopped at a unit: this kernel's consumer warps write the dead rows behind it
         k3_fill_unit_begin_ = 0;
-        if (dead_rows_zeroed_ == grads_dev && k2_fill_unit_end_ >= 0 && zero_fill_possible()) {
-            k3_zero_warp_ = true;
-            k3_fill_unit_begin_ = k2_fill_unit_end_;
-        }
+        if (dead_rows_zeroed_ == grads_dev && k2_fill_unit_end_ >= 0) k3_fill_unit_begin_ = k2_fill_unit_end_;
         k2_fill_unit_end_ = -1;
         dead_rows_zeroed_ = nullptr;  // (good for the one backward pass that follows directly)
         mark(2, stream);
-        if (k3_zero_warp_ && k3_fill_unit_begin_ == 0) last_k2_zero_warps_ = 32;
+        if (k3_zero_warp_) last_k2_zero_warps_ = 32;
         last_k2_fill_share_ = 100;
         if (k3_fill_unit_begin_ > 0)
             last_k2_fill_share_ = static_cast<int>(k3_fill_unit_begin_ * 100 / ((shape_.rows + kWarp - 1) / kWarp));
@@ -1101,14 +1098,18 @@ class Engine {
     }
 
     // How much of the zero fill the lattice kernel takes (percent of the batch's units of 32 rows, from the front, 1..100);
-    // the gradient kernel's zero-fill warp writes the rest next to its consumers, starting -- SM by SM, as the lattice
-    // kernel's CTAs leave -- before it waits for the lattice kernel.  The idea: the lattice kernel ends when its fill does
-    // (c2: ~50 us) although its recursions and coefficient phase are over after 26.  Measured (tools/share_sweep.py, the
-    // whole call in the stream): it LOSES wherever the gradient kernel is the long pole -- c2 321.7 us at 100 %, 327.8 at
-    // 90 %, 343.6 at 80 %, 365.5 at 60 %; c3 2113 -> 2146 at 70 %; a quarter of c3 565 -> 591 at 80 % -- one warp per SM
-    // next to 24 consumer warps writes its zeros far more slowly than the lattice kernel's idle SMs do, and the gradient
-    // kernel cannot end before it has.  Only an eighth of c3 (8 utterances of T <= 400: the recursions are 20 % of the call)
-    // gains, 311.3 -> 306.2 us at 35 %.  Hence 100 unless asked otherwise (MRNNT_OPT_K2_FILL_SHARE).
+    // the gradient kernel writes the dead rows behind that itself.  The idea: the lattice kernel alone ends when its fill
+    // does (c2: ~50 us) although its recursions and coefficient phase are over after 26, so a fill that ends with the
+    // phases might let the gradient kernel start earlier than the rest of the zeros costs it.  Measured
+    // (tools/share_sweep.py, the whole call in the stream), two ways of writing the rest:
+    //  * the gradient kernel's CONSUMER warps (what is built: k3_grad.cuh, own_dead_from): c2 322.8 us at 100 %, 325.0 at
+    //    90 %, 327.4 at 80 %, 330.2 at 60 %; a quarter of c3 567 -> 572 at 65 %; an eighth 312.3 -> 312.8; the whole of
+    //    c3 2113 -> 2101 at 55 % (-0.5 %) and back up to 2123 at 40 %;
+    //  * one more warp per CTA of the gradient kernel issuing bulk stores (ranges in zero_fill.cuh): c2 321.7 -> 343.6 at
+    //    80 %, 365.5 at 60 % -- its stores queue in the per-SM bulk-copy pipe in front of the producer's loads.
+    // In the stream the lattice kernel's tail already overlaps the gradient kernel's set-up (dependent launch), and what
+    // the fill moves costs the same bandwidth wherever it is written: nothing to win.  Hence 100 unless asked otherwise
+    // (MRNNT_OPT_K2_FILL_SHARE).
     int k2_fill_share() const {
         if (k2_fill_share_ >= 0) return k2_fill_share_ > 100 ? 100 : (k2_fill_share_ < 1 ? 1 : k2_fill_share_);
         return 100;
@@ -1147,13 +1148,8 @@ class Engine {
         if (zero_warp) {
             zero = zero_fill_args(grads, shared_fill_ctr_ != nullptr ? shared_fill_ctr_ : ws_.k2_flags + k2_zero_ctr_word(B_));
             if (shared_fill_ctr_ != nullptr) flags |= kK3ZeroShared;
-            if (k3_fill_unit_begin_ > 0) {
-                // (behind the lattice kernel's fill, which may still be running when this kernel's warps start: a
-                // counter pair of its own)
-                zero.unit_begin = k3_fill_unit_begin_;
-                zero.ctr = ws_.k2_flags + k2_zero_ctr_word(B_) + 4;
-            }
         }
+        const int64_t own_dead_from = (k3_fill_unit_begin_ > 0 && !k3_write_dead_) ? k3_fill_unit_begin_ * kWarp : INT64_MAX;
         const size_t smem = k3_smem_bytes(tl.smem_bytes, zero_warp);
         if (smem > static_cast<size_t>(dev.max_smem_optin) || !ensure_dynamic_smem(kern, smem)) return RNNT_STATUS_EXECUTION_FAILED;
         // K3 is persistent with one CTA per SM; `reserved_sms_` of them can be left to a collective that runs
@@ -1164,7 +1160,7 @@ class Engine {
         if (launch_kernel(kern, grid, (NW + (zero_warp ? 2 : 1)) * kWarp, smem, stream, pdl_ && k3_follows_k2_,
                           static_cast<const E *>(acts_), ws_.coef, ws_.rowlab, static_cast<E *>(grads), shape_.rows, V_, blank, tl.G,
                           tl.stages, ws_.rowutt, scale, cost_mirror(), flags, zero, tl.smem_bytes,
-                          ws_.k2_flags + stream_ctr_word(B_), peer_args(peer_in_k3_), tl.slot_bytes) != cudaSuccess)
+                          ws_.k2_flags + stream_ctr_word(B_), peer_args(peer_in_k3_), tl.slot_bytes, own_dead_from) != cudaSuccess)
             return RNNT_STATUS_EXECUTION_FAILED;
         return launched();
     }

@@ -126,7 +126,9 @@ static __global__ void __launch_bounds__((NW + 2) * kWarp, 1)
                        E *__restrict__ grads, int64_t rows, int V, int blank, int G, int stages,
                        const int *__restrict__ rowutt,
                        const float *__restrict__ scale, CostMirror mirror, int flags, ZeroFill zero, size_t ring_bytes,
-                       unsigned *__restrict__ dyn, PeerReduce peer, size_t slot_bytes) {
+                       unsigned *__restrict__ dyn, PeerReduce peer, size_t slot_bytes, int64_t own_dead_from) {
+    // own_dead_from: without kK3WriteDead, the plan's dead rows from this row on are nevertheless this kernel's to write
+    // (the lattice kernel's fill took the rows before it: Engine::k2_fill_share); INT64_MAX: none
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NE = Elem<E>::kPerVec;
     unsigned char *tiles = smem_raw;
@@ -234,7 +236,7 @@ static __global__ void __launch_bounds__((NW + 2) * kWarp, 1)
                 const float s2 = load_scale(t2);
                 const int l2 = load_lab(t2);
                 const uint32_t mask = __ballot_sync(0xffffffffu, !(c0.x == kNegInfF));
-                if (write_dead || mask != 0u) fill_slot(t0, c0, l0, s0, mask);
+                if (write_dead || mask != 0u || (t0 + 1) * G > own_dead_from) fill_slot(t0, c0, l0, s0, mask);
                 t0 = t1; c0 = c1; s0 = s1; l0 = l1;
                 t1 = t2; c1 = c2; s1 = s2; l1 = l2;
             }
@@ -316,7 +318,7 @@ static __global__ void __launch_bounds__((NW + 2) * kWarp, 1)
                 const uint32_t ball = __ballot_sync(0xffffffffu, !(cb.x == kNegInfF));
                 for (int j = 0; j < TPB && k0 + j < nloc; ++j) {
                     const uint32_t mask = (ball >> (j * G)) & gmask;
-                    if (mask == 0u) continue;
+                    if (mask == 0u && (blockIdx.x + (k0 + j) * gridDim.x + 1) * G <= own_dead_from) continue;
                     const int src = j * G + (lane % G);
                     float4 c;
                     c.x = __shfl_sync(0xffffffffu, cb.x, src);
@@ -384,7 +386,7 @@ static __global__ void __launch_bounds__((NW + 2) * kWarp, 1)
                     // a zero row; without write_dead somebody else zeroes the rows the plan calls dead (marked in the
                     // label slot; the lattice kernel's fill or a zero-fill warp, zero_fill.cuh), and only a row
                     // INSIDE the lattice that came out as zero (masked logits) is written here
-                    if (write_dead || lab != kRowDead) {
+                    if (write_dead || lab != kRowDead || row >= own_dead_from) {
                         const uint4 z = make_uint4(0u, 0u, 0u, 0u);  // +0.0 in either element type
                         for (int j = lane; j < nvec; j += kWarp) st_stream_u4(gv + j, z);
                         if (UNALIGNED && e_edge >= 0) grow[e_edge] = Elem<E>::from_float(0.0f);

@@ -392,9 +392,8 @@ def test_every_way_of_zeroing_the_dead_rows(gu, mode, restricted, dyn):
 @pytest.mark.parametrize("restricted", [False, True], ids=["free", "aligned"])
 def test_zero_fill_split_between_lattice_and_gradient_kernel(gu, share, restricted, dyn):
     """MRNNT_OPT_K2_FILL_SHARE: the lattice kernel's fill writes the zero rows of the first `share` percent of the batch's
-    units of 32 rows, the gradient kernel's zero-fill warp those of the rest (a counter pair of its own: it starts while
-    the lattice kernel's fill may still be running).  Every element written, the bits of the unsplit fill, three calls
-    in a row (both counter pairs come back to zero), and the two halves of a training step on their own."""
+    units of 32 rows, the gradient kernel's consumer warps those of the rest.  Every element written, the bits of the
+    unsplit fill, three calls in a row, and the two halves of a training step on their own."""
     import monotonic_rnnt_b200 as mr
     from monotonic_rnnt_b200 import _lib
     case = fixtures.random_case("fill_split", 777, B=7, V=1000, T_range=(25, 60), S_range=(4, 20), dist="uniform")
