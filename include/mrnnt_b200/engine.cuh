@@ -765,6 +765,8 @@ class Engine {
     void set_k2_zero_fill(int warps) { k2_zero_warps_ = warps; }
     // percent of the zero fill that stays in the lattice kernel (-1: automatic); see k2_fill_share()
     void set_k2_fill_share(int pct) { k2_fill_share_ = pct; }
+    // the lattice kernel takes part in a fill that the LSE and gradient kernels' zero-fill warps share (default on)
+    void set_k2_shared_fill(bool on) { k2_shared_fill_ = on; }
     // -1 automatic, 0 off, 1 on; 2..100: on, with that percentage of a CTA's share fixed before the counter takes over
     void set_dynamic_tiles(int mode) {
         dynamic_tiles_ = mode < 0 ? -1 : (mode != 0);
@@ -1007,6 +1009,7 @@ class Engine {
         a.row_bytes = static_cast<unsigned>(static_cast<size_t>(V_) * elem_bytes());
         a.zero_warps = 0;
         a.zero_unit_end = -1;
+        a.zero_shared_ctr = nullptr;
         k2_fill_unit_end_ = -1;
         a.zero_clear = shared_fill_clear_;
         last_k2_zero_warps_ = 0;
@@ -1036,6 +1039,13 @@ class Engine {
                     const int64_t nunits = (shape_.rows + kWarp - 1) / kWarp;
                     k2_fill_unit_end_ = nunits * share / 100;
                 }
+            } else if (need_beta && zero_dst_ != nullptr && shared_fill_ctr_ != nullptr && spare > 0 && k2_shared_fill_ &&
+                       zero_fill_possible()) {
+                // the fill the LSE kernel's zero-fill warp has begun and the gradient kernel's will finish (SHARED
+                // protocol): two warps per CTA of this kernel take units from the same counter while the recursions run
+                a.zero_dst = static_cast<unsigned char *>(zero_dst_);
+                a.zero_warps = spare < 2 ? spare : 2;
+                a.zero_shared_ctr = shared_fill_ctr_;
             }
             a.zero_unit_end = k2_fill_unit_end_;
             return K == 1   ? launch_k2_warp<1>(a, stream, dev)
@@ -1273,6 +1283,7 @@ class Engine {
     int last_k2_zero_warps_ = 0;        // what the last lattice launch ran with
     int k2_zero_warps_ = -1;            // warps per lattice CTA for the zero fill: -1 automatic, 0 off
     int last_k2_fill_share_ = 100;
+    bool k2_shared_fill_ = true;
     int k2_fill_share_ = -1;            // percent of the fill's units the lattice kernel takes: -1 automatic
     int64_t k2_fill_unit_end_ = -1;     // where the last lattice kernel's fill stops (-1: it takes everything)
     int64_t k3_fill_unit_begin_ = 0;    // ... and where the gradient kernel's zero-fill warp therefore starts

@@ -112,6 +112,9 @@ struct K2Args {
     int64_t rows;             // rows of the whole batch (= row_start[B])
     int B;                    // utterances; flags[k2_zero_ctr_word(B)...]: the zero fill's two counters
     unsigned *zero_clear;     // SHARED zero fill: the counter of the NEXT call, cleared here (nullptr: none)
+    unsigned *zero_shared_ctr;  // SHARED zero fill: this call's counter -- the fill warps of this kernel take units from it
+                              // between the LSE kernel's zero-fill warp and the gradient kernel's, for as long as the
+                              // recursions run (nullptr: the OWNED protocol, this kernel does the whole fill)
     int phase_ctas;           // B * parts; CTAs behind them (zero fill only) do nothing else
 };
 
@@ -617,14 +620,29 @@ __device__ __forceinline__ void k2_coef_rows(const K2Args &a, int b, int part, i
 
 // ---- cross-CTA hand-over of one utterance ----------------------------------------------------------------
 // ---- dead-row zero fill (zero_fill.cuh) ----------------------------------------------------------------------
-__device__ __forceinline__ void k2_zero_dead_rows(const K2Args &a, int fw, int nfw, unsigned char *zbuf) {
+// done_word: the "recursions done" word of an utterance (SHARED protocol: this kernel's fill stops when it carries this
+// launch's epoch -- what is left belongs to the gradient kernel's zero-fill warp, which is about to start)
+__device__ __forceinline__ void k2_zero_dead_rows(const K2Args &a, int fw, int nfw, unsigned char *zbuf, const unsigned *done_word) {
     ZeroFill z;
     z.dst = a.zero_dst;
     z.rowmeta = a.rowmeta;
     z.rows = a.rows;
     z.row_bytes = a.row_bytes;
-    z.ctr = a.flags + k2_zero_ctr_word(a.B);
     z.unit_begin = 0;
+    if (a.zero_shared_ctr != nullptr) {
+        z.ctr = a.zero_shared_ctr;
+        z.unit_end = -1;
+        // (the word is looked at one unit late: the load is in flight while a unit is being written)
+        unsigned seen = 0u;
+        const unsigned epoch = a.epoch;
+        zero_dead_rows_impl<false>(z, 0, 0, zbuf, [&] {
+            const bool over = seen == epoch;
+            seen = *reinterpret_cast<const volatile unsigned *>(done_word);
+            return over;
+        });
+        return;
+    }
+    z.ctr = a.flags + k2_zero_ctr_word(a.B);
     z.unit_end = a.zero_unit_end;
     zero_dead_rows(z, fw, nfw, zbuf);
 }
@@ -691,7 +709,9 @@ static __global__ void __launch_bounds__(kK2Threads) k2_lattice_kernel(K2Args a)
     pdl_launch_dependents();  // the gradient kernel may be scheduled as our CTAs retire (it waits for all of us)
     if (static_cast<int>(blockIdx.x) >= a.phase_ctas) {
         // a CTA that only fills zeros: needs nothing K1 wrote, so it does not wait for it either
-        if (warp < zw) k2_zero_dead_rows(a, blockIdx.x * zw + warp, gridDim.x * zw, k2_smem + k2_zero_offset(dir_bytes));
+        if (warp < zw)
+            k2_zero_dead_rows(a, blockIdx.x * zw + warp, gridDim.x * zw, k2_smem + k2_zero_offset(dir_bytes),
+                              a.flags + (static_cast<size_t>(a.epoch & 1u) * a.B + blockIdx.x % a.B) * kK2FlagWords + 2 * kK2MaxParts + 1);
         return;
     }
     const int b = blockIdx.x / parts;
@@ -702,7 +722,7 @@ static __global__ void __launch_bounds__(kK2Threads) k2_lattice_kernel(K2Args a)
     if (warp < zw) {
         // ---- zero fill: this warp's share of the batch's dead rows, nothing else (and nothing K1 wrote) ----
         if (warp == 0) MRNNT_K2_STAMP(53);
-        k2_zero_dead_rows(a, blockIdx.x * zw + warp, gridDim.x * zw, k2_smem + k2_zero_offset(dir_bytes));
+        k2_zero_dead_rows(a, blockIdx.x * zw + warp, gridDim.x * zw, k2_smem + k2_zero_offset(dir_bytes), done);
         if (warp == 0) MRNNT_K2_STAMP(54);
         return;
     }
@@ -779,7 +799,7 @@ static __global__ void __launch_bounds__(kK2Threads) k2_lattice_kernel(K2Args a)
         }
         if (!a.need_beta) return;
         k2_phase_sync(zw);
-        if (parts > 1 && tid == 0) {
+        if ((parts > 1 || a.zero_shared_ctr != nullptr) && tid == 0) {
             __threadfence();
             k2_st_release(done, a.epoch);
         }

@@ -19,7 +19,7 @@ from monotonic_rnnt_b200 import _lib  # noqa: E402
 
 
 def run(name: str, iters: int, combos, padded: bool = False, bf16: bool = False, compact: int = -1,
-        zeros=(-1,), dyn: int = -1, shard: str = "", parts: int = 0) -> None:
+        zeros=(-1,), dyn: int = -1, shard: str = "", parts: int = 0, share: int = -1) -> None:
     wl = mr.synth.workload(name)
     if shard:   # rank r's utterances of the batch cut over N ranks (LPT, as bench.py --scaling strong does)
         import dataclasses
@@ -51,6 +51,7 @@ def run(name: str, iters: int, combos, padded: bool = False, bf16: bool = False,
     h.set_option(_lib.OPT_K1_COMPACT, compact)
     h.set_option(_lib.OPT_DYNAMIC_TILES, dyn)
     h.set_option(_lib.OPT_K2_PARTS, parts)
+    h.set_option(_lib.OPT_K2_FILL_SHARE, share)
     costs = torch.empty(wl.B, dtype=torch.float32).pin_memory()
     n4 = wl.elements * (2 if bf16 else 4)
     for k1w, k3w, zf in [(a, b, z) for a, b in combos for z in zeros]:
@@ -70,7 +71,7 @@ def run(name: str, iters: int, combos, padded: bool = False, bf16: bool = False,
         k = np.median(np.array(ts), axis=0)
         w = float(np.median(wall))
         print(f"{wl.name}{' BF16' if bf16 else ''}{' PADDED rows=' + str(acts.numel() // wl.V) if padded else ''} B={wl.B} V={wl.V} rows={wl.rows} "
-              f"k1w={k1w} k3w={k3w} zero={zf} dyn={dyn}: "
+              f"k1w={k1w} k3w={k3w} zero={zf} dyn={dyn} share={share}: "
               f"K1 {k[0]*1e3:7.1f} us ({n4/k[0]/1e6:6.0f} GB/s of 1xN)  K2 {k[1]*1e3:7.1f} us  "
               f"K3 {k[2]*1e3:7.1f} us ({2*n4/k[2]/1e6:6.0f} GB/s of 2xN)  call {w*1e3:7.1f} us "
               f"({3*n4/w/1e6:6.0f} GB/s of 3xN, {wl.B/w*1e3:8.0f} utt/s)", flush=True)
@@ -96,8 +97,10 @@ if __name__ == "__main__":
     ap.add_argument("--zero", default="-1", help="comma list of MRNNT_OPT_K2_ZERO_FILL values to compare")
     ap.add_argument("--shard", default="", help="r/N: rank r's utterances of the batch cut over N ranks")
     ap.add_argument("--parts", type=int, default=0, help="MRNNT_OPT_K2_PARTS")
+    ap.add_argument("--share", default="-1", help="comma list of MRNNT_OPT_K2_FILL_SHARE values")
     a = ap.parse_args()
     combos = [tuple(int(x) for x in c.split(":")) for c in a.combos.split(",")]
     for name in a.workloads:
         for d in [int(x) for x in a.dyn.split(',')]:
-            run(name, a.iters, combos, a.padded, a.bf16, a.compact, [int(z) for z in a.zero.split(',')], d, a.shard, a.parts)
+            for sh in [int(x) for x in a.share.split(',')]:
+                run(name, a.iters, combos, a.padded, a.bf16, a.compact, [int(z) for z in a.zero.split(',')], d, a.shard, a.parts, sh)
