@@ -83,6 +83,35 @@ __global__ void runlist_interleaved(unsigned char *dst, const long long *run_off
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+// the run list again, written with ordinary 16-byte stores: piece p (of `piece_bytes`) -> warp p mod nwarps, the 32 lanes
+// of the warp store it together (512 contiguous bytes per instruction)
+__global__ void runlist_stg(unsigned char *dst, const long long *run_off, const long long *run_len, const long long *pre,
+                            int nruns, long long total, int piece_bytes) {
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long gw = (long long)(threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+    const long long pieces = (total + piece_bytes - 1) / piece_bytes;
+    int r = 0;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (long long p = gw; p < pieces; p += nwarps) {
+        long long b0 = p * piece_bytes;
+        const long long b1 = std::min<long long>(b0 + piece_bytes, total);
+        int lo = r, hi = nruns - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) / 2;
+            if (pre[mid] + run_len[mid] > b0) hi = mid; else lo = mid + 1;
+        }
+        r = lo;
+        while (b0 < b1) {
+            const long long e = std::min(b1, pre[r] + run_len[r]);
+            unsigned char *q = dst + run_off[r] + (b0 - pre[r]);
+            for (long long o = lane * 16; o < e - b0; o += 512) __stcs(reinterpret_cast<uint4 *>(q + o), z);
+            b0 = e;
+            if (b0 < b1) ++r;
+        }
+    }
+}
+
 template <class F> static float time_it(F f, int reps = 10) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     f(); CK(cudaDeviceSynchronize());
@@ -142,6 +171,24 @@ int main(int argc, char **argv) {
         for (int pb : {2048, 4096, 8192}) {
             const float r = time_it([&] { runlist_interleaved<<<148, w * 32, kZeroFillBytes>>>(dst, doff, dlen, dpre, (int)off.size(), total, pb); });
             printf("%d warps/CTA: run list, interleaved %4d B pieces %7.1f us (%6.0f GB/s)\n", w, pb, r * 1e3, total / r * 1e-6);
+        }
+    }
+    {   // the same two kernels on ONE run of the same size (is it the scatter, or the way of writing?)
+        long long one_off = 0, one_len = total, one_pre = 0, *d1;
+        CK(cudaMalloc(&d1, 24));
+        CK(cudaMemcpy(d1, &one_off, 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(d1 + 1, &one_len, 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d1 + 2, &one_pre, 8, cudaMemcpyHostToDevice));
+        for (int w : {2, 4}) {
+            const float r = time_it([&] { runlist_interleaved<<<148, w * 32, kZeroFillBytes>>>(dst, d1, d1 + 1, d1 + 2, 1, total, 8192); });
+            printf("%d warps/CTA: ONE run, interleaved 8192 B pieces %7.1f us (%6.0f GB/s)\n", w, r * 1e3, total / r * 1e-6);
+        }
+        for (int w : {2, 8, 24}) {
+            for (int pb : {8192, 32768}) {
+                const float r1 = time_it([&] { runlist_stg<<<148, w * 32>>>(dst, d1, d1 + 1, d1 + 2, 1, total, pb); });
+                const float r2 = time_it([&] { runlist_stg<<<148, w * 32>>>(dst, doff, dlen, dpre, (int)off.size(), total, pb); });
+                printf("%2d warps/CTA: 16-byte stores, %5d B pieces: ONE run %7.1f us (%6.0f GB/s)   the run list %7.1f us (%6.0f GB/s)\n", w, pb,
+                       r1 * 1e3, total / r1 * 1e-6, r2 * 1e3, total / r2 * 1e-6);
+            }
         }
     }
     CK(cudaDeviceSynchronize());
