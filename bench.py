@@ -732,10 +732,10 @@ def run_b200(args) -> None:
         k3_written = live_rows
         zero_note = "the dead rows' zeros are written by the lattice kernel's fill warps while its recursions run"
     elif zero_fill_warps >= 32 or (wl.alignment is not None and zero_fill_warps == 0):
-        # tight alignment band: the zero rows are written by one extra warp in K1 and one in K3 out of ONE counter
+        # tight alignment band: the zero rows are written by the zero-fill warps of K1, K2 and K3 out of ONE counter
         # (DESIGN 3.2); the split is not known on the host, K3 is charged with none of them (a lower bound)
         k3_written = live_rows
-        zero_note = "zero rows written by the fill warps of K1 and K3 from one counter; K3 charged with none of them"
+        zero_note = "zero rows written by the fill warps of K1, K2 and K3 from one counter; K3 charged with none of them"
     else:
         k3_written = wl.rows
     k3_bytes = 4 * wl.V * (live_rows + k3_written)
@@ -743,7 +743,7 @@ def run_b200(args) -> None:
     if (zero_fill_warps >= 32 or (wl.alignment is not None and zero_fill_warps == 0)) and k3_traffic is not None:
         # how many of the zero rows K3's fill warp took is only known from the counters: the capture's write bytes
         k3_bytes = max(k3_bytes, int(k3_traffic))
-        zero_note = ("zero rows written by the fill warps of K1 and K3 from one counter; K3's share taken from the ncu capture "
+        zero_note = ("zero rows written by the fill warps of K1, K2 and K3 from one counter; K3's share taken from the ncu capture "
                      "(profiles/traffic.json): its job is what it moved there")
     k3_gbs = k3_bytes / (k_ms[2] * 1e-3) / 1e9
     k3_dram_gbs = None if k3_traffic is None else k3_traffic / (k_ms[2] * 1e-3) / 1e9
