@@ -18,7 +18,7 @@ import monotonic_rnnt_b200 as mr  # noqa: E402
 from monotonic_rnnt_b200 import _lib  # noqa: E402
 
 
-def run(name, shares, steps, shard, zero, reps):
+def run(name, shares, steps, shard, zero, reps, opts=()):
     wl = mr.synth.workload(name)
     if shard:
         r, n = (int(x) for x in shard.split("/"))
@@ -36,6 +36,8 @@ def run(name, shares, steps, shard, zero, reps):
     grads = torch.empty_like(acts)
     costs = torch.empty(wl.B, dtype=torch.float32).pin_memory()
     h.set_option(_lib.OPT_K2_ZERO_FILL, zero)
+    for k, v in opts:
+        h.set_option(k, v)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ref = None
     for share in shares:
@@ -56,7 +58,7 @@ def run(name, shares, steps, shard, zero, reps):
             ev1.record()
             torch.cuda.synchronize()
             ts.append(ev0.elapsed_time(ev1) / steps * 1e3)
-        print(f"{wl.name} B={wl.B} zero={zero} share={share:4d} (used {h.get_option(_lib.OPT_K2_FILL_SHARE):3d}, fill warps "
+        print(f"{wl.name} B={wl.B} zero={zero} opts={list(opts)} share={share:4d} (used {h.get_option(_lib.OPT_K2_FILL_SHARE):3d}, fill warps "
               f"{h.get_option(_lib.OPT_K2_ZERO_FILL)}): call {np.median(ts):8.1f} us (min {min(ts):8.1f})  {wl.B / np.median(ts) * 1e6:9.0f} utt/s", flush=True)
     h.close()
 
@@ -69,6 +71,8 @@ if __name__ == "__main__":
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--shard", default="")
     ap.add_argument("--zero", type=int, default=-1)
+    ap.add_argument("--opt", action="append", default=[], help="ID=VALUE: mrnnt_set_option before the sweep (repeatable)")
     a = ap.parse_args()
     for name in a.workloads:
-        run(name, [int(x) for x in a.shares.split(",")], a.steps, a.shard, a.zero, a.reps)
+        run(name, [int(x) for x in a.shares.split(",")], a.steps, a.shard, a.zero, a.reps,
+            [tuple(int(x) for x in o.split("=")) for o in a.opt])
