@@ -119,6 +119,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     }
 }
 
+// Development aid (tools/timeline_probe.cu, -DMRNNT_TIMELINE): %globaltimer stamps of the three kernels of a call IN THE
+// STREAM -- first CTA in, first CTA past its wait for the predecessor, last warp out -- per call slot, so that the gaps
+// between the kernels of back-to-back calls can be read off.  Compiled out otherwise.
+#ifdef MRNNT_TIMELINE
+constexpr int kTimelineSlots = 16, kTimelineEvents = 16;
+__device__ unsigned long long g_timeline[kTimelineSlots][kTimelineEvents];
+__device__ __forceinline__ unsigned long long timeline_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define MRNNT_TL_MIN(slot, ev) atomicMin(&g_timeline[(slot) & (kTimelineSlots - 1)][ev], timeline_now())
+#define MRNNT_TL_MAX(slot, ev) atomicMax(&g_timeline[(slot) & (kTimelineSlots - 1)][ev], timeline_now())
+#else
+#define MRNNT_TL_MIN(slot, ev) ((void)0)
+#define MRNNT_TL_MAX(slot, ev) ((void)0)
+#endif
+
 // L2 eviction policies for the bulk copies (streamed-once data should not displace reusable lines)
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     uint64_t p;

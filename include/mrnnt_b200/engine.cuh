@@ -605,6 +605,7 @@ class Engine {
         // lattice kernel of this call clears the one the next call will use.
         shared_fill_ctr_ = shared_fill_clear_ = nullptr;
         zero_dst_ = grads_dev;
+        ++tl_call_;  // (MRNNT_TIMELINE: this call's slot)
         if (grads_dev != nullptr && k3_zero_warp_wanted() && zero_fill_possible() && base_ != nullptr) {
             unsigned *pair = ws_.k2_flags + k2_zero_ctr_word(B_) + 2;
             ++shared_seq_;
@@ -762,6 +763,7 @@ class Engine {
     void set_reserved_sms(int n) { reserved_sms_ = n < 0 ? 0 : n; }
     int last_k2_zero_warps() const { return last_k2_zero_warps_; }
     int last_k2_fill_share() const { return last_k2_fill_share_; }  // percent of the fill's units the lattice kernel took
+    int timeline_slot() const { return tl_call_; }
     void set_k2_zero_fill(int warps) { k2_zero_warps_ = warps; }
     // percent of the zero fill that stays in the lattice kernel (-1: automatic); see k2_fill_share()
     void set_k2_fill_share(int pct) { k2_fill_share_ = pct; }
@@ -873,6 +875,7 @@ class Engine {
         if (zero_warp) {
             zero = zero_fill_args(zero_dst_, shared_fill_ctr_);
         }
+        zero.tl_slot = tl_call_;
         const size_t smem = k1_smem_bytes(tl.smem_bytes, zero_warp);
         if (smem > static_cast<size_t>(dev.max_smem_optin) || !ensure_dynamic_smem(kern, smem)) return RNNT_STATUS_EXECUTION_FAILED;
         // (a programmatic dependent of whatever precedes it in the stream: behind the previous call's gradient kernel,
@@ -1016,6 +1019,7 @@ class Engine {
         a.rows = shape_.rows;
         a.B = B_;
         a.phase_ctas = 0;
+        a.tl_slot = tl_call_;
         // (a padded tensor with many label positions per frame can ask for more shared memory than an SM has while its
         // longest label sequence still fits the row of warps: the block-wide kernel takes it then)
         const bool warp_kernel_fits =
@@ -1159,6 +1163,7 @@ class Engine {
             zero = zero_fill_args(grads, shared_fill_ctr_ != nullptr ? shared_fill_ctr_ : ws_.k2_flags + k2_zero_ctr_word(B_));
             if (shared_fill_ctr_ != nullptr) flags |= kK3ZeroShared;
         }
+        zero.tl_slot = tl_call_;
         const int64_t own_dead_from = (k3_fill_unit_begin_ > 0 && !k3_write_dead_) ? k3_fill_unit_begin_ * kWarp : INT64_MAX;
         const size_t smem = k3_smem_bytes(tl.smem_bytes, zero_warp);
         if (smem > static_cast<size_t>(dev.max_smem_optin) || !ensure_dynamic_smem(kern, smem)) return RNNT_STATUS_EXECUTION_FAILED;
@@ -1284,6 +1289,7 @@ class Engine {
     int k2_zero_warps_ = -1;            // warps per lattice CTA for the zero fill: -1 automatic, 0 off
     int last_k2_fill_share_ = 100;
     bool k2_shared_fill_ = true;
+    int tl_call_ = -1;                  // calls enqueued so far - 1 (MRNNT_TIMELINE)
     int k2_fill_share_ = -1;            // percent of the fill's units the lattice kernel takes: -1 automatic
     int64_t k2_fill_unit_end_ = -1;     // where the last lattice kernel's fill stops (-1: it takes everything)
     int64_t k3_fill_unit_begin_ = 0;    // ... and where the gradient kernel's zero-fill warp therefore starts

@@ -482,8 +482,10 @@ static __global__ void __launch_bounds__((NW + (COMPACT ? 2 : 1)) * kWarp, 1)
         if (zero_warp) *consumers_done = 0;
     }
     __syncthreads();
+    if (threadIdx.x == 0) MRNNT_TL_MIN(zero.tl_slot, 0);
     pdl_launch_dependents();  // the lattice kernel may be scheduled as our CTAs retire (it waits for all of us)
     pdl_wait();               // (first kernel of a call: its predecessor is the previous call or a set-up kernel)
+    if (threadIdx.x == 0) MRNNT_TL_MIN(zero.tl_slot, 1);
     if (COMPACT && warp == NW + 1) {
         // ---------------- zero-fill warp: for as long as this CTA's consumer warps have work ----------------
         zero_dead_rows_impl<false>(zero, 0, 0, zbuf,
@@ -601,6 +603,7 @@ static __global__ void __launch_bounds__((NW + (COMPACT ? 2 : 1)) * kWarp, 1)
             MRNNT_K1_ADD(warp, 1, MRNNT_K1_CLOCK() - tw1);
         }
         if (zero_warp && lane == 0) atomicAdd(consumers_done, 1);
+        if (lane == 0) MRNNT_TL_MAX(zero.tl_slot, 2);
     }
 }
 

@@ -116,6 +116,7 @@ struct K2Args {
                               // between the LSE kernel's zero-fill warp and the gradient kernel's, for as long as the
                               // recursions run (nullptr: the OWNED protocol, this kernel does the whole fill)
     int phase_ctas;           // B * parts; CTAs behind them (zero fill only) do nothing else
+    int tl_slot;              // (MRNNT_TIMELINE: the call's slot of the timeline)
 };
 
 // States per lane for a launch whose widest utterance has `states` states; 0: use the wide kernel.  Measured
@@ -706,12 +707,14 @@ static __global__ void __launch_bounds__(kK2Threads) k2_lattice_kernel(K2Args a)
     const size_t chunk_bytes = static_cast<size_t>(a.chunk_frames) * (a.ld > 0 ? a.ld : a.S_max + 1) * sizeof(Weight);
     const int bufs = a.chunk_bufs;
     const size_t dir_bytes = k2_dir_bytes(chunk_bytes, bufs, nrw);
+    if (threadIdx.x == 0) MRNNT_TL_MIN(a.tl_slot, 3);
     pdl_launch_dependents();  // the gradient kernel may be scheduled as our CTAs retire (it waits for all of us)
     if (static_cast<int>(blockIdx.x) >= a.phase_ctas) {
         // a CTA that only fills zeros: needs nothing K1 wrote, so it does not wait for it either
         if (warp < zw)
             k2_zero_dead_rows(a, blockIdx.x * zw + warp, gridDim.x * zw, k2_smem + k2_zero_offset(dir_bytes),
                               a.flags + (static_cast<size_t>(a.epoch & 1u) * a.B + blockIdx.x % a.B) * kK2FlagWords + 2 * kK2MaxParts + 1);
+        if (warp < zw && (threadIdx.x & 31) == 0) MRNNT_TL_MAX(a.tl_slot, 7);
         return;
     }
     const int b = blockIdx.x / parts;
@@ -724,11 +727,13 @@ static __global__ void __launch_bounds__(kK2Threads) k2_lattice_kernel(K2Args a)
         if (warp == 0) MRNNT_K2_STAMP(53);
         k2_zero_dead_rows(a, blockIdx.x * zw + warp, gridDim.x * zw, k2_smem + k2_zero_offset(dir_bytes), done);
         if (warp == 0) MRNNT_K2_STAMP(54);
+        if ((threadIdx.x & 31) == 0) MRNNT_TL_MAX(a.tl_slot, 7);
         return;
     }
     const int nphase = kK2Threads - zw * kWarp;
     MRNNT_K2_STAMP(0);
     pdl_wait();  // K1's records
+    if (tid == 0) MRNNT_TL_MIN(a.tl_slot, 4);
     // (Nothing of the hand-over words is touched before this wait: under programmatic dependent launch this CTA can be
     // running while the PREVIOUS lattice launch has not yet cleared this set -- e.g. forward halves back to back with
     // small kernels that all fit on the device together.  Behind the wait the predecessor chain has completed.)
@@ -804,6 +809,7 @@ static __global__ void __launch_bounds__(kK2Threads) k2_lattice_kernel(K2Args a)
             k2_st_release(done, a.epoch);
         }
         MRNNT_K2_STAMP(51);
+        if (tid == 0) MRNNT_TL_MAX(a.tl_slot, 5);
     } else {
         if (!a.need_beta) return;
         // a helper claims its block of phase C while it waits for the recursions of its utterance's part 0
@@ -825,6 +831,7 @@ static __global__ void __launch_bounds__(kK2Threads) k2_lattice_kernel(K2Args a)
     }
     k2_phase_sync(zw);
     MRNNT_K2_STAMP(52);
+    if (tid == 0) MRNNT_TL_MAX(a.tl_slot, 6);
 }
 
 // ---- fallback for very long label sequences (more than 32 * 4 * kK2MaxRowWarps states) --------------------

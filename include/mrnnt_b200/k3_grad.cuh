@@ -156,8 +156,10 @@ static __global__ void __launch_bounds__((NW + 2) * kWarp, 1)
         else zero_dead_rows(zero, blockIdx.x, gridDim.x, zbuf);
         return;
     }
+    if (threadIdx.x == 0) MRNNT_TL_MIN(zero.tl_slot, 8);
     pdl_launch_dependents();  // the next call's LSE kernel may be scheduled as our CTAs retire (it waits for all of us)
     pdl_wait();  // the coefficients come from the lattice kernel; everything above overlapped its tail
+    if (threadIdx.x == 0) MRNNT_TL_MIN(zero.tl_slot, 9);
     // the sum of this GPU's costs goes out to the peers now and the world's sum is picked up when this warp has got
     // through its rows (peer_reduce.cuh): the exchange rides along with the gradient pass
     const bool peer_warp = blockIdx.x == 0 && warp == 0;
@@ -433,6 +435,7 @@ static __global__ void __launch_bounds__((NW + 2) * kWarp, 1)
             if (lane == 0) mbar_arrive(empty + stage);
         }
         if (peer_warp) peer_collect(peer);
+        if (lane == 0) MRNNT_TL_MAX(zero.tl_slot, 10);
     }
 }
 

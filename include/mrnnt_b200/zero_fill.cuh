@@ -22,6 +22,7 @@ struct ZeroFill {
     unsigned row_bytes;   // V * sizeof(element), a multiple of 4
     unsigned *ctr;        // the hand-out counter (OWNED: {units handed out, warps finished}, zero between launches)
     int64_t unit_begin = 0;   // the units (of 32 rows) this fill is responsible for: [unit_begin, unit_end);
+    int tl_slot = 0;          // (MRNNT_TIMELINE: the call's slot of the timeline; rides in this struct into K1 and K3)
     int64_t unit_end = -1;    // unit_end < 0: up to the last one.  (The lattice kernel's fill takes the front of the
                               // batch, the gradient kernel's zero-fill warp the rest: Engine::k2_fill_share.)
 };
