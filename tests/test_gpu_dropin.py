@@ -91,3 +91,44 @@ def test_reference_binding_cpu_entry_fails_loudly(ref_binding):
         ref_binding.cpu_monotonic_rnnt(t(case.acts, torch.float32), t(case.labels, torch.int32),
                                        t(case.T, torch.int32), t(case.S, torch.int32), torch.zeros(1),
                                        torch.zeros(12, 3), 0, 0)
+
+
+def test_c5_through_the_unmodified_reference_binding(ref_binding):
+    """BASELINE configs[4] as it names it: the alignment-restricted shape B=32 T=300 S=60 V=2000 "via PyTorch binding" --
+    the reference's own gpu_monotonic_rnnt_align_restrict (pytorch_binding/monotonic_rnnt.cu:116-150), compiled unmodified
+    against our include/, on the full c5 batch (4.7 GB of logits).  It must give the bits of this repository's own handle
+    on the same device tensors (the same engine behind both faces), every gradient element written (NaN-poisoned buffer,
+    95 % of the rows dead), and costs that match the double-precision oracle on a slice."""
+    import monotonic_rnnt_b200 as mr
+    from monotonic_rnnt_b200 import _lib
+    from oracle import oracle
+    wl = mr.synth.workload("c5")
+    dev = torch.device("cuda", 0)
+    acts = torch.empty((wl.rows, wl.V), dtype=torch.float32, device=dev)
+    _lib.check(_lib.load().mrnnt_synth_uniform(acts.data_ptr(), wl.elements, wl.logits_seed, 0,
+                                               torch.cuda.current_stream().cuda_stream), "synth")
+    labels, T, S = _dev(wl.labels, torch.int32), _dev(wl.T, torch.int32), _dev(wl.S, torch.int32)
+    al = _dev(wl.alignment, torch.int32)
+    grads = torch.full_like(acts, float("nan"))
+    costs = torch.zeros(wl.B, dtype=torch.float32)
+    for _ in range(2):   # (a new manager and workspace per call, as the binding does it; the second call reuses the block)
+        rc = ref_binding.gpu_monotonic_rnnt_align_restrict(acts, labels, T, S, al, wl.max_shift, costs, grads, wl.blank, 0)
+        assert rc == 0
+    torch.cuda.synchronize()
+    assert not torch.isnan(grads).any()
+    h = mr.LossHandle(acts, labels, T, S, lengths_host=(wl.T, wl.S))
+    h.restrict_to_alignment(al, wl.max_shift, wl.blank)
+    g2 = torch.full_like(acts, float("nan"))
+    c2 = h.cost_and_grad(wl.blank, g2)
+    torch.cuda.synchronize()
+    assert torch.equal(c2, costs)
+    assert torch.equal(g2, grads)
+    h.close()
+    # the first two utterances against the double-precision oracle
+    nb = 2
+    r1 = int(np.sum(wl.T[:nb].astype(np.int64) * (wl.S[:nb] + 1)))
+    a_h = acts[:r1].cpu().numpy()
+    ref = oracle.run(a_h, wl.labels[:nb], wl.T[:nb], wl.S[:nb], wl.V, blank=wl.blank, alignment=wl.alignment[:nb],
+                     max_shift=wl.max_shift, precision="f64_from_f32")
+    np.testing.assert_allclose(costs.numpy()[:nb], ref.costs, rtol=1e-5)
+    assert np.abs(grads[:r1].cpu().numpy() - ref.grads.reshape(r1, wl.V)).max() <= 1e-5
