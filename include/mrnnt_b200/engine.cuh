@@ -769,6 +769,8 @@ class Engine {
     void set_k2_fill_share(int pct) { k2_fill_share_ = pct; }
     // the lattice kernel takes part in a fill that the LSE and gradient kernels' zero-fill warps share (default on)
     void set_k2_shared_fill(bool on) { k2_shared_fill_ = on; }
+    // the plan in one launch (default) or as the three kernels it replaces (also used above kPlanFusedMaxB utterances)
+    void set_fused_plan(bool on) { fused_plan_ = on; }
     // -1 automatic, 0 off, 1 on; 2..100: on, with that percentage of a CTA's share fixed before the counter takes over
     void set_dynamic_tiles(int mode) {
         dynamic_tiles_ = mode < 0 ? -1 : (mode != 0);
@@ -816,6 +818,26 @@ class Engine {
 
     RNNTStatus setup(cudaStream_t stream) {
         if (order_behind_inflight(stream) != RNNT_STATUS_SUCCESS) return RNNT_STATUS_EXECUTION_FAILED;
+        if ((plan_dirty_ || band_dirty_) && B_ <= kPlanFusedMaxB && fused_plan_) {
+            // one launch for the whole plan (plan.cuh: plan_fused_kernel)
+            size_t smem = alignment_ != nullptr ? (static_cast<size_t>(shape_.T_max) + 1) * sizeof(int) : 0;
+            if (alignment_ != nullptr && align_stride_ != 0 && align_stride_ < shape_.T_max) return RNNT_STATUS_INVALID_VALUE;
+            if (smem > 48 * 1024) {
+                if (smem > static_cast<size_t>(device_info().max_smem_optin) - 2048) return RNNT_STATUS_INVALID_VALUE;
+                if (!ensure_dynamic_smem(plan_fused_kernel, smem)) return RNNT_STATUS_EXECUTION_FAILED;
+            }
+            const int64_t block_rows = static_cast<int64_t>(shape_.T_dim) * shape_.U;  // (padded layout; 0: packed)
+            const int64_t max_rows = block_rows > 0 ? block_rows : static_cast<int64_t>(shape_.T_max) * (shape_.S_max + 1);
+            int64_t parts = (max_rows + kPlanFusedRowsPerCta - 1) / kPlanFusedRowsPerCta;
+            parts = parts < 1 ? 1 : (parts > kPlanFusedMaxParts ? kPlanFusedMaxParts : parts);
+            plan_fused_kernel<<<dim3(static_cast<unsigned>(parts), static_cast<unsigned>(B_)), kPlanFusedThreads, smem, stream>>>(
+                T_dev_, S_dev_, B_, shape_.T_max, shape_.label_stride, shape_.U, block_rows, alignment_,
+                align_stride_ > 0 ? align_stride_ : shape_.T_max, max_shift_, align_blank_, ws_.row_start, ws_.band, ws_.rowmeta,
+                ws_.rowutt, ws_.k2_flags);
+            if (launched() != RNNT_STATUS_SUCCESS) return RNNT_STATUS_EXECUTION_FAILED;
+            plan_dirty_ = false;
+            band_dirty_ = false;
+        }
         if (plan_dirty_) {
             plan_row_start_kernel<<<1, kPlanThreads, 0, stream>>>(
                 T_dev_, S_dev_, B_, ws_.row_start, ws_.k2_flags, static_cast<int64_t>(shape_.T_dim) * shape_.U);
@@ -1289,6 +1311,7 @@ class Engine {
     int k2_zero_warps_ = -1;            // warps per lattice CTA for the zero fill: -1 automatic, 0 off
     int last_k2_fill_share_ = 100;
     bool k2_shared_fill_ = true;
+    bool fused_plan_ = true;
     int tl_call_ = -1;                  // calls enqueued so far - 1 (MRNNT_TIMELINE)
     int k2_fill_share_ = -1;            // percent of the fill's units the lattice kernel takes: -1 automatic
     int64_t k2_fill_unit_end_ = -1;     // where the last lattice kernel's fill stops (-1: it takes everything)

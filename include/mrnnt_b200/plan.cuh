@@ -278,6 +278,114 @@ static __global__ void __launch_bounds__(256) rowmeta_kernel(const int *__restri
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The three set-up kernels above as ONE launch (batches of up to kPlanFusedMaxB utterances): grid (parts, B), CTA (p, b)
+// works out row_start[b] (a block-wide sum over the utterances before b), the alignment counts m[] of utterance b in
+// shared memory, and from them rowmeta / rowutt of slice p of the utterance's rows; the CTAs with p == 0 also leave
+// row_start[] and band[] in the workspace for the lattice kernel, CTA (0, 0) clears the hand-over words.  The results
+// are those of the three kernels, bit for bit (tests: DBG_ROWSTART / DBG_BAND / DBG_ROWMETA against the host
+// restatement); what is saved are two launches and the two round trips through global memory between them -- ~6 us per
+// manager, which a caller like the reference's torch binding pays on every loss call (a new manager per call).
+// Shared memory: (T_max + 1) ints when there is an alignment, else none.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPlanFusedThreads = 256;
+constexpr int kPlanFusedMaxB = 1024;
+constexpr int kPlanFusedRowsPerCta = 2048;
+constexpr int kPlanFusedMaxParts = 64;
+
+static __global__ void __launch_bounds__(kPlanFusedThreads)
+    plan_fused_kernel(const int *__restrict__ T, const int *__restrict__ S, int B, int T_max, int label_stride, int ld_fixed,
+                      int64_t padded_block_rows, const int *__restrict__ alignment, int align_stride, int max_shift,
+                      int blank_idx, int64_t *__restrict__ row_start, int2 *__restrict__ band, int *__restrict__ rowmeta,
+                      int *__restrict__ rowutt, unsigned *__restrict__ k2_flags) {
+    extern __shared__ int m_sh[];  // [T_b + 1] when alignment != nullptr
+    __shared__ int64_t red_sh[kPlanFusedThreads / kWarp];
+    __shared__ int warp_tot[kPlanFusedThreads / kWarp];
+    __shared__ int carry_sh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y, p = blockIdx.x, nparts = gridDim.x;
+    const int Tb = T[b], Sb = S[b];
+    if (b == 0 && p == 0)
+        for (int i = tid; i < static_cast<int>(k2_flag_words(B)); i += kPlanFusedThreads) k2_flags[i] = 0u;
+
+    // ---- row_start[b] ----
+    int64_t start;
+    if (padded_block_rows > 0) {
+        start = b * padded_block_rows;
+    } else {
+        int64_t local = 0;
+        for (int i = tid; i < b; i += kPlanFusedThreads) local += static_cast<int64_t>(T[i]) * (S[i] + 1);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+        if (lane == 0) red_sh[warp] = local;
+        __syncthreads();
+        start = 0;
+        for (int w = 0; w < kPlanFusedThreads / kWarp; ++w) start += red_sh[w];
+    }
+    const int64_t nrows = padded_block_rows > 0 ? padded_block_rows : static_cast<int64_t>(Tb) * (Sb + 1);
+    if (p == 0 && tid == 0) {
+        row_start[b] = start;
+        if (b == B - 1) row_start[B] = start + nrows;
+    }
+
+    // ---- alignment counts m[0 .. T_b] (band_kernel above) ----
+    const bool restricted = alignment != nullptr;
+    const int shift = max_shift < 0 ? 0 : (max_shift > T_max ? T_max : max_shift);
+    if (restricted) {
+        const int *al = alignment + static_cast<size_t>(b) * align_stride;
+        if (tid == 0) {
+            carry_sh = 0;
+            m_sh[0] = 0;
+        }
+        __syncthreads();
+        for (int base = 0; base < Tb; base += kPlanFusedThreads) {
+            const int t = base + tid;
+            int incl = (t < Tb && al[t] != blank_idx) ? 1 : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            if (lane == 31) warp_tot[warp] = incl;
+            __syncthreads();
+            int before = carry_sh;
+            for (int w = 0; w < warp; ++w) before += warp_tot[w];
+            if (t < Tb) m_sh[t + 1] = before + incl;
+            __syncthreads();
+            if (tid == kPlanFusedThreads - 1) carry_sh = before + incl;
+            __syncthreads();
+        }
+    }
+    auto band_of = [&](int t) {  // (lo, hi) of frame t < T_b
+        if (!restricted) return make_int2(0, Sb);
+        const int a = t + 1 - shift, c = t + 1 + shift;
+        return make_int2(m_sh[a > 0 ? a : 0], m_sh[c < Tb ? c : Tb]);
+    };
+    if (p == 0) {
+        int2 *band_b = band + static_cast<size_t>(b) * T_max;
+        for (int t = tid; t < T_max; t += kPlanFusedThreads) band_b[t] = t < Tb ? band_of(t) : make_int2(0, Sb);
+    }
+
+    // ---- rowmeta / rowutt of this CTA's slice of the utterance's rows (rowmeta_kernel above) ----
+    const int ld = ld_fixed > 0 ? ld_fixed : Sb + 1;
+    const int64_t r0 = nrows * p / nparts, r1 = nrows * (p + 1) / nparts;
+    for (int64_t local = r0 + tid; local < r1; local += kPlanFusedThreads) {
+        const int t = static_cast<int>(local / ld);
+        const int s = static_cast<int>(local - static_cast<int64_t>(t) * ld);
+        bool live;
+        if (t >= Tb || s > Sb) {
+            live = false;
+        } else if (t == 0) {
+            live = (s == 0);
+        } else {
+            const int2 lh = band_of(t - 1);
+            live = s >= lh.x && s <= lh.y && s <= t && (Sb - s) <= (Tb - t);
+        }
+        rowmeta[start + local] = live ? (s < Sb ? b * label_stride + s : kRowNoLabel) : kRowDead;
+        rowutt[start + local] = b;
+    }
+}
+
 // Host -> device upload of the logits that will be read (Engine::upload_live_rows): a warp per row, live rows only,
 // straight out of pinned host memory over PCIe into the device array the kernels stream from.  The copy engine moves
 // whole tensors; which rows the lattice reads is known from the plan (rowmeta), and the rows it calls dead -- 27 % of

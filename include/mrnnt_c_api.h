@@ -173,6 +173,8 @@ enum {
                                     lattice kernel writes; the gradient kernel's zero-fill warp writes the rest; -1
                                     automatic (100: measured, the split loses on every named shape).  mrnnt_get_option:
                                     what the last call used                                                          */
+    MRNNT_OPT_FUSED_PLAN = 15,   /* 1 (default): row starts, alignment band and row flags are set up by ONE kernel launch (up
+                                    to 1024 utterances); 0: by the three kernels it replaces.  Before the first call.    */
     MRNNT_OPT_RETURN_EARLY = 13  /* 1 (default): mrnnt_cost_and_grad / compute_rnnt_loss with gradients return as soon as
                                     the costs are on the host; the gradient kernel may still be running and the gradients
                                     (and *total_out of a peer reduce) are complete in STREAM ORDER, like the result of any

@@ -27,6 +27,7 @@ OPT_LAUNCH_COUNT = 11
 OPT_UPLOAD_COPY_ENGINE = 12
 OPT_RETURN_EARLY = 13
 OPT_K2_FILL_SHARE = 14
+OPT_FUSED_PLAN = 15
 DBG_DENOM, DBG_ALPHA, DBG_BETA, DBG_LP, DBG_BAND, DBG_ROWMETA, DBG_LL, DBG_ROWSTART = range(1, 9)
 
 # every symbol include/mrnnt_c_api.h and include/rnnt_entrypoint.h declare

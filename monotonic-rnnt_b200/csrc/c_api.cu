@@ -282,6 +282,9 @@ RNNTStatus mrnnt_set_option(mrnnt_handle_t h, int option, int value) {
         case MRNNT_OPT_K2_FILL_SHARE:
             h->manager.engine().set_k2_fill_share(value);
             return RNNT_STATUS_SUCCESS;
+        case MRNNT_OPT_FUSED_PLAN:
+            h->manager.engine().set_fused_plan(value != 0);
+            return RNNT_STATUS_SUCCESS;
         default:
             return RNNT_STATUS_INVALID_VALUE;
     }

@@ -668,3 +668,58 @@ def test_owned_workspace_is_recycled_across_handles(gu):
     for old in keep:
         lib.mrnnt_free_workspace(old[0])
         lib.mrnnt_destroy(old[0])
+
+
+@pytest.mark.parametrize("shape", [
+    # name, B, V, T_range, S_range, aligned, max_shift
+    ("ragged_free", 9, 16, (5, 120), (1, 40), False, 0),
+    ("ragged_aligned", 9, 16, (5, 120), (1, 40), True, 2),
+    ("one_utterance_long", 1, 8, (700, 700), (90, 90), True, 5),
+    ("many_short", 300, 8, (3, 12), (0, 3), True, 1),
+    ("s_zero", 4, 8, (1, 6), (0, 0), False, 0),
+], ids=lambda s: s[0])
+def test_fused_plan_equals_the_three_kernels(gu, shape):
+    """MRNNT_OPT_FUSED_PLAN: row starts, band and row flags from ONE launch (plan.cuh: plan_fused_kernel) are the arrays
+    the three set-up kernels produce, bit for bit -- packed and padded, with and without an alignment band, after a
+    repeated restrict_to_alignment -- and so are the costs and gradients behind them."""
+    import monotonic_rnnt_b200 as mr
+    from monotonic_rnnt_b200 import _lib
+    name, B, V, tr, sr, aligned, shift = shape
+    case = fixtures.random_case("plan_" + name, 4000 + len(name), B=B, V=V, T_range=tr, S_range=sr, dist="uniform")
+    if aligned:
+        al = fixtures.random_alignment(np.random.default_rng(31), case.T, case.S, case.labels)
+        case = case.with_alignment(al, shift)
+    dev = torch.device("cuda", 0)
+    acts = torch.from_numpy(case.acts.reshape(case.rows, case.V)).to(dev)
+    out = {}
+    for fused in (0, 1):
+        h = mr.LossHandle(acts, torch.from_numpy(case.labels).to(dev), torch.from_numpy(case.T).to(dev),
+                          torch.from_numpy(case.S).to(dev))
+        h.set_option(_lib.OPT_FUSED_PLAN, fused)
+        if aligned:
+            ald = torch.from_numpy(case.alignment).to(dev)
+            h.restrict_to_alignment(ald, case.max_shift + 3, case.blank)     # (a first band, replaced before any call ...
+            h.restrict_to_alignment(ald, case.max_shift, case.blank)
+        g = torch.full_like(acts, float("nan"))
+        c = h.cost_and_grad(case.blank, g).clone()
+        if aligned:                                                            # ... and once more after a call)
+            h.restrict_to_alignment(ald, case.max_shift + 1, case.blank)
+            h.cost_and_grad(case.blank, torch.empty_like(acts))
+            h.restrict_to_alignment(ald, case.max_shift, case.blank)
+            g.fill_(float("nan"))
+            c2 = h.cost_and_grad(case.blank, g).clone()
+            assert torch.equal(c2, c)
+        torch.cuda.synchronize()
+        out[fused] = (h.debug(_lib.DBG_ROWSTART), h.debug(_lib.DBG_BAND), h.debug(_lib.DBG_ROWMETA), c, g.clone(),
+                      np.int64(h.get_option(_lib.OPT_LAUNCH_COUNT)))
+        h.close()
+    # the three kernels: 3 launches for the first plan, 2 (band, row flags) per later restrict_to_alignment; fused: 1 each
+    assert int(out[0][5]) - int(out[1][5]) == (4 if aligned else 2)
+    for a, b in zip(out[0][:5], out[1][:5]):
+        if isinstance(a, torch.Tensor):
+            assert torch.equal(a, b)
+        else:
+            assert np.array_equal(a, b)
+    o64 = _oracle(case, "f64_from_f32")
+    _check_costs(out[1][3].numpy(), o64.costs)
+    assert np.abs(out[1][4].cpu().numpy() - o64.grads).max() <= GRAD_ATOL
