@@ -171,12 +171,14 @@ struct CachedBlock {
     void *ptr = nullptr;
     size_t bytes = 0;
     int device = -1;
+    cudaEvent_t busy = nullptr;  // behind the last kernels that use the block (nullptr: nothing can still touch it); the
+                                 // cache owns the event, whoever takes the block orders its first launch behind it
 };
 static CachedBlock g_ws_cache[kWorkspaceCacheBlocks];
 static size_t g_ws_cache_limit = kWorkspaceCacheDefaultLimit;
 static std::mutex g_ws_cache_mutex;
 
-inline void *workspace_cache_take(size_t bytes, int device, size_t *got) {
+inline void *workspace_cache_take(size_t bytes, int device, size_t *got, cudaEvent_t *busy) {
     std::lock_guard<std::mutex> lock(g_ws_cache_mutex);
     int best = -1;
     for (int i = 0; i < kWorkspaceCacheBlocks; ++i) {
@@ -187,6 +189,7 @@ inline void *workspace_cache_take(size_t bytes, int device, size_t *got) {
     if (best < 0) return nullptr;
     void *p = g_ws_cache[best].ptr;
     *got = g_ws_cache[best].bytes;
+    *busy = g_ws_cache[best].busy;
     g_ws_cache[best] = CachedBlock();
     return p;
 }
@@ -198,14 +201,19 @@ inline void workspace_free_on(void *ptr, int device) {
     (void)cudaFree(ptr);
     if (cur != device && cur >= 0) (void)cudaSetDevice(cur);
 }
+inline void workspace_drop(const CachedBlock &c) {
+    workspace_free_on(c.ptr, c.device);  // (cudaFree waits for the device: whatever `busy` stands for is over then)
+    if (c.busy != nullptr) (void)cudaEventDestroy(c.busy);
+}
 // Keeps the block, or frees it (cache off, block above the byte limit); blocks the cache gives up for it are freed too.
-inline void workspace_cache_put(void *ptr, size_t bytes, int device) {
+// busy: see CachedBlock (ownership passes to the cache).
+inline void workspace_cache_put(void *ptr, size_t bytes, int device, cudaEvent_t busy = nullptr) {
     CachedBlock drop[kWorkspaceCacheBlocks + 1];
     int ndrop = 0;
     {
         std::lock_guard<std::mutex> lock(g_ws_cache_mutex);
         if (bytes > g_ws_cache_limit) {
-            drop[ndrop++] = CachedBlock{ptr, bytes, device};
+            drop[ndrop++] = CachedBlock{ptr, bytes, device, busy};
         } else {
             int slot = -1;
             for (int i = 0; i < kWorkspaceCacheBlocks && slot < 0; ++i)
@@ -216,7 +224,7 @@ inline void workspace_cache_put(void *ptr, size_t bytes, int device) {
                     if (g_ws_cache[i].bytes < g_ws_cache[slot].bytes) slot = i;
                 drop[ndrop++] = g_ws_cache[slot];
             }
-            g_ws_cache[slot] = CachedBlock{ptr, bytes, device};
+            g_ws_cache[slot] = CachedBlock{ptr, bytes, device, busy};
             // the byte limit: largest blocks first out
             for (;;) {
                 size_t total = 0;
@@ -232,7 +240,7 @@ inline void workspace_cache_put(void *ptr, size_t bytes, int device) {
             }
         }
     }
-    for (int i = 0; i < ndrop; ++i) workspace_free_on(drop[i].ptr, drop[i].device);
+    for (int i = 0; i < ndrop; ++i) workspace_drop(drop[i]);
 }
 inline void workspace_cache_trim() {
     CachedBlock drop[kWorkspaceCacheBlocks];
@@ -244,7 +252,7 @@ inline void workspace_cache_trim() {
         }
     }
     for (const CachedBlock &c : drop)
-        if (c.ptr != nullptr) workspace_free_on(c.ptr, c.device);
+        if (c.ptr != nullptr) workspace_drop(c);
 }
 inline void workspace_cache_set_limit(size_t bytes) {
     {
@@ -392,8 +400,11 @@ class Engine {
         int device = 0;
         if (cudaGetDevice(&device) != cudaSuccess) return RNNT_STATUS_EXECUTION_FAILED;
         size_t got = bytes;
-        void *p = workspace_cache_take(bytes, device, &got);
+        cudaEvent_t busy = nullptr;
+        void *p = workspace_cache_take(bytes, device, &got, &busy);
         if (p == nullptr && cudaMalloc(&p, bytes) != cudaSuccess) return RNNT_STATUS_MEMOPS_FAILED;
+        if (block_busy_ != nullptr) (void)cudaEventDestroy(block_busy_);
+        block_busy_ = busy;  // (the block's last user may still be running: setup() orders our first launch behind it)
         owned_ = p;
         owned_bytes_ = got;
         owned_device_ = device;
@@ -559,6 +570,8 @@ class Engine {
             const bool have_ev = inflight_ev_ != nullptr && cudaEventRecord(inflight_ev_, stream) == cudaSuccess;
             inflight_stream_ = stream;
             inflight_stream_set_ = have_ev;
+            if (have_ev) unrecorded_work_ = false;
+            stage_busy_ = peer_.world > 0;  // (the exchange writes its verdict into the staging buffer at K3's end)
             bool arrived = false;
             for (unsigned spins = 1; have_ev; ++spins) {
                 if (words[1] == stage_seq_) {
@@ -579,8 +592,9 @@ class Engine {
             } else if (cudaStreamSynchronize(stream) != cudaSuccess) {
                 st = RNNT_STATUS_EXECUTION_FAILED;
             }
-        } else if (st == RNNT_STATUS_SUCCESS && cudaStreamSynchronize(stream) != cudaSuccess) {
-            st = RNNT_STATUS_EXECUTION_FAILED;
+        } else if (st == RNNT_STATUS_SUCCESS) {
+            if (cudaStreamSynchronize(stream) != cudaSuccess) st = RNNT_STATUS_EXECUTION_FAILED;
+            else stage_busy_ = false;
         }
         if (st == RNNT_STATUS_SUCCESS && stage.host != nullptr) {
             std::memcpy(costs_host, stage.host, sizeof(float) * B_);
@@ -699,6 +713,7 @@ class Engine {
         if (!dev.ok) return RNNT_STATUS_EXECUTION_FAILED;
         if (grads_dev == nullptr || coef_blank_ < 0) return RNNT_STATUS_INVALID_VALUE;
         if (order_behind_inflight(stream) != RNNT_STATUS_SUCCESS) return RNNT_STATUS_EXECUTION_FAILED;
+        unrecorded_work_ = true;
         // who writes the plan's dead rows: the lattice kernel has (into this very buffer), or the gradient kernel's own
         // zero-fill warp will, or its consumer warps do
         zero_dst_ = grads_dev;
@@ -742,9 +757,12 @@ class Engine {
     ~Engine() {
         if (timing_)
             for (auto &e : ev_) cudaEventDestroy(e);
-        wait_inflight();
+        // (the gradient kernel of an early-return call may still be running: it has written all it ever writes into the
+        // staging buffer -- the costs, then the word we saw -- unless it carries a peer exchange)
+        if (stage_busy_) wait_inflight();
         release_owned();  // (mrnnt_destroy without mrnnt_free_workspace)
         if (inflight_ev_ != nullptr) cudaEventDestroy(inflight_ev_);
+        if (block_busy_ != nullptr) cudaEventDestroy(block_busy_);
         release_cost_stage(stage_);
     }
     // Returns when nothing an early-return call left behind is still running.
@@ -796,14 +814,29 @@ class Engine {
 
     // Hand the block create_workspace() allocated back (to the module's cache, or to the driver).  Like cudaFree it
     // returns only when nothing on the block's device can still touch it.
+    // When everything this handle has launched into the block lies in front of the event an early-return call has
+    // recorded (the usual case for a caller that makes one synchronous call per manager, like the reference's torch
+    // binding), the block goes back to the cache WITH that event and without a wait of the host: the next taker orders
+    // its first launch behind it (stream order, a no-op on the same stream).
     void release_owned() {
         if (owned_ == nullptr) return;
-        int cur = -1;
-        if (cudaGetDevice(&cur) != cudaSuccess) cur = -1;
-        if (cur != owned_device_) (void)cudaSetDevice(owned_device_);
-        (void)cudaDeviceSynchronize();
-        if (cur != owned_device_ && cur >= 0) (void)cudaSetDevice(cur);
-        workspace_cache_put(owned_, owned_bytes_, owned_device_);
+        cudaEvent_t busy = nullptr;
+        if (inflight_ev_ != nullptr && !unrecorded_work_ && block_busy_ == nullptr) {
+            busy = inflight_ev_;   // (ownership passes to the cache)
+            inflight_ev_ = nullptr;
+            inflight_stream_set_ = false;
+        } else {
+            int cur = -1;
+            if (cudaGetDevice(&cur) != cudaSuccess) cur = -1;
+            if (cur != owned_device_) (void)cudaSetDevice(owned_device_);
+            (void)cudaDeviceSynchronize();
+            if (cur != owned_device_ && cur >= 0) (void)cudaSetDevice(cur);
+        }
+        if (block_busy_ != nullptr) {  // (behind the device synchronisation above)
+            (void)cudaEventDestroy(block_busy_);
+            block_busy_ = nullptr;
+        }
+        workspace_cache_put(owned_, owned_bytes_, owned_device_, busy);
         if (base_ == owned_) base_ = nullptr;
         owned_ = nullptr;
     }
@@ -818,6 +851,13 @@ class Engine {
 
     RNNTStatus setup(cudaStream_t stream) {
         if (order_behind_inflight(stream) != RNNT_STATUS_SUCCESS) return RNNT_STATUS_EXECUTION_FAILED;
+        if (block_busy_ != nullptr) {  // the workspace block came out of the cache with its last user still running
+            const cudaError_t e = cudaStreamWaitEvent(stream, block_busy_, 0);
+            (void)cudaEventDestroy(block_busy_);
+            block_busy_ = nullptr;
+            if (e != cudaSuccess) return RNNT_STATUS_EXECUTION_FAILED;
+        }
+        unrecorded_work_ = true;  // (until an early-return call records its event behind everything)
         if ((plan_dirty_ || band_dirty_) && B_ <= kPlanFusedMaxB && fused_plan_) {
             // one launch for the whole plan (plan.cuh: plan_fused_kernel)
             size_t smem = alignment_ != nullptr ? (static_cast<size_t>(shape_.T_max) + 1) * sizeof(int) : 0;
@@ -1331,6 +1371,9 @@ class Engine {
     cudaEvent_t inflight_ev_ = nullptr;  // behind the last early-return call's kernels
     cudaStream_t inflight_stream_ = nullptr;
     bool inflight_stream_set_ = false;
+    bool unrecorded_work_ = false;   // something was enqueued that inflight_ev_ does not stand behind
+    bool stage_busy_ = false;        // the last early-return call's kernels may still write into the staging buffer
+    cudaEvent_t block_busy_ = nullptr;  // create_workspace(): the cached block's last user (see CachedBlock)
     int coef_blank_ = -1;  // blank label of the forward pass whose coefficients sit in the workspace (-1: none)
     bool timing_ = false;
     cudaEvent_t ev_[4] = {};

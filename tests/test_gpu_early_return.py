@@ -161,3 +161,59 @@ def test_peer_reduce_keeps_the_whole_wait_unless_asked(dev):
     h.set_peer_reduce(None, None)
     h.close()
     boards.close()
+
+
+def test_owned_workspace_goes_back_to_the_cache_while_the_gradient_kernel_runs(dev):
+    """create_workspace -> cost_and_grad (early return) -> free_workspace -> destroy, as the reference's torch binding does
+    it per call: free_workspace does not wait for the gradient kernel, the block goes back to the cache with the event
+    behind it, and the NEXT handle -- other inputs, ANOTHER stream -- that takes the block orders its kernels behind that
+    event.  Without the ordering the second handle's LSE kernel would overwrite the per-row records the first handle's
+    gradient kernel is still reading."""
+    import ctypes
+    from monotonic_rnnt_b200 import _lib
+    lib = _lib.load()
+    ca = fixtures.random_case("recycle_a", 71, B=32, V=1000, T_range=(150, 150), S_range=(40, 40), dist="uniform")
+    cb = fixtures.random_case("recycle_b", 72, B=32, V=1000, T_range=(150, 150), S_range=(40, 40), dist="normal3")
+    sa, sb = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def tensors(c):
+        return (torch.from_numpy(c.acts.reshape(c.rows, c.V)).to(dev), torch.from_numpy(c.labels).to(dev),
+                torch.from_numpy(c.T).to(dev), torch.from_numpy(c.S).to(dev))
+
+    ta, tb = tensors(ca), tensors(cb)
+
+    def one_call(c, t, stream, grads):
+        h = ctypes.c_void_p()
+        Th = np.ascontiguousarray(c.T, dtype=np.int32); Sh = np.ascontiguousarray(c.S, dtype=np.int32)
+        _lib.check(lib.mrnnt_create(ctypes.byref(h), t[0].data_ptr(), t[1].data_ptr(), c.B, t[2].data_ptr(), t[3].data_ptr(),
+                                    c.V, Th.ctypes.data, Sh.ctypes.data), "create")      # (host lengths: no blocking fetch)
+        _lib.check(lib.mrnnt_create_workspace(h), "create_workspace")
+        costs = torch.empty(c.B, dtype=torch.float32)
+        _lib.check(lib.mrnnt_cost_and_grad(h, c.blank, stream.cuda_stream, costs.data_ptr(), grads.data_ptr()), "call")
+        busy = not stream.query()
+        lib.mrnnt_free_workspace(h)
+        lib.mrnnt_destroy(h)
+        return costs, busy
+
+    torch.cuda.synchronize()
+    ga, gb = torch.empty_like(ta[0]), torch.empty_like(tb[0])
+    want_ca, _ = one_call(ca, ta, sa, ga)
+    torch.cuda.synchronize()
+    want_cb, _ = one_call(cb, tb, sb, gb)
+    torch.cuda.synchronize()
+    want_ga, want_gb = ga.clone(), gb.clone()
+    oa = oracle.run(ca.acts, ca.labels, ca.T, ca.S, ca.V, blank=ca.blank, precision="f64_from_f32")
+    np.testing.assert_allclose(want_ca.numpy(), oa.costs, rtol=1e-5)
+    assert np.abs(want_ga.cpu().numpy().reshape(-1) - oa.grads.reshape(-1)).max() <= 1e-5
+    ran_ahead = 0
+    for it in range(12):
+        ga.fill_(float("nan")); gb.fill_(float("nan"))
+        torch.cuda.synchronize()
+        c1, busy1 = one_call(ca, ta, sa, ga)          # returns while its gradient kernel runs; its block goes to the cache
+        c2, busy2 = one_call(cb, tb, sb, gb)          # takes that block, on another stream
+        ran_ahead += int(busy1)
+        torch.cuda.synchronize()
+        assert torch.equal(c1, want_ca) and torch.equal(c2, want_cb), it
+        assert torch.equal(ga, want_ga), it
+        assert torch.equal(gb, want_gb), it
+    assert ran_ahead >= 1      # (free_workspace really did not wait)
