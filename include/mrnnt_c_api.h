@@ -63,7 +63,7 @@ RNNTStatus mrnnt_create_workspace(mrnnt_handle_t h);
 void mrnnt_free_workspace(mrnnt_handle_t h);
 /* Blocks handed back by mrnnt_free_workspace / GpuRNNTWorkspaceManager::free_workspace are kept for the next
  * create_workspace of this library instead of going through cudaFree + cudaMalloc (the reference's torch binding
- * allocates and frees the workspace on every loss call: 2.9 ms against 0.36 ms on B=32 T=150 S=40 V=1000).  At most 4
+ * allocates and frees the workspace on every loss call: 2.9 ms against 0.34 ms on B=32 T=150 S=40 V=1000).  At most 4
  * blocks and `bytes` bytes are kept (default 1 GiB); 0 turns the cache off, free_workspace is then a cudaFree as in the
  * reference.  mrnnt_trim_workspace_cache returns everything that is cached to the driver now. */
 void mrnnt_set_workspace_cache_limit(size_t bytes);
@@ -91,11 +91,15 @@ RNNTStatus mrnnt_upload_acts(mrnnt_handle_t h, const void *host_acts, void *stre
 
 /* GpuRNNTComputer<float>::cost_and_grad / cost (reference include/gpu_rnnt.h:27-235) and therefore
  * compute_rnnt_loss (include/rnnt_entrypoint.h:24-25).  `stream` is a cudaStream_t / CUstream.
- * gradients == NULL selects cost only.  costs are valid on return (one stream synchronisation). */
+ * gradients == NULL selects cost only.  costs are valid on return; with gradients the call returns as soon as they
+ * are (MRNNT_OPT_RETURN_EARLY below): the gradients are complete in stream order. */
 RNNTStatus mrnnt_cost_and_grad(mrnnt_handle_t h, int blank_label, void *stream, float *costs_host, float *gradients);
 
 /* Same work, no host synchronisation: costs stay on the device (mrnnt_device_costs) for callers that
- * consume them there (e.g. an NCCL all-reduce of the summed cost on the same stream). */
+ * consume them there (e.g. an NCCL all-reduce of the summed cost on the same stream).
+ * Not for replay from a captured CUDA graph: every call carries host-side counters in its kernels' arguments (the
+ * lattice kernel's hand-over epoch, the alternating fill counters, the peer exchange's epoch), so a replayed launch
+ * would meet the words its first run left behind.  Launches are already off the critical path (dependent launches). */
 RNNTStatus mrnnt_enqueue(mrnnt_handle_t h, int blank_label, void *stream, float *gradients);
 const float *mrnnt_device_costs(mrnnt_handle_t h);
 
