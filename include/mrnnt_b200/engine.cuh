@@ -821,7 +821,7 @@ class Engine {
     void release_owned() {
         if (owned_ == nullptr) return;
         cudaEvent_t busy = nullptr;
-        if (inflight_ev_ != nullptr && !unrecorded_work_ && block_busy_ == nullptr) {
+        if (inflight_ev_ != nullptr && !unrecorded_work_ && block_busy_ == nullptr && !stage_busy_) {
             busy = inflight_ev_;   // (ownership passes to the cache)
             inflight_ev_ = nullptr;
             inflight_stream_set_ = false;
