@@ -284,3 +284,18 @@ def test_bench_cpu_sample_is_a_bounded_prefix(name):
         assert k == wl.B          # the headline shape is checked whole
     k1, rows_1, _, _ = bench._cpu_sample(wl, 1)
     assert k1 == 1 and rows_1 == int(wl.T[0]) * (int(wl.S[0]) + 1)
+
+
+def test_option_numbers_of_the_python_mirror_match_the_header():
+    """monotonic_rnnt_b200/_lib.py repeats the MRNNT_OPT_* / MRNNT_DBG_* numbers of include/mrnnt_c_api.h (ctypes cannot read a
+    header): every constant of the mirror must carry the header's value, and every option of the header must be there."""
+    import re
+    from monotonic_rnnt_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "mrnnt_c_api.h")).read()
+    header = {m.group(1): int(m.group(2)) for m in re.finditer(r"\bMRNNT_((?:OPT|DBG)_[A-Z0-9_]+)\s*=\s*(\d+)", text)}
+    assert len([k for k in header if k.startswith("OPT_")]) >= 15 and len([k for k in header if k.startswith("DBG_")]) >= 8
+    for name, value in header.items():
+        assert getattr(_lib, name, None) == value, name
+    for name in dir(_lib):
+        if name.startswith(("OPT_", "DBG_")):
+            assert header.get(name) == getattr(_lib, name), name
